@@ -1,0 +1,167 @@
+/* libsgmcmc_b200.so - C ABI of the B200-native SGMCMC hot path.
+ *
+ * The reference (jeremiecoullon/SGMCMCJax v0.2.13) is pure Python on JAX and has
+ * no FFI layer; the interface this library replaces is its closure API:
+ *
+ *   sgmcmcjax/samplers.py:27-60,98-136   build_*_sampler(...) -> sampler(key, Nsamples, params)
+ *   sgmcmcjax/kernels.py:17-124,130-601  build_*_kernel(...)  -> (init_fn, kernel, get_params)
+ *   sgmcmcjax/gradient_estimation.py:12-153  the three minibatch gradient estimators
+ *   sgmcmcjax/diffusions.py:47-347       the seven diffusion updates
+ *   sgmcmcjax/util.py:9-50               build_grad_log_post
+ *   sgmcmcjax/ksd.py:43-66               imq_KSD
+ *
+ * Conventions
+ *  - Every pointer documented as "device" is a CUDA device pointer on the
+ *    current device, BORROWED for the duration of the call (the model handle
+ *    additionally borrows nothing: sgmcmc_set_data copies into its own layout).
+ *  - `stream` is a cudaStream_t passed as void*; every call is stream-ordered
+ *    and returns without synchronising unless stated.
+ *  - Return value: 0 = OK, negative = error (see SGMCMC_E_*); the message of
+ *    the last error on the calling thread is returned by sgmcmc_last_error().
+ *  - A handle is not thread-safe; distinct handles are independent.
+ *  - All floating point is IEEE fp32, indices int32, PRNG words uint32
+ *    (jax 0.4.13 threefry2x32, non-partitionable layout).
+ */
+#ifndef SGMCMC_B200_H
+#define SGMCMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGMCMC_ABI_VERSION 1
+
+enum { SGMCMC_OK = 0, SGMCMC_E_INVALID = -1, SGMCMC_E_UNSUPPORTED = -2, SGMCMC_E_CUDA = -3,
+       SGMCMC_E_STATE = -4 };
+
+/* Registered model families (BASELINE.json north_star). */
+enum { SGMCMC_FAMILY_GAUSSIAN_MEAN = 0,   /* README.md:22-26, tests/models.py:6-24            */
+       SGMCMC_FAMILY_LOGREG = 1,          /* models/logistic_regression.py:65-72               */
+       SGMCMC_FAMILY_MLP = 2,             /* models/bayesian_NN/NN_model.py:31-58              */
+       SGMCMC_FAMILY_PMF = 3 };           /* SURVEY.md a15 (not in the reference)              */
+
+/* gradient_estimation.py:12-46 / :50-94 / :97-153 */
+enum { SGMCMC_EST_STANDARD = 0, SGMCMC_EST_CV = 1, SGMCMC_EST_SVRG = 2 };
+
+/* diffusions.py:47-347 */
+enum { SGMCMC_DIFF_SGLD = 0, SGMCMC_DIFF_PSGLD = 1, SGMCMC_DIFF_SGLDADAM = 2, SGMCMC_DIFF_SGHMC = 3,
+       SGMCMC_DIFF_BAOAB = 4, SGMCMC_DIFF_SGNHT = 5, SGMCMC_DIFF_BADODAB = 6 };
+
+#define SGMCMC_MAX_LEAVES 8
+
+typedef struct sgmcmc_config {
+  int32_t abi_version;        /* SGMCMC_ABI_VERSION */
+  int32_t family;             /* SGMCMC_FAMILY_*    */
+  int32_t estimator;          /* SGMCMC_EST_*       */
+  int32_t diffusion;          /* SGMCMC_DIFF_*      */
+  int64_t n_data;             /* rows of data[0] (util.py:41)                                   */
+  int32_t batch;              /* minibatch size; == n_data selects the static full-batch bypass
+                                 of the standard estimator (gradient_estimation.py:41-42)      */
+  int32_t n_leaves;           /* parameter pytree leaves, jax leaf order                        */
+  int32_t leaf_size[SGMCMC_MAX_LEAVES];   /* elements per leaf; P = sum                         */
+  int32_t data_dim;           /* columns of data[0]                                             */
+  int32_t leapfrog;           /* L of build_sghmc*_kernel (kernels.py:471-601); 0 otherwise     */
+  int32_t update_rate;        /* SVRG update_rate (gradient_estimation.py:134)                  */
+  int32_t flags;              /* SGMCMC_FLAG_*                                                  */
+  float lik_coef[SGMCMC_MAX_LEAVES];      /* gaussian_mean: a_l in  -a_l |x - theta_l|^2        */
+  float prior_coef[SGMCMC_MAX_LEAVES];    /* gaussian_mean: c_l in  -c_l |theta_l|^2 ;
+                                             logreg: prior_coef[0] = prior precision (0.1)      */
+  float hyper[4];             /* psgld {alpha, eps}; sgldAdam {beta1, beta2, eps};
+                                 sghmc {alpha}; sgnht {a}; badodab {a}                          */
+} sgmcmc_config;
+
+/* kernels.py:457-460: build_badodabCV_kernel binds both palindrome halves to badodab's
+ * update2.  With this flag the literal (buggy) wiring is reproduced. */
+#define SGMCMC_FLAG_BADODABCV_REFERENCE_BUG 1
+
+/* Per-chain sampler state, caller-owned device buffers, C = n_chains rows each
+ * (types.py:14-34: DiffusionState + param_grad + SVRGState; `key` is the carry of
+ * the lax.scan in samplers.py:47-57).  Unused members may be NULL. */
+typedef struct sgmcmc_state {
+  int32_t n_chains;
+  int32_t reserved;
+  float* theta;        /* [C, P]  x of every leaf, flattened in leaf order              */
+  float* aux1;         /* [C, P]  v (psgld/sghmc/baoab/sgnht/badodab) or m (sgldAdam)   */
+  float* aux2;         /* [C, P]  v of sgldAdam                                         */
+  float* alpha;        /* [C, n_leaves] thermostat scalar per leaf (sgnht/badodab)      */
+  float* grad;         /* [C, P]  carried param_grad (kernels.py:54,58)                 */
+  float* svrg_center;  /* [C, P]  SVRGState.centering_value                             */
+  float* svrg_grad;    /* [C, P]  SVRGState.fb_grad_center                              */
+  uint32_t* key;       /* [C, 2]  scan-carry key                                        */
+} sgmcmc_state;
+
+/* One entry per step i (or a single entry with stride 0 for a constant dt):
+ * h = fp32(dt(i)), hh = fp32(dt(i)/2), ca / cb = diffusion-specific coefficients
+ * evaluated by the host with the reference's weak-type rounding:
+ *   sgld     ca = sqrt(fp32(2 dt))
+ *   sgldAdam ca = 1 - beta1^(i+1), cb = 1 - beta2^(i+1)
+ *   sghmc    ca = sqrt(fp32(2 (alpha - beta) dt)), cb = sqrt(fp32(dt))      (resample)
+ *   baoab    ca = exp(fp32(-gamma dt)),  cb = fp32(tau) * sqrt(1 - ca^2)
+ *   sgnht    ca = sqrt(fp32(2 a dt)),    cb = sqrt(fp32(dt(0)))
+ *   badodab  ca = sqrt(fp32(dt))                                            (alpha == 0 branch) */
+typedef struct sgmcmc_step_coef { float h, hh, ca, cb; } sgmcmc_step_coef;
+
+typedef struct sgmcmc_handle sgmcmc_handle;
+
+const char* sgmcmc_last_error(void);
+int sgmcmc_abi_version(void);
+
+int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out);
+int sgmcmc_destroy(sgmcmc_handle* h);
+
+/* Ingest the data tuple (gradient_estimation.py:25-29).  x: device f32 [n_data, data_dim]
+ * row-major.  y: device, NULL for 1-tuples; logreg: int32 [n_data] in {0,1}.  The rows are
+ * re-laid-out into the handle's own HBM table (see DESIGN.md "data layout"). */
+int sgmcmc_set_data(sgmcmc_handle* h, const float* x, const void* y, void* stream);
+
+/* CV centring value (gradient_estimation.py:50-72): theta_hat device f32 [P]; the full-batch
+ * gradient at theta_hat is computed here (gradient_estimation.py:70). */
+int sgmcmc_set_centering(sgmcmc_handle* h, const float* theta_hat, void* stream);
+
+/* Full-batch grad_log_post (util.py:43-49 with all rows) at M parameter vectors:
+ * thetas device f32 [M, P] -> out device f32 [M, P]. */
+int sgmcmc_fullbatch_grad(sgmcmc_handle* h, const float* thetas, int32_t m, float* out, void* stream);
+
+/* init_fn(key, params) of kernels.py:48-51 for every chain: state->theta must hold params.
+ * keys: device u32 [C, 2].  sampler_mode != 0 additionally performs `key, subkey =
+ * split(key)` (samplers.py:53), uses subkey for init_gradient and stores the carry in
+ * state->key; sampler_mode == 0 uses keys[c] directly and leaves state->key alone. */
+int sgmcmc_init(sgmcmc_handle* h, sgmcmc_state* st, const uint32_t* keys, int32_t sampler_mode,
+                void* stream);
+
+/* K iterations of the scan body of samplers.py:47-51 for every chain, i = i0 .. i0+K-1.
+ * coef: device array of K entries (coef_stride 1) or one entry (coef_stride 0).
+ * samples: NULL, or device f32 with element (c, s, e) at samples[c * sample_chain_stride + s * P + e]
+ * (get_params after every iteration); sample_chain_stride == 0 means the dense [C, K, P]. */
+int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k,
+               const sgmcmc_step_coef* coef, int32_t coef_stride, float* samples,
+               int64_t sample_chain_stride, void* stream);
+
+/* kernel(i, key, state) of kernels.py:53-64 / :110-122 with caller-supplied per-chain keys
+ * (device u32 [C, 2]); state->key is not touched. */
+int sgmcmc_kernel_step(sgmcmc_handle* h, sgmcmc_state* st, int32_t i, const uint32_t* keys,
+                       const sgmcmc_step_coef* coef, void* stream);
+
+/* random.choice(key, arange(n), (batch,)) (gradient_estimation.py:32): key is a HOST
+ * pointer to 2 words, out a device int32 [batch].  Test hook for bit-exactness. */
+int sgmcmc_minibatch_indices(const uint32_t* key, int64_t n, int32_t batch, int32_t* out, void* stream);
+
+/* random.normal(key, (n,)) in fp32 (diffusions.py:67 etc.): key HOST pointer, out device f32 [n]. */
+int sgmcmc_normal(const uint32_t* key, int32_t n, float* out, void* stream);
+
+/* random.split(key, num): key HOST pointer, out device u32 [num, 2]. */
+int sgmcmc_split(const uint32_t* key, int32_t num, uint32_t* out, void* stream);
+
+/* Partial sum of the IMQ Stein kernel k_0 (ksd.py:7-37, c = 1, beta = -1/2) over the ordered
+ * pairs (i, j) with row0 <= i < row1 and 0 <= j < n.  x, g: device f32 [n, d] (samples,
+ * grads).  partial_sum: device double[1], overwritten.  imq_KSD = sqrt(sum over all row
+ * blocks) / n (ksd.py:65-66).  scratch may be NULL (allocated internally). */
+int sgmcmc_ksd_imq_partial(const float* x, const float* g, int32_t n, int32_t d, int32_t row0,
+                           int32_t row1, double* partial_sum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGMCMC_B200_H */

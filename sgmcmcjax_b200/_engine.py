@@ -1,0 +1,213 @@
+"""Host-side engine: owns a native model handle and drives the fused kernels.
+
+This is the single place where the Python API (samplers.py / kernels.py / gradient_estimation.py)
+meets the C ABI (include/sgmcmc_b200.h).  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _native, _tree
+from .diffusions import DIFFUSION_IDS, coef_is_constant, make_schedule, step_coefs
+from .models import resolve_family
+
+_EST = {"standard": _native.EST_STANDARD, "cv": _native.EST_CV, "svrg": _native.EST_SVRG}
+
+
+def _vp(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def to_device(a, dtype):
+    """numpy / torch / any __dlpack__ producer -> contiguous CUDA torch tensor of `dtype`."""
+    torch = _native.require_cuda()
+    if isinstance(a, torch.Tensor):
+        t = a
+    elif isinstance(a, np.ndarray) or np.isscalar(a) or isinstance(a, (list, tuple)):
+        arr = np.asarray(a)
+        if arr.dtype == np.uint32:
+            arr = arr.view(np.int32)
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+    elif hasattr(a, "__dlpack__"):
+        t = torch.from_dlpack(a)
+    else:
+        t = torch.as_tensor(np.asarray(a))
+    return t.to(device="cuda", dtype=dtype, non_blocking=True).contiguous()
+
+
+def keys_to_device(key):
+    """uint32[2] or uint32[C,2] (numpy / torch int32 view) -> CUDA int32 [C,2], and whether it was batched."""
+    torch = _native.require_cuda()
+    if isinstance(key, torch.Tensor):
+        t = key.to(device="cuda").contiguous()
+        if t.dtype != torch.int32:
+            t = t.to(torch.int64).to(torch.int32) if t.dtype not in (torch.uint32,) else t.view(torch.int32)
+    else:
+        arr = np.asarray(key)
+        arr = np.ascontiguousarray(arr.astype(np.uint32)).view(np.int32)
+        t = torch.from_numpy(arr).to("cuda")
+    batched = t.dim() == 2
+    return t.reshape(-1, 2).contiguous(), batched
+
+
+class Engine:
+    """One model (family + data + estimator + diffusion) bound to a native handle."""
+
+    def __init__(self, diffusion: str, dt, loglikelihood: Callable, logprior: Callable, data, batch_size: int,
+                 estimator: str = "standard", centering_value=None, update_rate: Optional[int] = None,
+                 leapfrog: int = 0, hyper: Optional[dict] = None, flags: int = 0):
+        torch = _native.require_cuda()
+        self.lib = _native.load()
+        if type(data) != tuple:                                   # gradient_estimation.py:25
+            raise AssertionError("data must be a tuple")
+        if len(data) not in (1, 2):                               # util.py:34-39
+            raise ValueError("'data' must be a tuple of size 1 or 2")
+        self.spec = resolve_family(loglikelihood, logprior)
+        if len(data) != self.spec.n_data_arrays:
+            raise ValueError(f"family {self.spec.name} expects a data tuple of {self.spec.n_data_arrays} arrays")
+        self.diffusion, self.estimator = diffusion, estimator
+        self.schedule = make_schedule(dt)
+        self.hp = dict(hyper or {})
+        self.leapfrog = int(leapfrog)
+        x = to_device(data[0], torch.float32)
+        if x.dim() != 2:
+            raise ValueError("data[0] must be [N, D]")
+        self.n_data, self.data_dim = int(x.shape[0]), int(x.shape[1])
+        y = to_device(data[1], torch.int32) if len(data) == 2 else None
+        if y is not None and y.shape[0] != self.n_data:
+            raise ValueError("data arrays must share their leading dimension")
+        self.batch = self.n_data if batch_size is None else int(batch_size)
+        n_leaves = max(len(self.spec.lik_coef), 1)
+        self.n_leaves, self.leaf_size = n_leaves, [self.data_dim] * n_leaves
+        self.P = sum(self.leaf_size)
+
+        cfg = _native.Config()
+        cfg.abi_version = _native.ABI_VERSION
+        cfg.family, cfg.estimator, cfg.diffusion = self.spec.family, _EST[estimator], DIFFUSION_IDS[diffusion]
+        cfg.n_data, cfg.batch, cfg.n_leaves, cfg.data_dim = self.n_data, self.batch, n_leaves, self.data_dim
+        for l, s in enumerate(self.leaf_size):
+            cfg.leaf_size[l] = s
+        cfg.leapfrog, cfg.update_rate, cfg.flags = self.leapfrog, int(update_rate or 0), int(flags)
+        for l, a in enumerate(self.spec.lik_coef):
+            cfg.lik_coef[l] = a
+        for l, c in enumerate(self.spec.prior_coef):
+            cfg.prior_coef[l] = c
+        order = {"psgld": ("alpha", "eps"), "sgldAdam": ("beta1", "beta2", "eps"), "sghmc": ("alpha",),
+                 "sgnht": ("a",), "badodab": ("a",)}.get(diffusion, ())
+        for k, name in enumerate(order):
+            cfg.hyper[k] = float(self.hp[name])
+        self._handle = C.c_void_p(0)
+        _native.check(self.lib.sgmcmc_create(C.byref(cfg), C.byref(self._handle)))
+        _native.check(self.lib.sgmcmc_set_data(self._handle, _vp(x), _vp(y), self._stream()))
+        if estimator == "cv":
+            center = self.flatten_params(centering_value, broadcast_chains=None)[0]
+            if center.shape[0] != 1:
+                raise ValueError("centering_value must be a single parameter pytree")
+            _native.check(self.lib.sgmcmc_set_centering(self._handle, _vp(center), self._stream()))
+        self._coef_cache = {}
+        torch.cuda.current_stream().synchronize()                 # inputs may be freed by the caller now
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) and self._handle.value:
+                self.lib.sgmcmc_destroy(self._handle)
+                self._handle = C.c_void_p(0)
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream():
+        import torch
+
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ---- parameter pytrees <-> flat [C, P] -------------------------------------------------
+    def flatten_params(self, params, broadcast_chains):
+        """-> (flat CUDA f32 [C, P], treedef, batched).  Leaves are [D] (one chain) or [C, D]."""
+        torch = _native.require_cuda()
+        leaves, treedef = _tree.flatten(params)
+        if len(leaves) != self.n_leaves:
+            raise TypeError(f"parameter pytree has {len(leaves)} leaves, the model expects {self.n_leaves}")
+        ts = [to_device(l, torch.float32) for l in leaves]
+        batched = ts[0].dim() == 2
+        ts = [t.reshape(-1, s) for t, s in zip(ts, self.leaf_size)]
+        flat = torch.cat(ts, dim=1).contiguous()
+        if broadcast_chains is not None and flat.shape[0] == 1 and broadcast_chains > 1:
+            flat = flat.expand(broadcast_chains, -1).contiguous()
+        return flat, treedef, batched
+
+    def unflatten_params(self, flat, treedef, lead_shape):
+        """flat [..., P] -> pytree with leaves [*lead_shape, D]."""
+        leaves, off = [], 0
+        for s in self.leaf_size:
+            leaves.append(flat[..., off:off + s].reshape(*lead_shape, s))
+            off += s
+        return _tree.unflatten(treedef, leaves)
+
+    # ---- state ------------------------------------------------------------------------------
+    def new_state(self, theta):
+        torch = _native.require_cuda()
+        c = theta.shape[0]
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device="cuda")
+        st = {"theta": theta.clone(), "grad": z(c, self.P), "key": torch.zeros(c, 2, dtype=torch.int32, device="cuda")}
+        if self.diffusion != "sgld":
+            st["aux1"] = z(c, self.P)
+        if self.diffusion == "sgldAdam":
+            st["aux2"] = z(c, self.P)
+        if self.diffusion in ("sgnht", "badodab"):
+            st["alpha"] = z(c, self.n_leaves)
+        if self.estimator == "svrg":
+            st["svrg_center"], st["svrg_grad"] = z(c, self.P), z(c, self.P)
+        return st
+
+    @staticmethod
+    def clone_state(st):
+        return {k: v.clone() for k, v in st.items()}
+
+    def _cstate(self, st):
+        s = _native.State()
+        s.n_chains = int(st["theta"].shape[0])
+        for name in ("theta", "aux1", "aux2", "alpha", "grad", "svrg_center", "svrg_grad", "key"):
+            t = st.get(name)
+            setattr(s, name, t.data_ptr() if t is not None else None)
+        return s
+
+    def _coefs(self, i0, k):
+        torch = _native.require_cuda()
+        if coef_is_constant(self.diffusion, self.schedule):
+            key = ("const",)
+            if key not in self._coef_cache:
+                self._coef_cache[key] = torch.from_numpy(
+                    step_coefs(self.diffusion, self.hp, self.schedule, 0, 1)).to("cuda")
+            return self._coef_cache[key], 0
+        return torch.from_numpy(step_coefs(self.diffusion, self.hp, self.schedule, i0, k)).to("cuda"), 1
+
+    # ---- native calls -----------------------------------------------------------------------
+    def init(self, st, keys, sampler_mode: bool):
+        cs = self._cstate(st)
+        _native.check(self.lib.sgmcmc_init(self._handle, C.byref(cs), _vp(keys), 1 if sampler_mode else 0,
+                                           self._stream()))
+
+    def run(self, st, i0: int, k: int, samples=None, sample_chain_stride: int = 0):
+        coef, stride = self._coefs(i0, k)
+        cs = self._cstate(st)
+        _native.check(self.lib.sgmcmc_run(self._handle, C.byref(cs), int(i0), int(k), _vp(coef), stride,
+                                          _vp(samples), int(sample_chain_stride), self._stream()))
+        return coef   # keep alive until the caller synchronises
+
+    def step(self, st, i: int, keys):
+        coef, _ = self._coefs(i, 1)
+        cs = self._cstate(st)
+        _native.check(self.lib.sgmcmc_kernel_step(self._handle, C.byref(cs), int(i), _vp(keys), _vp(coef),
+                                                  self._stream()))
+        return coef
+
+    def fullbatch_grad(self, thetas):
+        torch = _native.require_cuda()
+        out = torch.empty_like(thetas)
+        _native.check(self.lib.sgmcmc_fullbatch_grad(self._handle, _vp(thetas), int(thetas.shape[0]), _vp(out),
+                                                     self._stream()))
+        return out

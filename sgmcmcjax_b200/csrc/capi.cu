@@ -1,0 +1,393 @@
+// C-ABI entry points of libsgmcmc_b200.so (see include/sgmcmc_b200.h).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ksd.cuh"
+#include "vec_sampler.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(SGMCMC_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));         \
+  } while (0)
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct sgmcmc_handle {
+  sgmcmc_config cfg;
+  sg::VecModel vm;
+  int P = 0, DS = 0, nch = 1;
+  float* rows = nullptr;       // owned: [n_data][DS]
+  float* cv_center = nullptr;  // owned: [P]
+  float* cv_grad = nullptr;    // owned: [P]
+  float* partial = nullptr;    // owned scratch for sgmcmc_fullbatch_grad
+  size_t partial_elems = 0;
+  int num_sms = 148;
+  bool has_data = false, has_center = false;
+};
+
+namespace sg {
+
+// x[n][D] (+ y[n]) -> rows[n][DS]; logreg folds the label into the sign: (1 - 2y) x.
+__global__ void pack_rows_kernel(const float* __restrict__ x, const int* __restrict__ y, float* __restrict__ rows,
+                                 size_t n, int D, int DS, int family) {
+  const size_t total = n * (size_t)DS;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = t / DS;
+    const int d = (int)(t - r * DS);
+    float v = 0.f;
+    if (d < D) {
+      v = x[r * D + d];
+      if (family == SGMCMC_FAMILY_LOGREG && y[r] != 0) v = -v;
+    }
+    rows[t] = v;
+  }
+}
+
+// K2 stage 1: CTA (split, m) sums its row range at thetas[m] into partial[m][split][DS].
+template <int FAMILY, int NCH>
+__global__ void __launch_bounds__(1024 / NCH) fullgrad_partial_kernel(const VecModel m, const float* __restrict__ thetas,
+                                                                      float* __restrict__ partial, unsigned rows_per_split) {
+  extern __shared__ __align__(16) float smem_raw[];
+  const int W = blockDim.x >> 5;
+  float* s_theta = smem_raw;
+  float* s_part = smem_raw + m.DS;
+  const int mi = blockIdx.y, split = blockIdx.x;
+  for (int e = threadIdx.x; e < m.DS; e += blockDim.x) s_theta[e] = e < m.P ? thetas[(size_t)mi * m.P + e] : 0.f;
+  __syncthreads();
+  const unsigned lo = split * rows_per_split;
+  const unsigned hi = min(m.n_data, lo + rows_per_split);
+  RandintPlan dummy{};
+  row_pass<FAMILY, false, NCH>(m, true, dummy, lo, hi > lo ? hi - lo : 0u, s_theta, s_theta, s_part);
+  __syncthreads();
+  float* dst = partial + ((size_t)mi * gridDim.x + split) * m.DS;
+  for (int d = threadIdx.x; d < m.DS; d += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < W; ++w) t += s_part[w * m.DS + d];
+    dst[d] = t;
+  }
+}
+
+// K2 stage 2: fixed-order fold over splits + prior / scaling (util.py:43-44 with all rows).
+template <int FAMILY>
+__global__ void fullgrad_finish_kernel(const VecModel m, const float* __restrict__ thetas, const float* __restrict__ partial,
+                                       int splits, float* __restrict__ out) {
+  const int mi = blockIdx.x;
+  for (int e = threadIdx.x; e < m.P; e += blockDim.x) {
+    const int leaf = e / m.leaf_dim, d = e - leaf * m.leaf_dim;
+    float S = 0.f;
+    for (int sp = 0; sp < splits; ++sp) S += partial[((size_t)mi * splits + sp) * m.DS + d];
+    out[(size_t)mi * m.P + e] = grad_from_sum<FAMILY>(m, leaf, d, S, thetas[(size_t)mi * m.P + e], 1.0f, (float)m.n_data);
+  }
+}
+
+__global__ void indices_kernel(Key key, unsigned n, unsigned batch, int* out) {
+  const RandintPlan plan = randint_plan(key, n, batch);
+  const unsigned h = (batch + 1u) >> 1;
+  for (unsigned b = blockIdx.x * blockDim.x + threadIdx.x; b < h; b += gridDim.x * blockDim.x) {
+    unsigned i0, i1;
+    randint_block(plan, b, i0, i1);
+    out[b] = (int)i0;
+    if (b + h < batch) out[b + h] = (int)i1;
+  }
+}
+
+__global__ void normal_kernel(Key key, unsigned n, float* out) {
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) out[e] = normal_at(key, e, n);
+}
+
+__global__ void split_kernel(Key key, unsigned num, uint32_t* out) {
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < 2u * num; e += gridDim.x * blockDim.x)
+    out[e] = stream_word(key, e, 2u * num);
+}
+
+}  // namespace sg
+
+namespace {
+
+template <int FAMILY, bool CV, int NCH>
+int launch_vec(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
+  auto kern = sg::vec_sampler_kernel<FAMILY, CV, NCH>;
+  const int PP = ((h->P > h->DS ? h->P : h->DS) + 3) & ~3;
+  const size_t smem = sg::vec_smem_bytes(PP, h->DS, warps);
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<run.st.n_chains, warps * 32, smem, stream>>>(h->vm, run);
+  CUDA_TRY(cudaGetLastError());
+  return SGMCMC_OK;
+}
+
+template <int FAMILY, bool CV>
+int launch_vec_nch(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
+  switch (h->nch) {
+    case 1: return launch_vec<FAMILY, CV, 1>(h, run, warps, stream);
+    case 2: return launch_vec<FAMILY, CV, 2>(h, run, warps, stream);
+    case 4: return launch_vec<FAMILY, CV, 4>(h, run, warps, stream);
+  }
+  return fail(SGMCMC_E_UNSUPPORTED, "data_dim > 512 is not supported by the vector-family sampler");
+}
+
+int choose_warps(const sgmcmc_handle* h, int n_chains) {
+  const int max_warps = 32 / h->nch;
+  int w = env_int("SGMCMC_WARPS_PER_CHAIN", 0);
+  if (w <= 0) {
+    // fill the machine: ~32 resident warps on each of the SMs
+    const long target = (long)h->num_sms * 32 / (n_chains > 0 ? n_chains : 1);
+    w = 4;
+    while (w * 2 <= target && w * 2 <= max_warps) w *= 2;
+  }
+  if (w > max_warps) w = max_warps;
+  if (w < 1) w = 1;
+  return w;
+}
+
+int dispatch_vec(const sgmcmc_handle* h, const sg::VecRun& run, cudaStream_t stream) {
+  const int warps = choose_warps(h, run.st.n_chains);
+  const bool cv = h->cfg.estimator != SGMCMC_EST_STANDARD;
+  if (h->cfg.family == SGMCMC_FAMILY_GAUSSIAN_MEAN)
+    return cv ? launch_vec_nch<SGMCMC_FAMILY_GAUSSIAN_MEAN, true>(h, run, warps, stream)
+              : launch_vec_nch<SGMCMC_FAMILY_GAUSSIAN_MEAN, false>(h, run, warps, stream);
+  if (h->cfg.family == SGMCMC_FAMILY_LOGREG)
+    return cv ? launch_vec_nch<SGMCMC_FAMILY_LOGREG, true>(h, run, warps, stream)
+              : launch_vec_nch<SGMCMC_FAMILY_LOGREG, false>(h, run, warps, stream);
+  return fail(SGMCMC_E_UNSUPPORTED, "family not implemented by this build");
+}
+
+int check_state(const sgmcmc_handle* h, const sgmcmc_state* st) {
+  if (!h || !st) return fail(SGMCMC_E_INVALID, "null handle or state");
+  if (!h->has_data) return fail(SGMCMC_E_STATE, "sgmcmc_set_data has not been called");
+  if (st->n_chains <= 0) return fail(SGMCMC_E_INVALID, "n_chains must be positive");
+  if (!st->theta || !st->grad) return fail(SGMCMC_E_INVALID, "state.theta and state.grad are required");
+  const int d = h->cfg.diffusion;
+  if (d != SGMCMC_DIFF_SGLD && !st->aux1) return fail(SGMCMC_E_INVALID, "state.aux1 is required by this diffusion");
+  if (d == SGMCMC_DIFF_SGLDADAM && !st->aux2) return fail(SGMCMC_E_INVALID, "state.aux2 is required by sgldAdam");
+  if ((d == SGMCMC_DIFF_SGNHT || d == SGMCMC_DIFF_BADODAB) && !st->alpha)
+    return fail(SGMCMC_E_INVALID, "state.alpha is required by sgnht / badodab");
+  if (h->cfg.estimator == SGMCMC_EST_SVRG && (!st->svrg_center || !st->svrg_grad))
+    return fail(SGMCMC_E_INVALID, "state.svrg_center / svrg_grad are required by the SVRG estimator");
+  if (h->cfg.estimator == SGMCMC_EST_CV && !h->has_center)
+    return fail(SGMCMC_E_STATE, "sgmcmc_set_centering has not been called");
+  return SGMCMC_OK;
+}
+
+template <int FAMILY>
+int fullgrad_impl(sgmcmc_handle* h, const float* thetas, int m, float* out, cudaStream_t stream) {
+  const int warps = 8 / (h->nch > 2 ? 2 : 1);
+  int splits = (h->num_sms * 4 + m - 1) / m;
+  const unsigned min_rows = 512;
+  const unsigned max_splits = (h->vm.n_data + min_rows - 1) / min_rows;
+  if ((unsigned)splits > max_splits) splits = (int)max_splits;
+  if (splits < 1) splits = 1;
+  const unsigned rows_per_split = (h->vm.n_data + splits - 1) / splits;
+  const size_t need = (size_t)m * splits * h->DS;
+  if (need > h->partial_elems) {
+    if (h->partial) CUDA_TRY(cudaFree(h->partial));
+    h->partial = nullptr; h->partial_elems = 0;
+    CUDA_TRY(cudaMalloc(&h->partial, need * sizeof(float)));
+    h->partial_elems = need;
+  }
+  const size_t smem = sizeof(float) * (size_t)(h->DS + warps * h->DS);
+  dim3 grid(splits, m);
+  switch (h->nch) {
+    case 1: sg::fullgrad_partial_kernel<FAMILY, 1><<<grid, warps * 32, smem, stream>>>(h->vm, thetas, h->partial, rows_per_split); break;
+    case 2: sg::fullgrad_partial_kernel<FAMILY, 2><<<grid, warps * 32, smem, stream>>>(h->vm, thetas, h->partial, rows_per_split); break;
+    case 4: sg::fullgrad_partial_kernel<FAMILY, 4><<<grid, warps * 32, smem, stream>>>(h->vm, thetas, h->partial, rows_per_split); break;
+    default: return fail(SGMCMC_E_UNSUPPORTED, "data_dim > 512 is not supported");
+  }
+  CUDA_TRY(cudaGetLastError());
+  sg::fullgrad_finish_kernel<FAMILY><<<m, 128, 0, stream>>>(h->vm, thetas, h->partial, splits, out);
+  CUDA_TRY(cudaGetLastError());
+  return SGMCMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sgmcmc_last_error(void) { return g_err.c_str(); }
+int sgmcmc_abi_version(void) { return SGMCMC_ABI_VERSION; }
+
+int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
+  if (!cfg || !out) return fail(SGMCMC_E_INVALID, "null argument");
+  if (cfg->abi_version != SGMCMC_ABI_VERSION) return fail(SGMCMC_E_INVALID, "ABI version mismatch");
+  if (cfg->family != SGMCMC_FAMILY_GAUSSIAN_MEAN && cfg->family != SGMCMC_FAMILY_LOGREG)
+    return fail(SGMCMC_E_UNSUPPORTED, "family not implemented by this build (gaussian_mean, logreg)");
+  if (cfg->estimator < 0 || cfg->estimator > SGMCMC_EST_SVRG) return fail(SGMCMC_E_INVALID, "bad estimator");
+  if (cfg->diffusion < 0 || cfg->diffusion > SGMCMC_DIFF_BADODAB) return fail(SGMCMC_E_INVALID, "bad diffusion");
+  if (cfg->n_data <= 0 || cfg->n_data > 0x7fffffffLL) return fail(SGMCMC_E_INVALID, "n_data out of range");
+  if (cfg->batch <= 0) return fail(SGMCMC_E_INVALID, "batch must be positive");
+  if (cfg->n_leaves < 1 || cfg->n_leaves > SGMCMC_MAX_LEAVES) return fail(SGMCMC_E_INVALID, "n_leaves out of range");
+  if (cfg->data_dim < 1) return fail(SGMCMC_E_INVALID, "data_dim must be positive");
+  for (int l = 0; l < cfg->n_leaves; ++l)
+    if (cfg->leaf_size[l] != cfg->data_dim)
+      return fail(SGMCMC_E_INVALID, "vector families need every leaf to have data_dim elements");
+  if (cfg->family == SGMCMC_FAMILY_LOGREG && cfg->n_leaves != 1) return fail(SGMCMC_E_INVALID, "logreg has one leaf");
+  if (cfg->diffusion == SGMCMC_DIFF_SGHMC && cfg->leapfrog < 1) return fail(SGMCMC_E_INVALID, "sghmc needs leapfrog >= 1");
+  if (cfg->estimator == SGMCMC_EST_SVRG && cfg->update_rate < 1) return fail(SGMCMC_E_INVALID, "SVRG needs update_rate >= 1");
+
+  sgmcmc_handle* h = new sgmcmc_handle();
+  h->cfg = *cfg;
+  h->DS = (cfg->data_dim + 3) & ~3;
+  h->P = cfg->n_leaves * cfg->data_dim;
+  const int f4 = h->DS / 4;
+  h->nch = f4 <= 32 ? 1 : f4 <= 64 ? 2 : f4 <= 128 ? 4 : 8;
+  if (h->nch > 4) { delete h; return fail(SGMCMC_E_UNSUPPORTED, "data_dim > 512 is not supported by the vector-family sampler"); }
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) h->num_sms = sms;
+  }
+  sg::VecModel& vm = h->vm;
+  std::memset(&vm, 0, sizeof(vm));
+  vm.family = cfg->family; vm.estimator = cfg->estimator; vm.diffusion = cfg->diffusion; vm.flags = cfg->flags;
+  vm.n_leaves = cfg->n_leaves; vm.leaf_dim = cfg->data_dim; vm.P = h->P; vm.DS = h->DS;
+  vm.n_data = (unsigned)cfg->n_data; vm.batch = (unsigned)cfg->batch;
+  vm.full_batch = (cfg->estimator == SGMCMC_EST_STANDARD && (int64_t)cfg->batch == cfg->n_data) ? 1 : 0;
+  vm.leapfrog = cfg->leapfrog; vm.update_rate = cfg->update_rate;
+  vm.scale = (float)cfg->n_data / (float)cfg->batch;
+  for (int l = 0; l < SGMCMC_MAX_LEAVES; ++l) {
+    vm.lik2[l] = 2.0f * cfg->lik_coef[l];
+    vm.prior2[l] = cfg->family == SGMCMC_FAMILY_GAUSSIAN_MEAN ? 2.0f * cfg->prior_coef[l] : cfg->prior_coef[l];
+  }
+  for (int k = 0; k < 4; ++k) vm.hyper[k] = cfg->hyper[k];
+  *out = h;
+  return SGMCMC_OK;
+}
+
+int sgmcmc_destroy(sgmcmc_handle* h) {
+  if (!h) return SGMCMC_OK;
+  if (h->rows) cudaFree(h->rows);
+  if (h->cv_center) cudaFree(h->cv_center);
+  if (h->cv_grad) cudaFree(h->cv_grad);
+  if (h->partial) cudaFree(h->partial);
+  delete h;
+  return SGMCMC_OK;
+}
+
+int sgmcmc_set_data(sgmcmc_handle* h, const float* x, const void* y, void* stream) {
+  if (!h || !x) return fail(SGMCMC_E_INVALID, "null argument");
+  if (h->cfg.family == SGMCMC_FAMILY_LOGREG && !y) return fail(SGMCMC_E_INVALID, "logreg needs the label array");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)h->cfg.n_data;
+  if (!h->rows) CUDA_TRY(cudaMalloc(&h->rows, n * h->DS * sizeof(float)));
+  const size_t total = n * h->DS;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 16);
+  sg::pack_rows_kernel<<<blocks, 256, 0, s>>>(x, (const int*)y, h->rows, n, h->cfg.data_dim, h->DS, h->cfg.family);
+  CUDA_TRY(cudaGetLastError());
+  h->vm.rows = h->rows;
+  h->has_data = true;
+  return SGMCMC_OK;
+}
+
+int sgmcmc_fullbatch_grad(sgmcmc_handle* h, const float* thetas, int32_t m, float* out, void* stream) {
+  if (!h || !thetas || !out || m < 1) return fail(SGMCMC_E_INVALID, "bad argument");
+  if (!h->has_data) return fail(SGMCMC_E_STATE, "sgmcmc_set_data has not been called");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->cfg.family == SGMCMC_FAMILY_GAUSSIAN_MEAN) return fullgrad_impl<SGMCMC_FAMILY_GAUSSIAN_MEAN>(h, thetas, m, out, s);
+  return fullgrad_impl<SGMCMC_FAMILY_LOGREG>(h, thetas, m, out, s);
+}
+
+int sgmcmc_set_centering(sgmcmc_handle* h, const float* theta_hat, void* stream) {
+  if (!h || !theta_hat) return fail(SGMCMC_E_INVALID, "null argument");
+  if (!h->has_data) return fail(SGMCMC_E_STATE, "sgmcmc_set_data has not been called");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->cv_center) CUDA_TRY(cudaMalloc(&h->cv_center, h->P * sizeof(float)));
+  if (!h->cv_grad) CUDA_TRY(cudaMalloc(&h->cv_grad, h->P * sizeof(float)));
+  CUDA_TRY(cudaMemcpyAsync(h->cv_center, theta_hat, h->P * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  const int rc = sgmcmc_fullbatch_grad(h, h->cv_center, 1, h->cv_grad, stream);   // gradient_estimation.py:70
+  if (rc != SGMCMC_OK) return rc;
+  h->vm.cv_center = h->cv_center;
+  h->vm.cv_grad = h->cv_grad;
+  h->has_center = true;
+  return SGMCMC_OK;
+}
+
+int sgmcmc_init(sgmcmc_handle* h, sgmcmc_state* st, const uint32_t* keys, int32_t sampler_mode, void* stream) {
+  int rc = check_state(h, st);
+  if (rc != SGMCMC_OK) return rc;
+  if (!keys) return fail(SGMCMC_E_INVALID, "keys must not be null");
+  if (sampler_mode && !st->key) return fail(SGMCMC_E_INVALID, "state.key is required in sampler mode");
+  sg::VecRun run{};
+  run.st = *st; run.mode = sampler_mode ? 2 : 1; run.init_keys = keys;
+  return dispatch_vec(h, run, (cudaStream_t)stream);
+}
+
+int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const sgmcmc_step_coef* coef,
+               int32_t coef_stride, float* samples, int64_t sample_chain_stride, void* stream) {
+  int rc = check_state(h, st);
+  if (rc != SGMCMC_OK) return rc;
+  if (k < 0 || i0 < 0) return fail(SGMCMC_E_INVALID, "i0 and k must be non-negative");
+  if (!coef || (coef_stride != 0 && coef_stride != 1)) return fail(SGMCMC_E_INVALID, "bad step coefficients");
+  if (!st->key) return fail(SGMCMC_E_INVALID, "state.key is required");
+  if (k == 0) return SGMCMC_OK;
+  sg::VecRun run{};
+  run.st = *st; run.i0 = i0; run.K = k; run.coef = coef; run.coef_stride = coef_stride; run.samples = samples;
+  run.sample_chain_stride = sample_chain_stride > 0 ? (size_t)sample_chain_stride : (size_t)k * h->P;
+  return dispatch_vec(h, run, (cudaStream_t)stream);
+}
+
+int sgmcmc_kernel_step(sgmcmc_handle* h, sgmcmc_state* st, int32_t i, const uint32_t* keys,
+                       const sgmcmc_step_coef* coef, void* stream) {
+  int rc = check_state(h, st);
+  if (rc != SGMCMC_OK) return rc;
+  if (!keys || !coef || i < 0) return fail(SGMCMC_E_INVALID, "bad argument");
+  sg::VecRun run{};
+  run.st = *st; run.i0 = i; run.K = 1; run.coef = coef; run.coef_stride = 0; run.step_keys = keys;
+  return dispatch_vec(h, run, (cudaStream_t)stream);
+}
+
+int sgmcmc_minibatch_indices(const uint32_t* key, int64_t n, int32_t batch, int32_t* out, void* stream) {
+  if (!key || !out || n <= 0 || n > 0x7fffffffLL || batch <= 0) return fail(SGMCMC_E_INVALID, "bad argument");
+  sg::Key k{key[0], key[1]};
+  const unsigned h = ((unsigned)batch + 1u) >> 1;
+  sg::indices_kernel<<<(h + 255) / 256, 256, 0, (cudaStream_t)stream>>>(k, (unsigned)n, (unsigned)batch, out);
+  CUDA_TRY(cudaGetLastError());
+  return SGMCMC_OK;
+}
+
+int sgmcmc_normal(const uint32_t* key, int32_t n, float* out, void* stream) {
+  if (!key || !out || n <= 0) return fail(SGMCMC_E_INVALID, "bad argument");
+  sg::Key k{key[0], key[1]};
+  const int blocks = std::min((n + 255) / 256, 148 * 8);
+  sg::normal_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(k, (unsigned)n, out);
+  CUDA_TRY(cudaGetLastError());
+  return SGMCMC_OK;
+}
+
+int sgmcmc_split(const uint32_t* key, int32_t num, uint32_t* out, void* stream) {
+  if (!key || !out || num <= 0) return fail(SGMCMC_E_INVALID, "bad argument");
+  sg::Key k{key[0], key[1]};
+  const int blocks = std::min((2 * num + 255) / 256, 148 * 8);
+  sg::split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(k, (unsigned)num, out);
+  CUDA_TRY(cudaGetLastError());
+  return SGMCMC_OK;
+}
+
+int sgmcmc_ksd_imq_partial(const float* x, const float* g, int32_t n, int32_t d, int32_t row0, int32_t row1,
+                           double* partial_sum, void* stream) {
+  if (!x || !g || !partial_sum || n <= 0 || d <= 0 || row0 < 0 || row1 > n || row0 > row1)
+    return fail(SGMCMC_E_INVALID, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(partial_sum, 0, sizeof(double), s));
+  if (row1 == row0) return SGMCMC_OK;
+  dim3 grid((n + sg::KSD_T - 1) / sg::KSD_T, (row1 - row0 + sg::KSD_T - 1) / sg::KSD_T);
+  sg::ksd_simt_kernel<<<grid, 256, 0, s>>>(x, g, n, d, row0, row1, partial_sum);
+  CUDA_TRY(cudaGetLastError());
+  return SGMCMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,536 @@
+// K1: fused persistent sampler for vector-parameter families (gaussian_mean, logreg).
+//
+// One CTA owns one chain for all K steps of a launch; theta, the diffusion's auxiliary
+// arrays, the carried gradient and the CV / SVRG centre live in shared memory.  Each step
+// fuses, with no HBM round trip in between:
+//   key tree          samplers.py:47-51, kernels.py:53-64,110-122, diffusion_util.py:66,91,112
+//   diffusion update  diffusions.py:47-347 (in-register Gaussian noise, XLA erf_inv polynomial)
+//   index draw        gradient_estimation.py:32,75,140 (threefry randint, bit-exact)
+//   row gather        gradient_estimation.py:33,76,141 (warp-per-row float4 loads from HBM)
+//   per-example grad  util.py:43-49 for the registered family, reduced with warp shuffles
+//   CV / SVRG         gradient_estimation.py:72-85,134-151
+//
+// HBM data layout ("rows"): [n_data][DS] fp32, DS = D rounded up to 4.  gaussian_mean stores
+// x; logreg stores x~ = (1 - 2y) x, i.e. the label is folded into the sign of the row, which
+// is exactly the argument of the reference's loglik  -logsumexp([0, (1-2y) theta.x])
+// (models/logistic_regression.py:65-67): d loglik / d theta = -sigmoid(theta.x~) x~.
+#pragma once
+#include "prng.cuh"
+#include "../../include/sgmcmc_b200.h"
+
+namespace sg {
+
+constexpr int MAXL = SGMCMC_MAX_LEAVES;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct VecModel {
+  int family, estimator, diffusion, flags;
+  int n_leaves, leaf_dim, P, DS;
+  unsigned n_data, batch;
+  int full_batch;          // standard estimator with batch == n_data (gradient_estimation.py:41-42)
+  int leapfrog, update_rate;
+  float scale;             // fp32(n_data) / fp32(batch)   (util.py:44, mean then * Ndata)
+  float lik2[MAXL];        // gaussian_mean: 2 a_l
+  float prior2[MAXL];      // gaussian_mean: 2 c_l ; logreg: [0] = prior precision
+  float hyper[4];
+  const float* rows;       // [n_data][DS]
+  const float* cv_center;  // [P]  (CV only)
+  const float* cv_grad;    // [P]  full-batch gradient at cv_center
+};
+
+struct VecRun {
+  sgmcmc_state st;
+  int i0, K;
+  const sgmcmc_step_coef* coef;
+  int coef_stride;
+  float* samples;            // element (c, s, e) at samples[c * sample_chain_stride + s * P + e], or nullptr
+  size_t sample_chain_stride;
+  const uint32_t* step_keys; // [C][2]: kernel(i, key, state) mode (K == 1), else nullptr
+  int mode;                  // 0 = run, 1 = init_fn with keys as given, 2 = init with sampler split
+  const uint32_t* init_keys; // [C][2] for mode 1/2
+};
+
+// ---------------------------------------------------------------------------------------
+// shared-memory carve-up (dynamic): all arrays padded to DSP = max(P, DS) rounded to 4
+struct Smem {
+  float *theta, *aux1, *aux2, *grad, *center, *fb, *S, *part;
+  float* alpha;       // [MAXL]
+  float* red;         // [32] block-reduction scratch
+  uint32_t* keys;     // [2 * (4 + 2*MAXL)] step keys
+};
+
+__device__ __forceinline__ Smem carve(float* base, int PP, int DS, int W) {
+  Smem s;
+  s.theta = base;            base += PP;
+  s.aux1 = base;             base += PP;
+  s.aux2 = base;             base += PP;
+  s.grad = base;             base += PP;
+  s.center = base;           base += PP;
+  s.fb = base;               base += PP;
+  s.S = base;                base += DS;
+  s.part = base;             base += W * DS;
+  s.alpha = base;            base += MAXL;
+  s.red = base;              base += 32;
+  s.keys = reinterpret_cast<uint32_t*>(base);
+  return s;
+}
+constexpr int SMEM_KEY_WORDS = 2 * (4 + 2 * MAXL);
+__host__ __device__ inline size_t vec_smem_bytes(int PP, int DS, int W) {
+  return sizeof(float) * (size_t)(6 * PP + DS + W * DS + MAXL + 32) + sizeof(uint32_t) * SMEM_KEY_WORDS;
+}
+
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f(float z) {
+  // stable logistic; expf (not __expf): per-row relative error must stay ~1e-7
+  const float e = expf(-fabsf(z));
+  const float s = 1.0f / (1.0f + e);
+  return z >= 0.0f ? s : e * s;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ void axpy4(float4& acc, float w, const float4& x) {
+  acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y);
+  acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
+}
+
+// Sum 8 per-lane values across the warp with 9 shuffles.  On return every lane of quad
+// {4u .. 4u+3} holds the warp-wide total of p[u].
+__device__ __forceinline__ float reduce8(const float (&p)[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float q[4], r[2], s;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float send = b4 ? p[k] : p[k + 4];
+    const float keep = b4 ? p[k + 4] : p[k];
+    q[k] = keep + __shfl_xor_sync(FULL, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = b3 ? q[k] : q[k + 2];
+    const float keep = b3 ? q[k + 2] : q[k];
+    r[k] = keep + __shfl_xor_sync(FULL, send, 8);
+  }
+  {
+    const float send = b2 ? r[0] : r[1];
+    const float keep = b2 ? r[1] : r[0];
+    s = keep + __shfl_xor_sync(FULL, send, 4);
+  }
+  s += __shfl_xor_sync(FULL, s, 2);
+  s += __shfl_xor_sync(FULL, s, 1);
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// Row pass: every warp walks its share of the index stream, 64 rows per threefry batch,
+// 8 rows in flight per lane.  Result: part[warp][0..DS) = sum over the warp's rows of
+//   gaussian_mean: x            logreg: w x~  with  w = -sigmoid(theta.x~) [ + sigmoid(center.x~) if CV ]
+template <int FAMILY, bool CV, int NCH>
+__device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, const RandintPlan& plan,
+                                         unsigned seq_base, unsigned count, const float* s_theta, const float* s_center,
+                                         float* s_part) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const unsigned h = (count + 1u) >> 1;
+  const int DS = m.DS;
+  const float4* __restrict__ rows = reinterpret_cast<const float4*>(m.rows);
+  const int row_f4 = DS >> 2;
+
+  float4 acc[NCH], th[NCH], ct[NCH];
+  bool ok[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int f4 = lane + 32 * c;
+    ok[c] = f4 < row_f4;
+    acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    th[c] = ct[c] = acc[c];
+    if (FAMILY == SGMCMC_FAMILY_LOGREG && ok[c]) {
+      th[c] = reinterpret_cast<const float4*>(s_theta)[f4];
+      if (CV) ct[c] = reinterpret_cast<const float4*>(s_center)[f4];
+    }
+  }
+
+  for (unsigned b0 = warp * 32u; b0 < h; b0 += W * 32u) {
+    const unsigned b = b0 + lane;
+    int jA = -1, jB = -1;
+    if (b < h) {
+      unsigned iA, iB;
+      if (sequential) { iA = seq_base + b; iB = seq_base + b + h; } else { randint_block(plan, b, iA, iB); }
+      jA = (int)iA;
+      if (b + h < count) jB = (int)iB;
+    }
+#pragma unroll 1
+    for (int grp = 0; grp < 8; ++grp) {
+      const int src = (grp < 4) ? jA : jB;
+      const int base = (grp & 3) * 8;
+      int r[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) r[u] = __shfl_sync(FULL, src, base + u);
+      // validity is monotone in the stream position, so an invalid first row ends the group
+      if (r[0] < 0) continue;
+      float4 x[8][NCH];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          x[u][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok[c] && r[u] >= 0) x[u][c] = __ldg(rows + (size_t)r[u] * row_f4 + lane + 32 * c);
+        }
+      }
+      if (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            acc[c].x += x[u][c].x; acc[c].y += x[u][c].y; acc[c].z += x[u][c].z; acc[c].w += x[u][c].w;
+          }
+      } else {
+        float p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          p[u] = dot4(x[u][0], th[0]);
+#pragma unroll
+          for (int c = 1; c < NCH; ++c) p[u] += dot4(x[u][c], th[c]);
+        }
+        const float z = reduce8(p, lane);
+        float wgt = -sigmoid_f(z);
+        if (CV) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            p[u] = dot4(x[u][0], ct[0]);
+#pragma unroll
+            for (int c = 1; c < NCH; ++c) p[u] += dot4(x[u][c], ct[c]);
+          }
+          wgt += sigmoid_f(reduce8(p, lane));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          // rows past the tail were loaded as zeros, so their weight is irrelevant
+          const float wu = __shfl_sync(FULL, wgt, 4 * u);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) axpy4(acc[c], wu, x[u][c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+    if (ok[c]) reinterpret_cast<float4*>(s_part + warp * DS)[lane + 32 * c] = acc[c];
+}
+
+// part[W][DS] -> S[DS]  (fixed summation order: deterministic)
+__device__ __forceinline__ void fold_parts(const Smem& s, int DS) {
+  const int W = blockDim.x >> 5;
+  __syncthreads();
+  for (int d = threadIdx.x; d < DS; d += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < W; ++w) t += s.part[w * DS + d];
+    s.S[d] = t;
+  }
+  __syncthreads();
+}
+
+// grad_log_post at theta from the folded row sum S (util.py:43-44).
+//   rows_in_S = number of rows summed (as float), scale = Ndata / rows_in_S
+template <int FAMILY>
+__device__ __forceinline__ float grad_from_sum(const VecModel& m, int leaf, int d, float S_d, float theta_e,
+                                               float scale, float rows_in_S) {
+  if (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN)
+    return scale * (m.lik2[leaf] * (S_d - rows_in_S * theta_e)) - m.prior2[leaf] * theta_e;
+  return scale * S_d - m.prior2[0] * theta_e;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < W; ++w) t += red[w];   // same order in every thread: deterministic
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------
+template <int FAMILY, bool CV, int NCH>
+struct ChainCtx {
+  const VecModel& m;
+  Smem s;
+  __device__ ChainCtx(const VecModel& mm, const Smem& ss) : m(mm), s(ss) {}
+
+  // full-batch gradient at s.theta into dst[] (sequential pass over every row)
+  __device__ void full_grad(float* dst) {
+    RandintPlan dummy{};
+    row_pass<FAMILY, false, NCH>(m, true, dummy, 0u, m.n_data, s.theta, s.center, s.part);
+    fold_parts(s, m.DS);
+    const float rows = (float)m.n_data;
+    for (int e = threadIdx.x; e < m.P; e += blockDim.x) {
+      const int leaf = e / m.leaf_dim, d = e - leaf * m.leaf_dim;
+      dst[e] = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.theta[e], 1.0f, rows);
+    }
+    __syncthreads();
+  }
+
+  // estimate_gradient(i, key, theta, svrg_state) -> s.grad
+  __device__ void estimate(int i, Key k2, bool is_init) {
+    if (m.estimator == SGMCMC_EST_SVRG) {
+      if (is_init) {                                   // gradient_estimation.py:124-128
+        full_grad(s.fb);
+        for (int e = threadIdx.x; e < m.P; e += blockDim.x) { s.center[e] = s.theta[e]; s.grad[e] = s.fb[e]; }
+        __syncthreads();
+        return;
+      }
+      if (i % m.update_rate == 0) {                    // gradient_estimation.py:134-139
+        full_grad(s.fb);
+        for (int e = threadIdx.x; e < m.P; e += blockDim.x) s.center[e] = s.theta[e];
+        __syncthreads();
+      }
+    } else if (m.estimator == SGMCMC_EST_STANDARD && m.full_batch && !is_init) {
+      full_grad(s.grad);                               // gradient_estimation.py:41-42
+      return;
+    }
+    const RandintPlan plan = randint_plan(k2, m.n_data, m.batch);
+    row_pass<FAMILY, CV, NCH>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part);
+    fold_parts(s, m.DS);
+    const float rows = (float)m.batch;
+    for (int e = threadIdx.x; e < m.P; e += blockDim.x) {
+      const int leaf = e / m.leaf_dim, d = e - leaf * m.leaf_dim;
+      float g;
+      if (!CV) {
+        g = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.theta[e], m.scale, rows);
+      } else if (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN) {
+        // (c + g) - gc, gradient_estimation.py:72
+        const float gt = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.theta[e], m.scale, rows);
+        const float gc = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.center[e], m.scale, rows);
+        g = (s.fb[e] + gt) - gc;
+      } else {
+        // S already holds sum (w - w_c) x~ : c + (g - gc) without the fp32 cancellation
+        g = s.fb[e] + (m.scale * s.S[d] - m.prior2[0] * (s.theta[e] - s.center[e]));
+      }
+      s.grad[e] = g;
+    }
+    __syncthreads();
+  }
+
+  // per-leaf noise keys: split(k, n_leaves)[leaf]   (diffusion_util.py:66,91,112)
+  __device__ __forceinline__ Key leaf_key(int slot, int leaf) const {
+    Key k; k.a = s.keys[slot + 2 * leaf]; k.b = s.keys[slot + 2 * leaf + 1]; return k;
+  }
+
+  // warp 0 expands `key` into split(key)[0], split(key)[1] and split(split(key)[0], n_leaves):
+  //   keys[0..1] = k1, keys[2..3] = k2, keys[4 + 2j ..] = leaf keys of k1
+  __device__ void expand_step_keys(Key key) {
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      uint32_t w = lane < 4 ? stream_word(key, lane, 4u) : 0u;
+      Key k1; k1.a = __shfl_sync(FULL, w, 0); k1.b = __shfl_sync(FULL, w, 1);
+      if (lane < 4) s.keys[lane] = w;
+      const uint32_t nl = m.n_leaves;
+      if (lane < 2 * (int)nl) s.keys[4 + lane] = stream_word(k1, lane, 2u * nl);
+    }
+    __syncthreads();
+  }
+
+  // diffusion update, phase 1 = `update` (before the new gradient), phase 2 = `update2`
+  __device__ void diffuse(int phase, int i, const sgmcmc_step_coef& cf, int key_slot) {
+    const int D = m.leaf_dim;
+    const bool bug = (m.flags & SGMCMC_FLAG_BADODABCV_REFERENCE_BUG) && m.diffusion == SGMCMC_DIFF_BADODAB;
+    if (phase == 2 || bug) {                      // baoab / badodab update2: v += dt/2 * g
+      for (int e = threadIdx.x; e < m.P; e += blockDim.x) s.aux1[e] = fmaf(cf.hh, s.grad[e], s.aux1[e]);
+      __syncthreads();
+      return;
+    }
+    for (int leaf = 0; leaf < m.n_leaves; ++leaf) {
+      const Key lk = leaf_key(key_slot, leaf);
+      const int off = leaf * D;
+      switch (m.diffusion) {
+        case SGMCMC_DIFF_SGLD:
+          for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const int e = off + d;
+            s.theta[e] = fmaf(cf.ca, normal_at(lk, d, D), fmaf(cf.h, s.grad[e], s.theta[e]));
+          }
+          break;
+        case SGMCMC_DIFF_PSGLD:
+          for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const int e = off + d;
+            const float g = s.grad[e], alpha = m.hyper[0], eps = m.hyper[1];
+            const float v = alpha * s.aux1[e] + (1.0f - alpha) * (g * g);
+            const float G = 1.0f / (sqrtf(v) + eps);
+            s.aux1[e] = v;
+            s.theta[e] = s.theta[e] + cf.hh * G * g + sqrtf(cf.h * G) * normal_at(lk, d, D);
+          }
+          break;
+        case SGMCMC_DIFF_SGLDADAM:
+          for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const int e = off + d;
+            const float g = s.grad[e], b1 = m.hyper[0], b2 = m.hyper[1], eps = m.hyper[2];
+            const float mm = b1 * s.aux1[e] + (1.0f - b1) * g;
+            const float vv = b2 * s.aux2[e] + (1.0f - b2) * (g * g);
+            const float mh = mm / cf.ca, vh = vv / cf.cb;
+            const float a = cf.h / (sqrtf(vh) + eps);
+            s.aux1[e] = mm; s.aux2[e] = vv;
+            s.theta[e] = s.theta[e] + a * 0.5f * mh + sqrtf(a) * normal_at(lk, d, D);
+          }
+          break;
+        case SGMCMC_DIFF_SGHMC:
+          for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const int e = off + d;
+            const float v = s.aux1[e], alpha = m.hyper[0];
+            s.theta[e] += v;
+            s.aux1[e] = v + cf.h * s.grad[e] - alpha * v + cf.ca * normal_at(lk, d, D);
+          }
+          break;
+        case SGMCMC_DIFF_BAOAB:
+          for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const int e = off + d;
+            float v = fmaf(cf.hh, s.grad[e], s.aux1[e]);
+            float x = s.theta[e] + v * cf.h * 0.5f;
+            v = cf.ca * v + cf.cb * normal_at(lk, d, D);
+            x = x + v * cf.h * 0.5f;
+            s.aux1[e] = v; s.theta[e] = x;
+          }
+          break;
+        case SGMCMC_DIFF_SGNHT: {
+          Key kn = lk;
+          const float alpha = s.alpha[leaf];
+          float ss = 0.f;
+          if (i == 0) {                              // diffusions.py:268-278
+            Key sub; split2(lk, kn, sub);
+            for (int d = threadIdx.x; d < D; d += blockDim.x) s.aux1[off + d] = cf.cb * normal_at(sub, d, D);
+          }
+          for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const int e = off + d;
+            float v = s.aux1[e];
+            v = v - alpha * v + cf.h * s.grad[e] + cf.ca * normal_at(kn, d, D);
+            s.aux1[e] = v; s.theta[e] += v;
+            ss = fmaf(v, v, ss);
+          }
+          const float nrm = sqrtf(block_sum(ss, s.red));
+          if (threadIdx.x == 0) s.alpha[leaf] = alpha + (nrm * nrm) / (float)D - cf.h;
+          break;
+        }
+        case SGMCMC_DIFF_BADODAB: {
+          float alpha = s.alpha[leaf];
+          float ss = 0.f;
+          for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const int e = off + d;
+            const float v = fmaf(cf.hh, s.grad[e], s.aux1[e]);
+            s.aux1[e] = v; s.theta[e] = fmaf(cf.hh, v, s.theta[e]);
+            ss = fmaf(v, v, ss);
+          }
+          alpha = alpha + cf.hh * (sqrtf(block_sum(ss, s.red)) - (float)D);
+          const float c1 = expf(-alpha * cf.h);
+          const float c2 = (alpha == 0.0f) ? cf.ca : sqrtf(fabsf((1.0f - c1 * c1) / (2.0f * alpha)));
+          ss = 0.f;
+          for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const int e = off + d;
+            const float v = c1 * s.aux1[e] + c2 * normal_at(lk, d, D);
+            s.aux1[e] = v; ss = fmaf(v, v, ss);
+          }
+          alpha = alpha + cf.hh * (sqrtf(block_sum(ss, s.red)) - (float)D);
+          for (int d = threadIdx.x; d < D; d += blockDim.x) s.theta[off + d] = fmaf(cf.hh, s.aux1[off + d], s.theta[off + d]);
+          __syncthreads();
+          if (threadIdx.x == 0) s.alpha[leaf] = alpha;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // langevin kernel, kernels.py:53-64
+  __device__ void langevin(int i, Key key, const sgmcmc_step_coef& cf) {
+    expand_step_keys(key);
+    Key k2; k2.a = s.keys[2]; k2.b = s.keys[3];
+    diffuse(1, i, cf, 4);
+    estimate(i, k2, false);
+    if (m.diffusion == SGMCMC_DIFF_BAOAB || m.diffusion == SGMCMC_DIFF_BADODAB) diffuse(2, i, cf, 4);
+  }
+
+  // one sample: langevin kernel, or the SGHMC wrapper of kernels.py:110-122
+  __device__ void transition(int i, Key key, const sgmcmc_step_coef& cf) {
+    if (m.diffusion != SGMCMC_DIFF_SGHMC) { langevin(i, key, cf); return; }
+    Key k1, k2;
+    split2(key, k1, k2);
+    const int D = m.leaf_dim;
+    for (int leaf = 0; leaf < m.n_leaves; ++leaf) {      // resample_momentum, diffusions.py:197-199
+      const Key lk = split_at(k1, m.n_leaves, leaf);
+      for (int d = threadIdx.x; d < D; d += blockDim.x) s.aux1[leaf * D + d] = cf.cb * normal_at(lk, d, D);
+    }
+    __syncthreads();
+    for (int l = 0; l < m.leapfrog; ++l) langevin(i, split_at(k2, m.leapfrog, l), cf);
+  }
+};
+
+template <int FAMILY, bool CV, int NCH>
+__global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel m, const VecRun run) {
+  extern __shared__ __align__(16) float smem_raw[];
+  const int W = blockDim.x >> 5;
+  const int PP = ((m.P > m.DS ? m.P : m.DS) + 3) & ~3;
+  const Smem s = carve(smem_raw, PP, m.DS, W);
+  const int c = blockIdx.x;
+  const int P = m.P;
+  const sgmcmc_state& st = run.st;
+
+  for (int e = threadIdx.x; e < PP; e += blockDim.x) {
+    const bool in = e < P;
+    s.theta[e] = in ? st.theta[(size_t)c * P + e] : 0.f;
+    s.aux1[e] = (in && st.aux1 && run.mode == 0) ? st.aux1[(size_t)c * P + e] : 0.f;
+    s.aux2[e] = (in && st.aux2 && run.mode == 0) ? st.aux2[(size_t)c * P + e] : 0.f;
+    s.grad[e] = (in && run.mode == 0) ? st.grad[(size_t)c * P + e] : 0.f;
+    float ce = 0.f, fe = 0.f;
+    if (in && m.estimator == SGMCMC_EST_CV) { ce = m.cv_center[e]; fe = m.cv_grad[e]; }
+    if (in && m.estimator == SGMCMC_EST_SVRG && run.mode == 0) {
+      ce = st.svrg_center[(size_t)c * P + e]; fe = st.svrg_grad[(size_t)c * P + e];
+    }
+    s.center[e] = ce; s.fb[e] = fe;
+  }
+  if (threadIdx.x < MAXL) {
+    float a = 0.f;
+    if (st.alpha && threadIdx.x < m.n_leaves)
+      a = run.mode == 0 ? st.alpha[(size_t)c * m.n_leaves + threadIdx.x] : m.hyper[0];
+    s.alpha[threadIdx.x] = a;
+  }
+  __syncthreads();
+
+  ChainCtx<FAMILY, CV, NCH> ctx(m, s);
+  Key carry{0u, 0u};
+
+  if (run.mode != 0) {
+    // init_fn (kernels.py:48-51), optionally preceded by samplers.py:53
+    Key k; k.a = run.init_keys[2 * c]; k.b = run.init_keys[2 * c + 1];
+    if (run.mode == 2) { Key sub; split2(k, carry, sub); k = sub; }
+    ctx.estimate(0, k, true);
+  } else {
+    if (run.step_keys == nullptr) { carry.a = st.key[2 * c]; carry.b = st.key[2 * c + 1]; }
+    for (int sidx = 0; sidx < run.K; ++sidx) {
+      const int i = run.i0 + sidx;
+      const sgmcmc_step_coef cf = run.coef[(size_t)sidx * run.coef_stride];
+      Key sub;
+      if (run.step_keys) { sub.a = run.step_keys[2 * c]; sub.b = run.step_keys[2 * c + 1]; }
+      else { Key nk; split2(carry, nk, sub); carry = nk; }      // samplers.py:49
+      ctx.transition(i, sub, cf);
+      if (run.samples) {
+        float* dst = run.samples + (size_t)c * run.sample_chain_stride + (size_t)sidx * P;
+        for (int e = threadIdx.x; e < P; e += blockDim.x) dst[e] = s.theta[e];
+      }
+    }
+  }
+
+  // write the chain state back
+  for (int e = threadIdx.x; e < P; e += blockDim.x) {
+    const size_t o = (size_t)c * P + e;
+    if (run.mode == 0) st.theta[o] = s.theta[e];
+    if (st.aux1) st.aux1[o] = s.aux1[e];
+    if (st.aux2) st.aux2[o] = s.aux2[e];
+    st.grad[o] = s.grad[e];
+    if (m.estimator == SGMCMC_EST_SVRG) { st.svrg_center[o] = s.center[e]; st.svrg_grad[o] = s.fb[e]; }
+  }
+  if (st.alpha && threadIdx.x < m.n_leaves) st.alpha[(size_t)c * m.n_leaves + threadIdx.x] = s.alpha[threadIdx.x];
+  if (threadIdx.x == 0 && st.key && (run.mode == 2 || (run.mode == 0 && run.step_keys == nullptr))) {
+    st.key[2 * c] = carry.a; st.key[2 * c + 1] = carry.b;
+  }
+}
+
+}  // namespace sg

@@ -1,0 +1,110 @@
+"""The sampler factories of sgmcmcjax/samplers.py:98-136: ``build_*_sampler(...)`` takes exactly
+the arguments of the matching ``build_*_kernel`` plus ``compiled`` / ``pbar`` and returns
+``sampler(key, Nsamples, params) -> samples``.
+
+The scan of samplers.py:45-58 runs as ONE kernel launch (K steps per launch, one CTA per chain);
+``pbar=True`` splits it into at most 20 launches and advances a host-side tqdm bar between them
+(the reference updates every Nsamples/20 iterations, util.py:130).  ``compiled=False`` keeps the
+reference's return type for that mode: a Python list with one parameter pytree per sample
+(samplers.py:81-93).  Multi-chain: ``key`` uint32[C,2] and parameter leaves [C,D] give samples with
+leaves [C, Nsamples, D] (``vmap(sampler, in_axes=(0, None, 0))`` semantics).
+"""
+from __future__ import annotations
+
+import functools
+from typing import Callable
+
+from . import _native, _tree
+from ._engine import keys_to_device
+from .kernels import (
+    _like,
+    build_badodab_kernel,
+    build_badodabCV_kernel,
+    build_baoab_kernel,
+    build_psgld_kernel,
+    build_sghmc_kernel,
+    build_sghmc_SVRG_kernel,
+    build_sghmcCV_kernel,
+    build_sgld_kernel,
+    build_sgld_SVRG_kernel,
+    build_sgldAdam_kernel,
+    build_sgldCV_kernel,
+    build_sgnht_kernel,
+    build_sgnhtCV_kernel,
+)
+
+
+def _build_native_sampler(init_fn: Callable, as_list: bool, pbar: bool) -> Callable:
+    eng = init_fn.engine
+
+    def sampler(key, Nsamples: int, params):
+        torch = _native.require_cuda()
+        keys, kb = keys_to_device(key)
+        flat, treedef, pb = eng.flatten_params(params, broadcast_chains=keys.shape[0])
+        if keys.shape[0] != flat.shape[0]:
+            raise ValueError("need one key per chain")
+        batched = kb or pb
+        n_chains, nsamp = flat.shape[0], int(Nsamples)
+        st = eng.new_state(flat)
+        eng.init(st, keys, sampler_mode=True)                     # samplers.py:53-54
+        samples = torch.empty((n_chains, nsamp, eng.P), dtype=torch.float32, device="cuda")
+        keep = []
+        if pbar and nsamp > 0:
+            from tqdm.auto import tqdm
+
+            bar = tqdm(total=nsamp)
+            bar.set_description(f"Running for {nsamp:,} iterations", refresh=False)
+            chunk = max(nsamp // 20, 1)
+            for i0 in range(0, nsamp, chunk):
+                k = min(chunk, nsamp - i0)
+                keep.append(eng.run(st, i0, k, samples[:, i0:], sample_chain_stride=nsamp * eng.P))
+                torch.cuda.current_stream().synchronize()
+                bar.update(k)
+            bar.close()
+        elif nsamp > 0:
+            keep.append(eng.run(st, 0, nsamp, samples))           # samplers.py:57
+        like = _tree.flatten(params)[0][0]
+        if as_list:                                               # samplers.py:81-93
+            out = []
+            host = samples if batched else samples[0]
+            for i in range(nsamp):
+                tree = eng.unflatten_params(host[..., i, :], treedef, (n_chains,) if batched else ())
+                leaves, td = _tree.flatten(tree)
+                out.append(_tree.unflatten(td, [_like(l, like) for l in leaves]))
+            return out
+        lead = (n_chains, nsamp) if batched else (nsamp,)
+        tree = eng.unflatten_params(samples if batched else samples[0], treedef, lead)
+        leaves, td = _tree.flatten(tree)
+        return _tree.unflatten(td, [_like(l, like) for l in leaves])
+
+    sampler.engine = eng
+    return sampler
+
+
+def sgmcmc_sampler(build_kernel_fn: Callable) -> Callable:
+    """Decorator turning a kernel factory into a sampler factory (samplers.py:98-122)."""
+
+    @functools.wraps(build_kernel_fn)
+    def wrapper(*args, **kwargs):
+        compiled = kwargs.pop("compiled", True)
+        pbar = kwargs.pop("pbar", True)
+        init_fn, _kernel, _get_params = build_kernel_fn(*args, **kwargs)
+        return _build_native_sampler(init_fn, as_list=not compiled, pbar=pbar)
+
+    return wrapper
+
+
+build_sgld_sampler = sgmcmc_sampler(build_sgld_kernel)
+build_sgldCV_sampler = sgmcmc_sampler(build_sgldCV_kernel)
+build_sgld_SVRG_sampler = sgmcmc_sampler(build_sgld_SVRG_kernel)
+build_psgld_sampler = sgmcmc_sampler(build_psgld_kernel)
+build_sghmc_sampler = sgmcmc_sampler(build_sghmc_kernel)
+build_sghmcCV_sampler = sgmcmc_sampler(build_sghmcCV_kernel)
+build_sghmc_SVRG_sampler = sgmcmc_sampler(build_sghmc_SVRG_kernel)
+build_baoab_sampler = sgmcmc_sampler(build_baoab_kernel)
+build_sgnht_sampler = sgmcmc_sampler(build_sgnht_kernel)
+build_sgnhtCV_sampler = sgmcmc_sampler(build_sgnhtCV_kernel)
+build_badodab_sampler = sgmcmc_sampler(build_badodab_kernel)
+build_badodabCV_sampler = sgmcmc_sampler(build_badodabCV_kernel)
+# the reference has the kernel but no sampler for sgldAdam; provided here
+build_sgldAdam_sampler = sgmcmc_sampler(build_sgldAdam_kernel)

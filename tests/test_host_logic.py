@@ -1,0 +1,72 @@
+"""Host-side logic that runs without a GPU: pytrees, schedules / step coefficients, registry, sharding."""
+import numpy as np
+import pytest
+
+from sgmcmcjax_b200 import _tree, diffusions, ksd, models
+from sgmcmcjax_b200.models import resolve_family
+
+
+def test_tree_roundtrip_leaf_order():
+    tree = {"b": [1, (2, 3)], "a": 0}
+    leaves, td = _tree.flatten(tree)
+    assert leaves == [0, 1, 2, 3]                          # dict keys sorted, sequences in order
+    assert _tree.unflatten(td, [10, 11, 12, 13]) == {"a": 10, "b": [11, (12, 13)]}
+    leaves, td = _tree.flatten(5)
+    assert leaves == [5] and _tree.unflatten(td, [7]) == 7
+
+
+def test_schedules_match_reference_formulas():
+    s = diffusions.welling_teh_schedule(1e-3, 10.0)
+    assert s(5) == pytest.approx(1e-3 * 15.0 ** -0.55)
+    c = diffusions.cyclical_schedule(1e-2, 4, 100)          # period ceil(100/4) = 25
+    assert c(1) == pytest.approx(1e-2) and c(26) == pytest.approx(1e-2)
+    assert diffusions.make_schedule(0.5)(123) == 0.5
+    with pytest.raises(TypeError):
+        diffusions.make_schedule(np.zeros(3))
+
+
+def test_step_coefs_weak_type_rounding():
+    f = np.float32
+    sch = diffusions.make_schedule(1e-5)
+    row = diffusions.step_coefs("sgld", {}, sch, 0, 1)[0]
+    assert row[0] == f(1e-5) and row[1] == f(0.5e-5) and row[2] == np.sqrt(f(2e-5))
+    rows = diffusions.step_coefs("sgldAdam", dict(beta1=0.9, beta2=0.999, eps=1e-8), sch, 3, 2)
+    assert rows.shape == (2, 4) and rows[0, 2] == f(1) - np.power(f(0.9), f(4))
+    b = diffusions.step_coefs("baoab", dict(gamma=5.0, tau=1.0), diffusions.make_schedule(1e-3), 0, 1)[0]
+    assert b[2] == np.exp(f(-5e-3)) and b[3] == np.sqrt(f(1) - b[2] * b[2])
+    assert diffusions.coef_is_constant("sgld", sch) and not diffusions.coef_is_constant("sgldAdam", sch)
+    assert not diffusions.coef_is_constant("sgld", diffusions.welling_teh_schedule(1.0, 1.0))
+
+
+def test_family_registry():
+    spec = resolve_family(models.logistic_regression.loglikelihood, models.logistic_regression.logprior)
+    assert spec.name == "logistic_regression" and spec.prior_coef == (0.1,)
+    g = resolve_family(models.gaussian_mean.loglikelihood_list_array, models.gaussian_mean.logprior_list_array)
+    assert g.lik_coef == (0.5, 0.1) and g.prior_coef == (0.001, 0.001)
+    with pytest.raises(NotImplementedError):
+        resolve_family(lambda th, x: 0.0, lambda th: 0.0)
+    with pytest.raises(ValueError):
+        resolve_family(models.gaussian_mean.loglikelihood, models.logistic_regression.logprior)
+    with pytest.raises(ValueError):
+        resolve_family(models.gaussian_mean.logprior, models.gaussian_mean.loglikelihood)
+
+
+def test_ksd_row_blocks_partition_rows():
+    for n, w in [(50000, 8), (10, 3), (7, 8), (1, 1)]:
+        blocks = [ksd.row_block(n, r, w) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(b[1] == nb[0] for b, nb in zip(blocks, blocks[1:]))
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    from sgmcmcjax_b200 import _native
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_native.NativeError):
+        from sgmcmcjax_b200.samplers import build_sgld_sampler
+
+        build_sgld_sampler(1e-5, models.gaussian_mean.loglikelihood, models.gaussian_mean.logprior,
+                           (np.zeros((10, 4), np.float32),), 2)
