@@ -1,0 +1,369 @@
+"""bench.py - SGLD chain-steps/sec on logistic regression (BASELINE.json metric), plus imq_KSD pairs/sec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): logistic regression N=1e6 rows, D=100, minibatch 1e4, SGLD
+(dt=1e-5), 1024 independent chains PER GPU (chains are the unit that shards; no collective on the data
+path; scaling "weak").  One bench "step" = one launch of the fused sampler kernel advancing every chain
+by --inner SGLD iterations (threefry index draw + random row gather + per-example gradients + reduction
++ diffusion update with in-register Gaussian noise, samples written to HBM).
+
+value      chain-steps/s over all GPUs, inputs resident in HBM, CUDA-event timed, max over ranks.
+e2e        same metric through the public API `sampler(key, Nsamples, params)` with HOST (numpy) keys and
+           parameters in and HOST samples out (H2D + D2H inside the timed region).
+roofline   algorithmic bytes (B*(row+label bytes) + 8P + 4P per chain-step) / kernel time
+           against the measured HBM copy bandwidth of MEASURED_PEAKS.json.
+cpu_baseline  the numpy oracle (restatement of the reference's JAX semantics; JAX itself is not installable
+           here) on the host cores, one chain per worker process, bounded sample.
+ksd        imq_KSD on N=50k x D=100 (configs[4]) in pairs/s; row blocks shard over ranks, one all-reduce.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_DATA, DIM, BATCH, CHAINS, DT = 1_000_000, 100, 10_000, 1024, 1e-5
+KSD_N = 50_000
+METRIC = "SGLD chain-steps/sec, logistic reg. D=100"
+UNIT = "chain-steps/s"
+
+
+def algorithmic_bytes_per_chain_step(batch=BATCH, dim=DIM, n_state=1):
+    # B*(row_bytes(X)+row_bytes(y)) + 4P*(2 n_state) + 4P (sample emitted)
+    return batch * (4 * dim + 4) + 4 * dim * 2 * n_state + 4 * dim
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    """One oracle chain on the shared synthetic table; returns (chain_steps, seconds)."""
+    seed, n_steps, budget_s = args
+    from oracle import jax_prng as P
+    from oracle import models as M
+    from oracle import sgmcmc as S
+
+    X, y, theta = _CPU_DATA
+    kern = S.build_kernel("sgld", M.LogisticRegression(), (X, y), BATCH, DT)
+    key = P.PRNGKey(seed)
+    key, sub = P.split(key)
+    state = kern.init_fn(sub, [theta])
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(n_steps):
+        key, sub = P.split(key)
+        state = kern.kernel(i, sub, state)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return done, time.perf_counter() - t0
+
+
+_CPU_DATA = None
+
+
+def cpu_data():
+    """Synthetic table of the C2 shape for the host arm (numpy RNG: content does not change the cost)."""
+    global _CPU_DATA
+    if _CPU_DATA is None:
+        rng = np.random.default_rng(42)
+        theta = (np.sqrt(10.0) * rng.standard_normal(DIM)).astype(np.float32)
+        X = rng.standard_normal((N_DATA, DIM), dtype=np.float32)
+        y = (rng.random(N_DATA) < 1.0 / (1.0 + np.exp(-(X @ theta)))).astype(np.int32)
+        _CPU_DATA = (X, y, theta)
+    return _CPU_DATA
+
+
+def run_cpu_arm(budget_s: float, max_steps: int = 1_000_000):
+    """Oracle chains on every host core (fork before CUDA is initialised; table shared copy-on-write)."""
+    import multiprocessing as mp
+
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)                      # one chain per core, no BLAS oversubscription
+    except Exception:
+        pass
+    cores = len(os.sched_getaffinity(0))
+    cpu_data()
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(s, max_steps, budget_s) for s in range(cores)])
+    wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return {"value": steps / slowest, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{cores} oracle chains (one per core), {steps} chain-steps of the C2 workload in "
+                      f"{slowest:.1f} s (numpy restatement of SGMCMCJax/JAX-0.4.13 semantics, not XLA)",
+            "wall_s": wall, "chain_steps": steps}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step_budget = 6.0
+    vals, times = [], []
+    for s in range(args.warmup + args.steps):
+        r = run_cpu_arm(per_step_budget if s >= args.warmup else 2.0)
+        if s >= args.warmup:
+            vals.append(r["value"])
+            times.append(r["wall_s"])
+    v = float(statistics.mean(vals))
+    line = {
+        "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(statistics.mean(times)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "note": "reference arm = numpy oracle on host cores; the "
+                   "reference itself needs jax==0.4.13, which is not installable in this image"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_name(args):
+    return (f"logreg N={N_DATA} D={DIM} batch={args.batch} SGLD dt={DT}, {args.chains} chains/GPU, "
+            f"{args.inner} chain-steps per launch")
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def gpu_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = run_cpu_arm(args.cpu_budget)           # before CUDA init (fork-safe)
+        for k in ("wall_s", "chain_steps"):
+            cpu_base.pop(k, None)
+        global _CPU_DATA
+        _CPU_DATA = None
+
+    import torch
+    import torch.distributed as dist
+
+    from sgmcmcjax_b200 import _native, ksd, random, samplers
+    from sgmcmcjax_b200.models import logistic_regression as L
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _native.load()
+    hbm_peak, bf16_peak, peak_src = peaks()
+
+    # synthetic C2 data, generated on device with the jax-compatible PRNG (same table on every rank)
+    theta_true, X, y = L.gen_data(random.PRNGKey(42), DIM, N_DATA)
+    sampler = samplers.build_sgld_sampler(DT, L.loglikelihood, L.logprior, (X, y), args.batch, pbar=False)
+    eng = sampler.engine
+    C, K, P = args.chains, args.inner, DIM
+    all_keys = random.split(random.PRNGKey(0), C * world)             # chain c of the job == key c, any N
+    keys_host = np.ascontiguousarray(all_keys[rank * C:(rank + 1) * C])
+    theta0_host = np.tile(theta_true.cpu().numpy(), (C, 1)).astype(np.float32)
+
+    # ---- device-resident timing: state lives in HBM, one launch per bench step
+    from sgmcmcjax_b200._engine import keys_to_device
+    keys_dev, _ = keys_to_device(keys_host)
+    st = eng.new_state(torch.from_numpy(theta0_host).cuda())
+    eng.init(st, keys_dev, sampler_mode=True)
+    samples = torch.empty((C, K, P), dtype=torch.float32, device="cuda")
+    i0 = 0
+    for _ in range(args.warmup):
+        eng.run(st, i0, K, samples); i0 += K
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = lib.sgmcmc_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_wall0 = time.perf_counter()
+    ev[0].record()
+    for s in range(args.steps):
+        eng.run(st, i0, K, samples); i0 += K
+        ev[s + 1].record()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    launches = lib.sgmcmc_launch_count() - l0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    per_launch_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * C * K * args.steps / (total_ms_max * 1e-3)
+    assert torch.isfinite(samples).all(), "non-finite samples"
+
+    kern_ms = float(statistics.mean(per_launch_ms))
+    alg_bytes = algorithmic_bytes_per_chain_step(args.batch) * C * K
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": args.traffic, "kernel": "vec_sampler_kernel<LOGREG>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms}
+
+    # ---- end to end through the public API: host keys + host params in, host samples out
+    Ke = args.e2e_steps
+    sampler(keys_host, Ke, theta0_host)                               # warm-up (allocator, coefficient cache)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps, e2e_t = 3, []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = sampler(keys_host, Ke, theta0_host)                     # numpy in -> numpy out
+        e2e_t.append(time.perf_counter() - t0)
+    assert isinstance(out, np.ndarray) and out.shape == (C, Ke, P)
+    te = torch.tensor([statistics.median(e2e_t)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    # Ke chain-steps are counted; the init_fn gradient (samplers.py:54) is extra uncounted work
+    e2e = {"value": world * C * Ke / float(te.item()), "unit": UNIT,
+           "h2d_bytes_per_step": int((keys_host.nbytes + theta0_host.nbytes) * K / Ke),
+           "d2h_bytes_per_step": int(C * K * P * 4),
+           "note": f"sampler(key, {Ke}, params) with numpy in/out incl. init_fn; bytes scaled to one bench step "
+                   f"({K} chain-steps per chain)"}
+
+    # ---- KSD (configs[4]): 50k x 100 points, row blocks over ranks, one all-reduce of a double
+    ksd_line = None
+    if not args.no_ksd:
+        n = args.ksd_n
+        pts = theta_true[None, :] + 0.02 * random.normal(random.PRNGKey(7), (n, DIM))
+        grads = -50.0 * (pts - theta_true[None, :]) + random.normal(random.PRNGKey(8), (n, DIM))
+        pts, grads = pts.contiguous(), grads.contiguous()
+        r0, r1 = ksd.row_block(n, rank, world)
+        for _ in range(2):
+            ksd.imq_KSD(pts, grads, distributed=world > 1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        a.record()
+        for _ in range(reps):
+            val = ksd.imq_KSD(pts, grads, distributed=world > 1)
+        b.record()
+        torch.cuda.synchronize()
+        tk = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        ms = float(tk.item())
+        pairs = float(n) * n
+        flops = 6.0 * DIM * pairs                                     # 3 Gram contractions, 2 flops per MAC
+        ksd_line = {"metric": "imq_KSD pairs/sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n": n, "d": DIM,
+                    "ms": ms, "ksd": float(val), "equiv_tflops": flops / (ms * 1e-3) / 1e12,
+                    "rows_this_rank": [r0, r1]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "l2": "data table 400 MB > 126 MB L2, rows drawn at random "
+                       "every step (inputs larger than L2; no explicit flush)", "chains_total": world * C,
+                       "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
+            "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clk, "ksd": ksd_line,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS, help="chains per GPU")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--inner", type=int, default=10, help="chain-steps per launch (= per bench step)")
+    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--ksd-n", type=int, default=KSD_N)
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of host work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ksd", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="dram bytes per launch from the committed ncu --set full capture (profiles/)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        print("note: fewer than 3 warm-up steps", file=sys.stderr)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "native" and world != args.gpus and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -108,6 +108,10 @@ typedef struct sgmcmc_handle sgmcmc_handle;
 const char* sgmcmc_last_error(void);
 int sgmcmc_abi_version(void);
 
+/* Number of CUDA kernels this library has launched in the calling process so far
+ * (monotone; bench.py reports the difference over its timed region as gpu_launches). */
+int64_t sgmcmc_launch_count(void);
+
 int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out);
 int sgmcmc_destroy(sgmcmc_handle* h);
 

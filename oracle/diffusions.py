@@ -17,6 +17,14 @@ import numpy as np
 from . import jax_prng as prng
 
 
+def exp_f32(x):
+    """fp32 ``exp`` of an fp32 argument, correctly rounded (evaluated in double, rounded once).
+    XLA's, numpy's and CUDA's single-precision ``exp`` each differ from this by at most 1-2 ulp and
+    from one another; BAOAB / BADODAB form ``1 - exp(-a*h)**2`` with a*h ~ 1e-5..1e-2, which amplifies
+    that last-bit disagreement by ~1/(a*h), so the oracle fixes the correctly rounded value."""
+    return np.float32(np.exp(np.float64(np.float32(x))))
+
+
 def make_schedule(dt):
     """diffusions.py:377-383 - a float becomes a constant schedule."""
     return dt if callable(dt) else (lambda i: dt)
@@ -140,7 +148,7 @@ class BAOAB(Diffusion):
         f, h = self.f, self.dt(i)
         v = s["v"] + f(h * 0.5) * g
         x = s["x"] + v * f(h) * f(0.5)
-        c1 = np.exp(f(-self.gamma * h))
+        c1 = exp_f32(f(-self.gamma * h))
         c2 = np.sqrt(f(1) - c1 * c1)
         v = c1 * v + f(self.tau) * c2 * self.normal(key, g.shape)
         x = x + v * f(h) * f(0.5)
@@ -195,7 +203,7 @@ class BADODAB(Diffusion):
         x = s["x"] + dt2 * v
         nrm = lambda a: np.sqrt(np.sum(np.square(a), dtype=f))
         alpha = f(s["alpha"] + dt2 * (nrm(v) - f(v.size)))
-        c1 = np.exp(-alpha * f(h))
+        c1 = exp_f32(-alpha * f(h))
         with np.errstate(divide="ignore", invalid="ignore"):
             c2 = np.sqrt(f(h)) if alpha == 0 else np.sqrt(np.abs((f(1) - c1 * c1) / (f(2) * alpha)))
         v = (c1 * v + c2 * self.normal(key, g.shape)).astype(f)

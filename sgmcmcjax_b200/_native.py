@@ -19,7 +19,7 @@ EST_STANDARD, EST_CV, EST_SVRG = 0, 1, 2
 FLAG_BADODABCV_REFERENCE_BUG = 1
 
 EXPORTS = [
-    "sgmcmc_last_error", "sgmcmc_abi_version", "sgmcmc_create", "sgmcmc_destroy", "sgmcmc_set_data",
+    "sgmcmc_last_error", "sgmcmc_abi_version", "sgmcmc_launch_count", "sgmcmc_create", "sgmcmc_destroy", "sgmcmc_set_data",
     "sgmcmc_set_centering", "sgmcmc_fullbatch_grad", "sgmcmc_init", "sgmcmc_run", "sgmcmc_kernel_step",
     "sgmcmc_minibatch_indices", "sgmcmc_normal", "sgmcmc_split", "sgmcmc_ksd_imq_partial",
 ]
@@ -73,6 +73,8 @@ def load(build_if_missing: bool = True):
     lib.sgmcmc_last_error.restype = C.c_char_p
     lib.sgmcmc_last_error.argtypes = []
     lib.sgmcmc_abi_version.restype = i32
+    lib.sgmcmc_launch_count.restype = i64
+    lib.sgmcmc_launch_count.argtypes = []
     sigs = {
         "sgmcmc_create": [C.POINTER(Config), C.POINTER(vp)],
         "sgmcmc_destroy": [vp],

@@ -1,4 +1,5 @@
 // C-ABI entry points of libsgmcmc_b200.so (see include/sgmcmc_b200.h).
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -11,6 +12,7 @@
 namespace {
 
 thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
@@ -127,7 +129,7 @@ int launch_vec(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStr
   const size_t smem = sg::vec_smem_bytes(PP, h->DS, warps);
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<run.st.n_chains, warps * 32, smem, stream>>>(h->vm, run);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
   return SGMCMC_OK;
 }
 
@@ -208,9 +210,9 @@ int fullgrad_impl(sgmcmc_handle* h, const float* thetas, int m, float* out, cuda
     case 4: sg::fullgrad_partial_kernel<FAMILY, 4><<<grid, warps * 32, smem, stream>>>(h->vm, thetas, h->partial, rows_per_split); break;
     default: return fail(SGMCMC_E_UNSUPPORTED, "data_dim > 512 is not supported");
   }
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
   sg::fullgrad_finish_kernel<FAMILY><<<m, 128, 0, stream>>>(h->vm, thetas, h->partial, splits, out);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
   return SGMCMC_OK;
 }
 
@@ -220,6 +222,7 @@ extern "C" {
 
 const char* sgmcmc_last_error(void) { return g_err.c_str(); }
 int sgmcmc_abi_version(void) { return SGMCMC_ABI_VERSION; }
+int64_t sgmcmc_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
   if (!cfg || !out) return fail(SGMCMC_E_INVALID, "null argument");
@@ -287,7 +290,7 @@ int sgmcmc_set_data(sgmcmc_handle* h, const float* x, const void* y, void* strea
   const size_t total = n * h->DS;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 16);
   sg::pack_rows_kernel<<<blocks, 256, 0, s>>>(x, (const int*)y, h->rows, n, h->cfg.data_dim, h->DS, h->cfg.family);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
   h->vm.rows = h->rows;
   h->has_data = true;
   return SGMCMC_OK;
@@ -355,7 +358,7 @@ int sgmcmc_minibatch_indices(const uint32_t* key, int64_t n, int32_t batch, int3
   sg::Key k{key[0], key[1]};
   const unsigned h = ((unsigned)batch + 1u) >> 1;
   sg::indices_kernel<<<(h + 255) / 256, 256, 0, (cudaStream_t)stream>>>(k, (unsigned)n, (unsigned)batch, out);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
   return SGMCMC_OK;
 }
 
@@ -364,7 +367,7 @@ int sgmcmc_normal(const uint32_t* key, int32_t n, float* out, void* stream) {
   sg::Key k{key[0], key[1]};
   const int blocks = std::min((n + 255) / 256, 148 * 8);
   sg::normal_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(k, (unsigned)n, out);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
   return SGMCMC_OK;
 }
 
@@ -373,7 +376,7 @@ int sgmcmc_split(const uint32_t* key, int32_t num, uint32_t* out, void* stream) 
   sg::Key k{key[0], key[1]};
   const int blocks = std::min((2 * num + 255) / 256, 148 * 8);
   sg::split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(k, (unsigned)num, out);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
   return SGMCMC_OK;
 }
 
@@ -386,7 +389,7 @@ int sgmcmc_ksd_imq_partial(const float* x, const float* g, int32_t n, int32_t d,
   if (row1 == row0) return SGMCMC_OK;
   dim3 grid((n + sg::KSD_T - 1) / sg::KSD_T, (row1 - row0 + sg::KSD_T - 1) / sg::KSD_T);
   sg::ksd_simt_kernel<<<grid, 256, 0, s>>>(x, g, n, d, row0, row1, partial_sum);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
   return SGMCMC_OK;
 }
 

@@ -420,7 +420,8 @@ struct ChainCtx {
             ss = fmaf(v, v, ss);
           }
           alpha = alpha + cf.hh * (sqrtf(block_sum(ss, s.red)) - (float)D);
-          const float c1 = expf(-alpha * cf.h);
+          // correctly rounded fp32 exp: 1 - c1^2 amplifies a 1-ulp error of expf by ~1/(alpha h)
+          const float c1 = (float)exp((double)(-alpha * cf.h));
           const float c2 = (alpha == 0.0f) ? cf.ca : sqrtf(fabsf((1.0f - c1 * c1) / (2.0f * alpha)));
           ss = 0.f;
           for (int d = threadIdx.x; d < D; d += blockDim.x) {

@@ -82,7 +82,7 @@ def step_coefs(diffusion: str, hp: dict, schedule: Callable, i0: int, k: int) ->
             ca = np.sqrt(f32(2 * (hp["alpha"] - hp.get("beta", 0.0)) * dt))
             cb = np.sqrt(f32(dt))
         elif diffusion == "baoab":                                # diffusions.py:229-232
-            ca = np.exp(f32(-hp["gamma"] * dt))
+            ca = f32(np.exp(np.float64(f32(-hp["gamma"] * dt))))   # correctly rounded fp32 exp
             cb = f32(hp["tau"]) * np.sqrt(f32(1) - ca * ca)
         elif diffusion == "sgnht":                                # diffusions.py:273,283
             ca = np.sqrt(f32(2 * hp["a"] * dt))

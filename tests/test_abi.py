@@ -11,7 +11,7 @@ def declared_functions():
     names = []
     for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
         src = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
-        names += re.findall(r"\b(?:int|const char\*)\s+(sgmcmc_\w+)\s*\(", src)
+        names += re.findall(r"\b(?:int|int64_t|const char\*)\s+(sgmcmc_\w+)\s*\(", src)
     return sorted(set(names))
 
 
@@ -22,7 +22,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     assert os.path.exists(path)
     lib = ctypes.CDLL(path)
     fns = declared_functions()
-    assert len(fns) >= 14
+    assert len(fns) >= 15
     for name in fns:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     assert sorted(_native.EXPORTS) == fns
