@@ -165,6 +165,15 @@ int sgmcmc_split(const uint32_t* key, int32_t num, uint32_t* out, void* stream);
 int sgmcmc_ksd_imq_partial(const float* x, const float* g, int32_t n, int32_t d, int32_t row0,
                            int32_t row1, double* partial_sum, void* stream);
 
+/* Tensor-core (tcgen05, 3xTF32) variant of the same sum, sharded by Gram TILES instead of rows: the
+ * upper-triangular 128 x 128 tile list (k_0 is symmetric; off-diagonal tiles count twice) is dealt
+ * round-robin to `nparts` partitions and this call sums partition `part`.  The sum over all partitions
+ * is the sum over all n^2 ordered pairs.  workspace: device scratch of sgmcmc_ksd_workspace_bytes(n, d)
+ * bytes (centred / tf32-split operands, row terms), borrowed for the call. */
+int64_t sgmcmc_ksd_workspace_bytes(int32_t n, int32_t d);
+int sgmcmc_ksd_imq_tc(const float* x, const float* g, int32_t n, int32_t d, int32_t part, int32_t nparts,
+                      void* workspace, double* partial_sum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ FLAG_BADODABCV_REFERENCE_BUG = 1
 EXPORTS = [
     "sgmcmc_last_error", "sgmcmc_abi_version", "sgmcmc_launch_count", "sgmcmc_create", "sgmcmc_destroy", "sgmcmc_set_data",
     "sgmcmc_set_centering", "sgmcmc_fullbatch_grad", "sgmcmc_init", "sgmcmc_run", "sgmcmc_kernel_step",
-    "sgmcmc_minibatch_indices", "sgmcmc_normal", "sgmcmc_split", "sgmcmc_ksd_imq_partial",
+    "sgmcmc_minibatch_indices", "sgmcmc_normal", "sgmcmc_split", "sgmcmc_ksd_imq_partial", "sgmcmc_ksd_workspace_bytes", "sgmcmc_ksd_imq_tc",
 ]
 
 
@@ -88,7 +88,10 @@ def load(build_if_missing: bool = True):
         "sgmcmc_normal": [C.POINTER(C.c_uint32), i32, vp, vp],
         "sgmcmc_split": [C.POINTER(C.c_uint32), i32, vp, vp],
         "sgmcmc_ksd_imq_partial": [vp, vp, i32, i32, i32, i32, vp, vp],
+        "sgmcmc_ksd_imq_tc": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
     }
+    lib.sgmcmc_ksd_workspace_bytes.restype = i64
+    lib.sgmcmc_ksd_workspace_bytes.argtypes = [i32, i32]
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "ksd.cuh"
+#include "ksd_tc.cuh"
 #include "vec_sampler.cuh"
 
 namespace {
@@ -389,6 +390,55 @@ int sgmcmc_ksd_imq_partial(const float* x, const float* g, int32_t n, int32_t d,
   if (row1 == row0) return SGMCMC_OK;
   dim3 grid((n + sg::KSD_T - 1) / sg::KSD_T, (row1 - row0 + sg::KSD_T - 1) / sg::KSD_T);
   sg::ksd_simt_kernel<<<grid, 256, 0, s>>>(x, g, n, d, row0, row1, partial_sum);
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
+  return SGMCMC_OK;
+}
+
+int64_t sgmcmc_ksd_workspace_bytes(int32_t n, int32_t d) {
+  if (n <= 0 || d <= 0) return 0;
+  return (int64_t)sg::ksdtc::workspace_bytes(n, d);
+}
+
+int sgmcmc_ksd_imq_tc(const float* x, const float* g, int32_t n, int32_t d, int32_t part, int32_t nparts,
+                      void* workspace, double* partial_sum, void* stream) {
+  namespace kt = sg::ksdtc;
+  if (!x || !g || !workspace || !partial_sum || n <= 0 || d <= 0 || nparts <= 0 || part < 0 || part >= nparts)
+    return fail(SGMCMC_E_INVALID, "bad argument");
+  if (((uintptr_t)workspace & 255) != 0) return fail(SGMCMC_E_INVALID, "workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int dp = kt::padded_dim(d);
+  uint8_t* w = (uint8_t*)workspace;
+  float* Z = (float*)w;                       w += kt::align_up((size_t)n * 4 * dp * sizeof(float), 256);
+  float4* rt = (float4*)w;                    w += kt::align_up((size_t)n * sizeof(float4), 256);
+  double* sums = (double*)w;
+  CUDA_TRY(cudaMemsetAsync(partial_sum, 0, sizeof(double), s));
+  CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)2 * d * sizeof(double), s));
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  kt::colsum_kernel<<<std::min(n, sms * 8), 128, 0, s>>>(x, g, n, d, sums);
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
+  kt::split_kernel<<<(n + 7) / 8, 256, 0, s>>>(x, g, n, d, dp, sums, Z, rt);
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
+
+  kt::EncodeTiledFn encode = kt::encode_tiled_fn();
+  if (!encode) return fail(SGMCMC_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  CUtensorMap zmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)4 * dp, (cuuint64_t)n};
+  const cuuint64_t gstride[1] = {(cuuint64_t)4 * dp * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kt::KC, (cuuint32_t)kt::TILE};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = encode(&zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Z, gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(SGMCMC_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)cr));
+
+  const long long T = (n + kt::TILE - 1) / kt::TILE;
+  const long long total = T * (T + 1) / 2;
+  const long long n_local = total > part ? (total - part + nparts - 1) / nparts : 0;
+  if (n_local == 0) return SGMCMC_OK;
+  CUDA_TRY(cudaFuncSetAttribute(kt::ksd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt::SMEM_BYTES));
+  const int grid = (int)std::min<long long>(n_local, sms);
+  kt::ksd_tc_kernel<<<grid, kt::NUM_THREADS, kt::SMEM_BYTES, s>>>(zmap, rt, n, d, dp, part, nparts, partial_sum);
   CUDA_TRY(cudaGetLastError()); ++g_launches;
   return SGMCMC_OK;
 }

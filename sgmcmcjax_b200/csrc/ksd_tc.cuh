@@ -1,0 +1,388 @@
+// K3 (tensor-core variant): IMQ kernel Stein discrepancy as Gram contractions on tcgen05.
+//
+// ksd.py:7-37 with c = 1, beta = -1/2:   k0 = gg b^-1/2 + (gd + D) b^-3/2 - 3 dd b^-5/2,  b = 1 + dd
+//   dd = |x_i - x_j|^2 = xx_i + xx_j - 2 x_i.x_j
+//   gd = (g_i - g_j).(x_i - x_j) = gx_i + gx_j - (g_i.x_j + x_i.g_j)
+//   gg = g_i.g_j
+// k0 is symmetric in (i, j), so only tiles J >= I of the 128 x 128 tiling are computed and
+// off-diagonal tiles count twice (imq_KSD sums all N^2 ordered pairs, ksd.py:58-66).
+//
+// Numerics.  dd and gd depend on differences only, so samples and grads are centred by their
+// column means first (removes the catastrophic cancellation of xx_i + xx_j - 2 x_i.x_j for
+// tightly clustered posterior samples); gg is reconstructed as gc_i.gc_j + r_i + r_j with
+// r_i = mg.gc_i + |mg|^2 / 2.  Every dot product runs as 3xTF32: a = a_hi + a_lo with
+// a_hi = rna_tf32(a), a_lo = rna_tf32(a - a_hi);  a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi
+// (error ~2^-21 |a||b|, fp32 accumulation in TMEM).  The N^2 sum is accumulated in fp64.
+//
+// Operand matrix  Z[n][4][Dp]  fp32 (Dp = D rounded up to 8, zero padded), segments
+// 0 = xc_hi, 1 = xc_lo, 2 = gc_hi, 3 = gc_lo; row terms rt[n] = (xx, gx, r, |g|^2).
+// Exact diagonal: for i == j the reference has x_i - x_j = 0 exactly, k0 = |g_i|^2 + D; the 3xTF32 residual
+// (~1e-6 |x|^2 in dd) would otherwise be amplified by (gg/2 + 3D/2), so the diagonal uses dd = gd = 0, gg = |g_i|^2.
+// Per 128 x 128 tile and K-chunk of 16 columns, TMA brings the 4 row-side and 4 column-side
+// segment chunks into one 64 KB smem stage (64-byte swizzle, K-major); 12 segment products
+// (3 for x.x, 3 for g.g, 6 for the cross term) accumulate into three 128-column fp32
+// accumulators in TMEM.  Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc),
+// 2..5 = epilogue (tcgen05.ld -> IMQ formula -> fp64 partial sums).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace sg {
+namespace ksdtc {
+
+constexpr int TILE = 128;          // tile edge (rows I and rows J)
+constexpr int KC = 16;             // K-chunk (floats) per smem stage = 64 bytes = swizzle span
+constexpr int STAGES = 3;
+constexpr int CHUNK_BYTES = TILE * KC * 4;           // 8 KB per (segment, side) chunk
+constexpr int STAGE_BYTES = 8 * CHUNK_BYTES;         // 64 KB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;     // 3 accumulators x 128 columns = 384 -> next power of two
+constexpr int UMMA_K = 8;          // tf32: 32 bytes of K per instruction
+
+struct SmemTail {                  // after the stage buffers
+  uint64_t full[STAGES], empty[STAGES], tmem_full, tmem_empty;
+  uint32_t tmem_base;
+  uint32_t pad;
+  float4 colterm[2][TILE];
+};
+constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {   // ~4 s at 2 GHz
+      printf("ksd_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate, M = 128, N = 128, K = 8.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 64-byte-swizzled operand tile of TILE rows x 16 floats: row pitch 64 B, 8-row groups 512 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64))
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                    // leading byte offset: unused for swizzled K-major
+  d |= (uint64_t)(512 >> 4) << 32;           // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)4 << 61;                    // SWIZZLE_64B
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b format TF32 [7,10)/[10,13)=2, K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t IDESC_TF32_128x128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------------------------------ prep
+// Column sums of X and G in double: sums[0][d], sums[1][d].
+__global__ void colsum_kernel(const float* __restrict__ X, const float* __restrict__ G, int n, int d, double* sums) {
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    double sx = 0.0, sgr = 0.0;
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+      sx += (double)X[(size_t)r * d + c];
+      sgr += (double)G[(size_t)r * d + c];
+    }
+    atomicAdd(&sums[c], sx);
+    atomicAdd(&sums[d + c], sgr);
+  }
+}
+
+// One warp per row: centre, split into tf32 hi / lo, row terms.
+__global__ void split_kernel(const float* __restrict__ X, const float* __restrict__ G, int n, int d, int dp,
+                             const double* __restrict__ sums, float* __restrict__ Z, float4* __restrict__ rt) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const double inv_n = 1.0 / (double)n;
+  float xx = 0.f, gx = 0.f, r = 0.f, mm = 0.f, g2 = 0.f;
+  float* z = Z + (size_t)row * 4 * dp;
+  for (int c = lane; c < dp; c += 32) {
+    float xh = 0.f, xl = 0.f, gh = 0.f, gl = 0.f;
+    if (c < d) {
+      const float mx = (float)(sums[c] * inv_n), mg = (float)(sums[d + c] * inv_n);
+      const float xc = X[(size_t)row * d + c] - mx;
+      const float graw = G[(size_t)row * d + c];
+      const float gc = graw - mg;
+      g2 = fmaf(graw, graw, g2);
+      xh = tf32_rna(xc); xl = tf32_rna(xc - xh);
+      gh = tf32_rna(gc); gl = tf32_rna(gc - gh);
+      xx = fmaf(xc, xc, xx); gx = fmaf(gc, xc, gx); r = fmaf(mg, gc, r); mm = fmaf(mg, mg, mm);
+    }
+    z[c] = xh; z[dp + c] = xl; z[2 * dp + c] = gh; z[3 * dp + c] = gl;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    xx += __shfl_xor_sync(0xffffffffu, xx, o); gx += __shfl_xor_sync(0xffffffffu, gx, o);
+    r += __shfl_xor_sync(0xffffffffu, r, o);   mm += __shfl_xor_sync(0xffffffffu, mm, o);
+    g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+  }
+  if (lane == 0) rt[row] = make_float4(xx, gx, r + 0.5f * mm, g2);
+}
+
+// ------------------------------------------------------------------------------------------ tiles
+// Upper-triangular tile list, row-major: t -> (I, J >= I) with T tiles per side.
+__device__ __forceinline__ void tile_of(long long t, int T, int& I, int& J) {
+  // row I starts at S(I) = I*T - I*(I-1)/2
+  const double tt = (double)T + 0.5;
+  int i = (int)(tt - sqrt(tt * tt - 2.0 * (double)t));
+  if (i < 0) i = 0;
+  if (i > T - 1) i = T - 1;
+  auto start = [T](int ii) { return (long long)ii * T - (long long)ii * (ii - 1) / 2; };
+  while (i > 0 && start(i) > t) --i;
+  while (i < T - 1 && start(i + 1) <= t) ++i;
+  I = i;
+  J = i + (int)(t - start(i));
+}
+
+__device__ __forceinline__ float imq_k0_tc(float dd, float gg, float gd, float dim) {
+  const float b = 1.0f + dd;
+  const float r = rsqrtf(b);
+  const float r2 = r * r;
+  const float r3 = r2 * r;
+  return gg * r + (gd + dim) * r3 - 3.0f * dd * r3 * r2;
+}
+
+// product table: (accumulator, row-side segment, column-side segment); segments 0 xh, 1 xl, 2 gh, 3 gl
+__constant__ int8_t PROD[12][3] = {
+    {0, 0, 0}, {0, 0, 1}, {0, 1, 0},                                  // x.x
+    {1, 2, 2}, {1, 2, 3}, {1, 3, 2},                                  // g.g
+    {2, 2, 0}, {2, 2, 1}, {2, 3, 0}, {2, 0, 2}, {2, 0, 3}, {2, 1, 2}  // g_i.x_j + x_i.g_j
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict__ rt, int n, int d, int dp,
+              int part, int nparts, double* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int T = (n + TILE - 1) / TILE;
+  const long long total = (long long)T * (T + 1) / 2;
+  // tiles of this partition: g = part + nparts * u, u = 0 .. n_local-1; this CTA takes u = blockIdx.x + k * gridDim.x
+  const long long n_local = total > part ? (total - part + nparts - 1) / nparts : 0;
+  const int n_chunks = (dp + KC - 1) / KC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
+    mbar_init(&tail->tmem_full, 1);
+    mbar_init(&tail->tmem_empty, 4);       // one arrival per epilogue warp
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(&tail->tmem_base, TMEM_COLS); tmem_relinquish(); }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&zmap);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long u = blockIdx.x; u < n_local; u += gridDim.x) {
+        int I, J;
+        tile_of(part + (long long)nparts * u, T, I, J);
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(&tail->empty[stage], phase ^ 1);
+          uint8_t* sbase = smem + (size_t)stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&tail->full[stage], STAGE_BYTES);
+#pragma unroll
+          for (int seg = 0; seg < 4; ++seg) {
+            tma_load_2d(sbase + seg * CHUNK_BYTES, &zmap, seg * dp + c * KC, I * TILE, &tail->full[stage]);
+            tma_load_2d(sbase + (4 + seg) * CHUNK_BYTES, &zmap, seg * dp + c * KC, J * TILE, &tail->full[stage]);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc_phase = 0;
+      for (long long u = blockIdx.x; u < n_local; u += gridDim.x) {
+        mbar_wait(&tail->tmem_empty, acc_phase ^ 1);
+        tc_fence_after();
+        uint32_t started = 0;                                  // bit a set once accumulator a holds data
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(&tail->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const int valid = min(KC, dp - c * KC);              // dp is a multiple of 8
+          const int slices = valid / UMMA_K;
+#pragma unroll
+          for (int p = 0; p < 12; ++p) {
+            const int a = PROD[p][0];
+            const uint64_t da = make_desc_sw64(sbase + PROD[p][1] * CHUNK_BYTES);
+            const uint64_t db = make_desc_sw64(sbase + (4 + PROD[p][2]) * CHUNK_BYTES);
+            for (int k = 0; k < slices; ++k) {
+              // advancing K inside the swizzle atom = +32 bytes on the start address (>>4 => +2)
+              umma_tf32(tmem_base + a * TILE, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_TF32_128x128,
+                        (started >> a) & 1u);
+              started |= 1u << a;
+            }
+          }
+          tc_commit(&tail->empty[stage]);                      // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tail->tmem_full);                           // accumulators complete
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    const int et = threadIdx.x - 64;                           // 0..127
+    const float dim = (float)d;
+    double acc = 0.0;
+    uint32_t acc_phase = 0;
+    int buf = 0;
+    for (long long u = blockIdx.x; u < n_local; u += gridDim.x) {
+      int I, J;
+      tile_of(part + (long long)nparts * u, T, I, J);
+      const int gi = I * TILE + row_in_tile;
+      const int gjc = J * TILE + et;
+      tail->colterm[buf][et] = gjc < n ? rt[gjc] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 ri = gi < n ? rt[gi] : make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // colterm[buf] visible to the 4 epilogue warps
+      mbar_wait(&tail->tmem_full, acc_phase);
+      tc_fence_after();
+      float tsum = 0.f;
+      const bool diag_tile = I == J;
+      const int jmax = min(TILE, n - J * TILE);
+      const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int cb = 0; cb < TILE; cb += 16) {
+        uint32_t p1[16], p2[16], p3[16];
+        tmem_ld16(tl + cb, p1);
+        tmem_ld16(tl + TILE + cb, p2);
+        tmem_ld16(tl + 2 * TILE + cb, p3);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float4 cj = tail->colterm[buf][cb + e];
+          float dd = fmaf(-2.0f, __uint_as_float(p1[e]), ri.x + cj.x);
+          float gg = __uint_as_float(p2[e]) + (ri.z + cj.z);
+          float gd = (ri.y + cj.y) - __uint_as_float(p3[e]);
+          if (diag_tile && cb + e == row_in_tile) { dd = 0.f; gd = 0.f; gg = ri.w; }   // i == j: exact
+          const float k0 = imq_k0_tc(dd, gg, gd, dim);
+          tsum += (gi < n && cb + e < jmax) ? k0 : 0.f;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->tmem_empty);           // accumulators may be overwritten
+      acc += (double)tsum * (I == J ? 1.0 : 2.0);
+      acc_phase ^= 1;
+      buf ^= 1;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0 && acc != 0.0) atomicAdd(out, acc);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------ host
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int padded_dim(int d) { return (d + 7) & ~7; }
+// workspace: Z [n][4][dp] floats | row terms [n] float4 | column sums [2 d] doubles
+inline size_t workspace_bytes(int n, int d) {
+  const size_t dp = padded_dim(d);
+  return align_up((size_t)n * 4 * dp * sizeof(float), 256) + align_up((size_t)n * sizeof(float4), 256) +
+         align_up((size_t)2 * d * sizeof(double), 256);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace ksdtc
+}  // namespace sg

@@ -22,7 +22,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     assert os.path.exists(path)
     lib = ctypes.CDLL(path)
     fns = declared_functions()
-    assert len(fns) >= 15
+    assert len(fns) >= 17
     for name in fns:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     assert sorted(_native.EXPORTS) == fns

@@ -495,16 +495,44 @@ def test_logreg_c2_shape_size_independent_properties(cuda):
 
 
 # ------------------------------------------------------------------------------ KSD
-@pytest.mark.parametrize("n,d", [(1, 3), (17, 1), (64, 100), (200, 100), (333, 7), (1000, 100)])
-def test_ksd_matches_fp64_literal(cuda, n, d):
+def ksd_case(n, d, kind="posterior"):
+    rng = np.random.default_rng(n * 1000 + d)
+    if kind == "posterior":          # tightly clustered samples far from the origin, gradients ~ -precision * (x - mode)
+        X = (0.05 * rng.normal(size=(n, d)) + 1.0).astype(np.float32)
+        G = (-(X - 1.0) / 0.0025 * 1e-2 + 0.1 * rng.normal(size=(n, d))).astype(np.float32)
+    elif kind == "logreg":           # posterior sd ~1e-3 around |theta| ~ 3, gradients O(1e2) with a common offset
+        X = (3.0 * rng.normal(size=(1, d)) + 1e-3 * rng.normal(size=(n, d))).astype(np.float32)
+        G = (-1e5 * (X - X.mean(0)) + 30.0 + 50.0 * rng.normal(size=(n, d))).astype(np.float32)
+    else:                            # spread-out samples, dd >> 1
+        X = rng.normal(size=(n, d)).astype(np.float32) * 3.0
+        G = (-X + rng.normal(size=(n, d))).astype(np.float32)
+    return X, G
+
+
+@pytest.mark.parametrize("method", ["tc", "simt"])
+@pytest.mark.parametrize("n,d", [(1, 3), (17, 1), (64, 100), (129, 100), (200, 100), (333, 7), (1000, 100), (700, 260)])
+@pytest.mark.parametrize("kind", ["posterior", "logreg", "wide"])
+def test_ksd_matches_fp64_literal(cuda, n, d, kind, method):
     from sgmcmcjax_b200 import ksd as NKSD
 
-    rng = np.random.default_rng(n * 1000 + d)
-    X = (0.05 * rng.normal(size=(n, d)) + 1.0).astype(np.float32)
-    G = (-(X - 1.0) / 0.0025 * 1e-2 + 0.1 * rng.normal(size=(n, d))).astype(np.float32)
+    X, G = ksd_case(n, d, kind)
     ref = OK.imq_ksd_literal(X, G)
-    got = float(NKSD.imq_KSD(X, G))
+    got = float(NKSD.imq_KSD(X, G, method=method))
     assert abs(got - ref) <= 1e-4 * abs(ref), (got, ref)
+
+
+def test_ksd_tc_tile_partitions_sum_to_whole(cuda):
+    from sgmcmcjax_b200 import ksd as NKSD
+
+    X, G = ksd_case(1100, 100)
+    whole = float(NKSD.imq_KSD_tiles(X, G, 0, 1).cpu()[0])
+    for nparts in (2, 3, 8, 64):
+        parts = sum(float(NKSD.imq_KSD_tiles(X, G, p, nparts).cpu()[0]) for p in range(nparts))
+        assert abs(whole - parts) <= 1e-9 * abs(whole)
+    ref = float(OK.imq_ksd_sum(X, G))
+    assert abs(whole - ref) <= 2e-4 * abs(ref)
+    simt = float(NKSD.imq_KSD_partial(X, G, 0, 1100).cpu()[0])
+    assert abs(whole - simt) <= 2e-4 * abs(ref)
 
 
 def test_ksd_row_blocks_sum_to_whole_and_golden(cuda):
