@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SGMCMC_ABI_VERSION 1
+#define SGMCMC_ABI_VERSION 2
 
 enum { SGMCMC_OK = 0, SGMCMC_E_INVALID = -1, SGMCMC_E_UNSUPPORTED = -2, SGMCMC_E_CUDA = -3,
        SGMCMC_E_STATE = -4 };
@@ -70,6 +70,10 @@ typedef struct sgmcmc_config {
                                              logreg: prior_coef[0] = prior precision (0.1)      */
   float hyper[4];             /* psgld {alpha, eps}; sgldAdam {beta1, beta2, eps};
                                  sghmc {alpha}; sgnht {a}; badodab {a}                          */
+  int32_t dims[8];            /* pmf: {n_users, n_items, rank}, leaves (U[n_users, rank], V[n_items, rank]),
+                                 lik_coef[0] = alpha (rating precision), prior_coef[0] = lambda;
+                                 mlp: {n_layers, size_0, ..., size_L}, leaves (W_1[size_1, size_0], b_1, ...),
+                                 prior_coef[0] = prior precision (1 for NN_model.py:53-58)          */
 } sgmcmc_config;
 
 /* kernels.py:457-460: build_badodabCV_kernel binds both palindrome halves to badodab's
@@ -115,10 +119,12 @@ int64_t sgmcmc_launch_count(void);
 int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out);
 int sgmcmc_destroy(sgmcmc_handle* h);
 
-/* Ingest the data tuple (gradient_estimation.py:25-29).  x: device f32 [n_data, data_dim]
- * row-major.  y: device, NULL for 1-tuples; logreg: int32 [n_data] in {0,1}.  The rows are
- * re-laid-out into the handle's own HBM table (see DESIGN.md "data layout"). */
-int sgmcmc_set_data(sgmcmc_handle* h, const float* x, const void* y, void* stream);
+/* Ingest the data tuple (gradient_estimation.py:25-29).  x: device [n_data, data_dim] row-major,
+ * f32 (gaussian_mean, logreg, mlp) or int32 (pmf: (user, item) pairs, data_dim = 2).
+ * y: device, NULL for 1-tuples; logreg: int32 [n_data] in {0,1}; mlp: f32 [n_data, size_L];
+ * pmf: f32 [n_data] ratings.  The rows are re-laid-out into the handle's own HBM table
+ * (see DESIGN.md "data layout"). */
+int sgmcmc_set_data(sgmcmc_handle* h, const void* x, const void* y, void* stream);
 
 /* CV centring value (gradient_estimation.py:50-72): theta_hat device f32 [P]; the full-batch
  * gradient at theta_hat is computed here (gradient_estimation.py:70). */

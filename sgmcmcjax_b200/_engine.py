@@ -54,7 +54,12 @@ def keys_to_device(key):
 
 
 class Engine:
-    """One model (family + data + estimator + diffusion) bound to a native handle."""
+    """One model (family + data + estimator + diffusion) bound to a native handle.
+
+    Vector families (gaussian_mean, logreg) know their parameter geometry from the data, so the
+    handle exists after construction.  For the big families (bayesian_mlp, pmf) the leaf shapes are
+    only known once a parameter pytree is seen (``centering_value`` at build time, else the first
+    ``init_fn`` / ``sampler`` call): the handle is created then and is fixed afterwards."""
 
     def __init__(self, diffusion: str, dt, loglikelihood: Callable, logprior: Callable, data, batch_size: int,
                  estimator: str = "standard", centering_value=None, update_rate: Optional[int] = None,
@@ -72,43 +77,65 @@ class Engine:
         self.schedule = make_schedule(dt)
         self.hp = dict(hyper or {})
         self.leapfrog = int(leapfrog)
-        x = to_device(data[0], torch.float32)
+        self.update_rate, self.flags = int(update_rate or 0), int(flags)
+        dts = [getattr(torch, n) for n in self.spec.data_dtypes()]
+        self._data = [to_device(a, dt_) for a, dt_ in zip(data, dts)]
+        x = self._data[0]
         if x.dim() != 2:
             raise ValueError("data[0] must be [N, D]")
         self.n_data, self.data_dim = int(x.shape[0]), int(x.shape[1])
-        y = to_device(data[1], torch.int32) if len(data) == 2 else None
-        if y is not None and y.shape[0] != self.n_data:
+        if len(self._data) == 2 and self._data[1].shape[0] != self.n_data:
             raise ValueError("data arrays must share their leading dimension")
         self.batch = self.n_data if batch_size is None else int(batch_size)
-        n_leaves = max(len(self.spec.lik_coef), 1)
-        self.n_leaves, self.leaf_size = n_leaves, [self.data_dim] * n_leaves
+        self._handle = C.c_void_p(0)
+        self._coef_cache = {}
+        self.leaf_shapes = None
+        self._centering_value = centering_value
+        if self.spec.vector:
+            n_leaves = max(len(self.spec.lik_coef), 1)
+            self._bind([(self.data_dim,)] * n_leaves)
+        elif estimator == "cv":
+            self.flatten_params(centering_value, broadcast_chains=None)   # binds from the centre's shapes
+        torch.cuda.current_stream().synchronize()                 # inputs may be freed by the caller now
+
+    def _bind(self, leaf_shapes):
+        """Create the native handle for a parameter geometry and ingest data (+ CV centre)."""
+        shapes = [tuple(int(d) for d in s) for s in leaf_shapes]
+        if not 1 <= len(shapes) <= _native.MAX_LEAVES:
+            raise TypeError(f"parameter pytrees need 1..{_native.MAX_LEAVES} leaves")
+        dims = self.spec.geometry(shapes, [tuple(d.shape) for d in self._data])   # raises before any state changes
+        self.leaf_shapes, self.n_leaves = shapes, len(shapes)
+        self.leaf_size = [int(np.prod(s)) for s in self.leaf_shapes]
         self.P = sum(self.leaf_size)
 
         cfg = _native.Config()
         cfg.abi_version = _native.ABI_VERSION
-        cfg.family, cfg.estimator, cfg.diffusion = self.spec.family, _EST[estimator], DIFFUSION_IDS[diffusion]
-        cfg.n_data, cfg.batch, cfg.n_leaves, cfg.data_dim = self.n_data, self.batch, n_leaves, self.data_dim
+        cfg.family, cfg.estimator = self.spec.family, _EST[self.estimator]
+        cfg.diffusion = DIFFUSION_IDS[self.diffusion]
+        cfg.n_data, cfg.batch, cfg.n_leaves, cfg.data_dim = self.n_data, self.batch, self.n_leaves, self.data_dim
         for l, s in enumerate(self.leaf_size):
             cfg.leaf_size[l] = s
-        cfg.leapfrog, cfg.update_rate, cfg.flags = self.leapfrog, int(update_rate or 0), int(flags)
+        cfg.leapfrog, cfg.update_rate, cfg.flags = self.leapfrog, self.update_rate, self.flags
         for l, a in enumerate(self.spec.lik_coef):
             cfg.lik_coef[l] = a
         for l, c in enumerate(self.spec.prior_coef):
             cfg.prior_coef[l] = c
+        for k, v in enumerate(dims):
+            cfg.dims[k] = int(v)
         order = {"psgld": ("alpha", "eps"), "sgldAdam": ("beta1", "beta2", "eps"), "sghmc": ("alpha",),
-                 "sgnht": ("a",), "badodab": ("a",)}.get(diffusion, ())
+                 "sgnht": ("a",), "badodab": ("a",)}.get(self.diffusion, ())
         for k, name in enumerate(order):
             cfg.hyper[k] = float(self.hp[name])
-        self._handle = C.c_void_p(0)
         _native.check(self.lib.sgmcmc_create(C.byref(cfg), C.byref(self._handle)))
-        _native.check(self.lib.sgmcmc_set_data(self._handle, _vp(x), _vp(y), self._stream()))
-        if estimator == "cv":
-            center = self.flatten_params(centering_value, broadcast_chains=None)[0]
+        y = self._data[1] if len(self._data) == 2 else None
+        _native.check(self.lib.sgmcmc_set_data(self._handle, _vp(self._data[0]), _vp(y), self._stream()))
+        if self.spec.vector:
+            self._data = None                                     # the handle owns its re-laid-out copy
+        if self.estimator == "cv":
+            center = self.flatten_params(self._centering_value, broadcast_chains=None)[0]
             if center.shape[0] != 1:
                 raise ValueError("centering_value must be a single parameter pytree")
             _native.check(self.lib.sgmcmc_set_centering(self._handle, _vp(center), self._stream()))
-        self._coef_cache = {}
-        torch.cuda.current_stream().synchronize()                 # inputs may be freed by the caller now
 
     def __del__(self):
         try:
@@ -126,13 +153,24 @@ class Engine:
 
     # ---- parameter pytrees <-> flat [C, P] -------------------------------------------------
     def flatten_params(self, params, broadcast_chains):
-        """-> (flat CUDA f32 [C, P], treedef, batched).  Leaves are [D] (one chain) or [C, D]."""
+        """-> (flat CUDA f32 [C, P], treedef, batched).  A leaf with one axis more than its
+        per-chain rank is multi-chain ([C, *leaf_shape])."""
         torch = _native.require_cuda()
         leaves, treedef = _tree.flatten(params)
-        if len(leaves) != self.n_leaves:
-            raise TypeError(f"parameter pytree has {len(leaves)} leaves, the model expects {self.n_leaves}")
         ts = [to_device(l, torch.float32) for l in leaves]
-        batched = ts[0].dim() == 2
+        ranks = self.spec.leaf_ndims(len(ts))
+        if len(ranks) != len(ts) or any(t.dim() not in (r, r + 1) for t, r in zip(ts, ranks)):
+            raise TypeError(f"parameter pytree does not fit the {self.spec.name} family")
+        batched = ts[0].dim() == ranks[0] + 1
+        if any((t.dim() == r + 1) != batched for t, r in zip(ts, ranks)):
+            raise TypeError("either every parameter leaf carries a chain axis or none does")
+        shapes = [tuple(t.shape[1:] if batched else t.shape) for t in ts]
+        if self.leaf_shapes is None:
+            self._bind(shapes)
+        if len(shapes) != self.n_leaves:
+            raise TypeError(f"parameter pytree has {len(shapes)} leaves, the model expects {self.n_leaves}")
+        if shapes != self.leaf_shapes:                            # diffusion_util.py:58-64 raises TypeError too
+            raise TypeError(f"parameter leaf shapes {shapes} do not match the model's {self.leaf_shapes}")
         ts = [t.reshape(-1, s) for t, s in zip(ts, self.leaf_size)]
         flat = torch.cat(ts, dim=1).contiguous()
         if broadcast_chains is not None and flat.shape[0] == 1 and broadcast_chains > 1:
@@ -140,10 +178,10 @@ class Engine:
         return flat, treedef, batched
 
     def unflatten_params(self, flat, treedef, lead_shape):
-        """flat [..., P] -> pytree with leaves [*lead_shape, D]."""
+        """flat [..., P] -> pytree with leaves [*lead_shape, *leaf_shape]."""
         leaves, off = [], 0
-        for s in self.leaf_size:
-            leaves.append(flat[..., off:off + s].reshape(*lead_shape, s))
+        for s, shp in zip(self.leaf_size, self.leaf_shapes):
+            leaves.append(flat[..., off:off + s].reshape(*lead_shape, *shp))
             off += s
         return _tree.unflatten(treedef, leaves)
 

@@ -11,7 +11,7 @@ import os
 from . import _build
 
 MAX_LEAVES = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FAMILY_GAUSSIAN_MEAN, FAMILY_LOGREG, FAMILY_MLP, FAMILY_PMF = 0, 1, 2, 3
 EST_STANDARD, EST_CV, EST_SVRG = 0, 1, 2
@@ -32,6 +32,7 @@ class Config(C.Structure):
         ("leaf_size", C.c_int32 * MAX_LEAVES), ("data_dim", C.c_int32), ("leapfrog", C.c_int32),
         ("update_rate", C.c_int32), ("flags", C.c_int32),
         ("lik_coef", C.c_float * MAX_LEAVES), ("prior_coef", C.c_float * MAX_LEAVES), ("hyper", C.c_float * 4),
+        ("dims", C.c_int32 * 8),
     ]
 
 

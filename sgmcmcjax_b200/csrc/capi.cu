@@ -6,8 +6,10 @@
 #include <string>
 #include <vector>
 
+#include "big_sampler.cuh"
 #include "ksd.cuh"
 #include "ksd_tc.cuh"
+#include "mlp_grad.cuh"
 #include "vec_sampler.cuh"
 
 namespace {
@@ -34,6 +36,10 @@ int env_int(const char* name, int dflt) {
 struct sgmcmc_handle {
   sgmcmc_config cfg;
   sg::VecModel vm;
+  sg::BigModel bm;             // families with parameters in global memory (pmf, mlp)
+  bool big = false;
+  void* data0 = nullptr;       // owned (big families)
+  void* data1 = nullptr;       // owned (big families)
   int P = 0, DS = 0, nch = 1;
   float* rows = nullptr;       // owned: [n_data][DS]
   float* cv_center = nullptr;  // owned: [P]
@@ -60,6 +66,12 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, const int* __restr
     }
     rows[t] = v;
   }
+}
+
+// pmf: (ij[n][2], y[n]) -> int4 {i, j, bits(y), 0}
+__global__ void pack_ratings_kernel(const int* __restrict__ ij, const float* __restrict__ y, int4* __restrict__ out, size_t n) {
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
+    out[t] = make_int4(ij[2 * t], ij[2 * t + 1], __float_as_int(y[t]), 0);
 }
 
 // K2 stage 1: CTA (split, m) sums its row range at thetas[m] into partial[m][split][DS].
@@ -170,6 +182,22 @@ int dispatch_vec(const sgmcmc_handle* h, const sg::VecRun& run, cudaStream_t str
   return fail(SGMCMC_E_UNSUPPORTED, "family not implemented by this build");
 }
 
+template <int FAMILY>
+int launch_big(const sgmcmc_handle* h, const sg::BigRun& run, int blocks, cudaStream_t stream) {
+  auto kern = sg::big_sampler_kernel<FAMILY>;
+  const size_t smem = ((sizeof(sg::BigSmem) + 127) & ~(size_t)127) + sg::FamilyGrad<FAMILY>::smem_bytes(h->bm);
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<blocks, sg::BigThreads<FAMILY>::value, smem, stream>>>(h->bm, run);
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
+  return SGMCMC_OK;
+}
+
+int dispatch_big(const sgmcmc_handle* h, const sg::BigRun& run, int blocks, cudaStream_t stream) {
+  if (h->cfg.family == SGMCMC_FAMILY_PMF) return launch_big<SGMCMC_FAMILY_PMF>(h, run, blocks, stream);
+  if (h->cfg.family == SGMCMC_FAMILY_MLP) return launch_big<SGMCMC_FAMILY_MLP>(h, run, blocks, stream);
+  return fail(SGMCMC_E_UNSUPPORTED, "family not implemented by this build");
+}
+
 int check_state(const sgmcmc_handle* h, const sgmcmc_state* st) {
   if (!h || !st) return fail(SGMCMC_E_INVALID, "null handle or state");
   if (!h->has_data) return fail(SGMCMC_E_STATE, "sgmcmc_set_data has not been called");
@@ -228,20 +256,61 @@ int64_t sgmcmc_launch_count(void) { return (int64_t)g_launches.load(); }
 int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
   if (!cfg || !out) return fail(SGMCMC_E_INVALID, "null argument");
   if (cfg->abi_version != SGMCMC_ABI_VERSION) return fail(SGMCMC_E_INVALID, "ABI version mismatch");
-  if (cfg->family != SGMCMC_FAMILY_GAUSSIAN_MEAN && cfg->family != SGMCMC_FAMILY_LOGREG)
-    return fail(SGMCMC_E_UNSUPPORTED, "family not implemented by this build (gaussian_mean, logreg)");
+  if (cfg->family < SGMCMC_FAMILY_GAUSSIAN_MEAN || cfg->family > SGMCMC_FAMILY_PMF)
+    return fail(SGMCMC_E_UNSUPPORTED, "unknown model family");
   if (cfg->estimator < 0 || cfg->estimator > SGMCMC_EST_SVRG) return fail(SGMCMC_E_INVALID, "bad estimator");
   if (cfg->diffusion < 0 || cfg->diffusion > SGMCMC_DIFF_BADODAB) return fail(SGMCMC_E_INVALID, "bad diffusion");
   if (cfg->n_data <= 0 || cfg->n_data > 0x7fffffffLL) return fail(SGMCMC_E_INVALID, "n_data out of range");
   if (cfg->batch <= 0) return fail(SGMCMC_E_INVALID, "batch must be positive");
   if (cfg->n_leaves < 1 || cfg->n_leaves > SGMCMC_MAX_LEAVES) return fail(SGMCMC_E_INVALID, "n_leaves out of range");
   if (cfg->data_dim < 1) return fail(SGMCMC_E_INVALID, "data_dim must be positive");
+  if (cfg->diffusion == SGMCMC_DIFF_SGHMC && cfg->leapfrog < 1) return fail(SGMCMC_E_INVALID, "sghmc needs leapfrog >= 1");
+  if (cfg->estimator == SGMCMC_EST_SVRG && cfg->update_rate < 1) return fail(SGMCMC_E_INVALID, "SVRG needs update_rate >= 1");
+  if (cfg->family == SGMCMC_FAMILY_PMF || cfg->family == SGMCMC_FAMILY_MLP) {
+    long long P = 0;
+    for (int l = 0; l < cfg->n_leaves; ++l) {
+      if (cfg->leaf_size[l] < 1) return fail(SGMCMC_E_INVALID, "leaf sizes must be positive");
+      P += cfg->leaf_size[l];
+    }
+    if (P > 0x7fffffffLL) return fail(SGMCMC_E_INVALID, "parameter vector too large");
+    if (cfg->family == SGMCMC_FAMILY_PMF) {
+      const int nu = cfg->dims[0], ni = cfg->dims[1], r = cfg->dims[2];
+      if (cfg->n_leaves != 2 || nu < 1 || ni < 1 || r < 1 || cfg->leaf_size[0] != nu * r || cfg->leaf_size[1] != ni * r)
+        return fail(SGMCMC_E_INVALID, "pmf needs leaves (U[n_users, rank], V[n_items, rank]) and dims {n_users, n_items, rank}");
+      if (cfg->data_dim != 2) return fail(SGMCMC_E_INVALID, "pmf data[0] is int32 [n, 2]");
+    } else {
+      const char* err = sg::mlp_validate(cfg);
+      if (err) return fail(SGMCMC_E_INVALID, err);
+    }
+    sgmcmc_handle* h = new sgmcmc_handle();
+    h->cfg = *cfg;
+    h->big = true;
+    h->P = (int)P;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+      int sms = 0;
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) h->num_sms = sms;
+    }
+    sg::BigModel& bm = h->bm;
+    std::memset(&bm, 0, sizeof(bm));
+    bm.family = cfg->family; bm.estimator = cfg->estimator; bm.diffusion = cfg->diffusion; bm.flags = cfg->flags;
+    bm.n_leaves = cfg->n_leaves; bm.P = h->P;
+    for (int l = 0; l < cfg->n_leaves; ++l) bm.leaf_off[l + 1] = bm.leaf_off[l] + cfg->leaf_size[l];
+    bm.n_data = (unsigned)cfg->n_data; bm.batch = (unsigned)cfg->batch;
+    bm.full_batch = (cfg->estimator == SGMCMC_EST_STANDARD && (int64_t)cfg->batch == cfg->n_data) ? 1 : 0;
+    bm.leapfrog = cfg->leapfrog; bm.update_rate = cfg->update_rate;
+    bm.scale = (float)cfg->n_data / (float)cfg->batch;
+    for (int k = 0; k < 4; ++k) bm.hyper[k] = cfg->hyper[k];
+    for (int k = 0; k < 8; ++k) bm.dims[k] = cfg->dims[k];
+    bm.coef[0] = cfg->lik_coef[0];
+    bm.coef[1] = cfg->prior_coef[0];
+    *out = h;
+    return SGMCMC_OK;
+  }
   for (int l = 0; l < cfg->n_leaves; ++l)
     if (cfg->leaf_size[l] != cfg->data_dim)
       return fail(SGMCMC_E_INVALID, "vector families need every leaf to have data_dim elements");
   if (cfg->family == SGMCMC_FAMILY_LOGREG && cfg->n_leaves != 1) return fail(SGMCMC_E_INVALID, "logreg has one leaf");
-  if (cfg->diffusion == SGMCMC_DIFF_SGHMC && cfg->leapfrog < 1) return fail(SGMCMC_E_INVALID, "sghmc needs leapfrog >= 1");
-  if (cfg->estimator == SGMCMC_EST_SVRG && cfg->update_rate < 1) return fail(SGMCMC_E_INVALID, "SVRG needs update_rate >= 1");
 
   sgmcmc_handle* h = new sgmcmc_handle();
   h->cfg = *cfg;
@@ -275,6 +344,8 @@ int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
 int sgmcmc_destroy(sgmcmc_handle* h) {
   if (!h) return SGMCMC_OK;
   if (h->rows) cudaFree(h->rows);
+  if (h->data0) cudaFree(h->data0);
+  if (h->data1) cudaFree(h->data1);
   if (h->cv_center) cudaFree(h->cv_center);
   if (h->cv_grad) cudaFree(h->cv_grad);
   if (h->partial) cudaFree(h->partial);
@@ -282,11 +353,32 @@ int sgmcmc_destroy(sgmcmc_handle* h) {
   return SGMCMC_OK;
 }
 
-int sgmcmc_set_data(sgmcmc_handle* h, const float* x, const void* y, void* stream) {
-  if (!h || !x) return fail(SGMCMC_E_INVALID, "null argument");
-  if (h->cfg.family == SGMCMC_FAMILY_LOGREG && !y) return fail(SGMCMC_E_INVALID, "logreg needs the label array");
+int sgmcmc_set_data(sgmcmc_handle* h, const void* xv, const void* y, void* stream) {
+  if (!h || !xv) return fail(SGMCMC_E_INVALID, "null argument");
+  if (h->cfg.family != SGMCMC_FAMILY_GAUSSIAN_MEAN && !y) return fail(SGMCMC_E_INVALID, "this family needs a second data array");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)h->cfg.n_data;
+  if (h->cfg.family == SGMCMC_FAMILY_PMF) {
+    if (!h->data0) CUDA_TRY(cudaMalloc(&h->data0, n * sizeof(int4)));
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->num_sms * 16);
+    sg::pack_ratings_kernel<<<blocks, 256, 0, s>>>((const int*)xv, (const float*)y, (int4*)h->data0, n);
+    CUDA_TRY(cudaGetLastError()); ++g_launches;
+    h->bm.data0 = h->data0;
+    h->has_data = true;
+    return SGMCMC_OK;
+  }
+  if (h->cfg.family == SGMCMC_FAMILY_MLP) {
+    const size_t b0 = n * (size_t)h->cfg.dims[1] * sizeof(float);
+    const size_t b1 = n * (size_t)h->cfg.dims[1 + h->cfg.dims[0]] * sizeof(float);
+    if (!h->data0) CUDA_TRY(cudaMalloc(&h->data0, b0));
+    if (!h->data1) CUDA_TRY(cudaMalloc(&h->data1, b1));
+    CUDA_TRY(cudaMemcpyAsync(h->data0, xv, b0, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->data1, y, b1, cudaMemcpyDeviceToDevice, s));
+    h->bm.data0 = h->data0; h->bm.data1 = h->data1;
+    h->has_data = true;
+    return SGMCMC_OK;
+  }
+  const float* x = (const float*)xv;
   if (!h->rows) CUDA_TRY(cudaMalloc(&h->rows, n * h->DS * sizeof(float)));
   const size_t total = n * h->DS;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 16);
@@ -301,6 +393,11 @@ int sgmcmc_fullbatch_grad(sgmcmc_handle* h, const float* thetas, int32_t m, floa
   if (!h || !thetas || !out || m < 1) return fail(SGMCMC_E_INVALID, "bad argument");
   if (!h->has_data) return fail(SGMCMC_E_STATE, "sgmcmc_set_data has not been called");
   cudaStream_t s = (cudaStream_t)stream;
+  if (h->big) {
+    sg::BigRun run{};
+    run.mode = 3; run.fg_thetas = thetas; run.fg_out = out;
+    return dispatch_big(h, run, m, s);
+  }
   if (h->cfg.family == SGMCMC_FAMILY_GAUSSIAN_MEAN) return fullgrad_impl<SGMCMC_FAMILY_GAUSSIAN_MEAN>(h, thetas, m, out, s);
   return fullgrad_impl<SGMCMC_FAMILY_LOGREG>(h, thetas, m, out, s);
 }
@@ -316,6 +413,8 @@ int sgmcmc_set_centering(sgmcmc_handle* h, const float* theta_hat, void* stream)
   if (rc != SGMCMC_OK) return rc;
   h->vm.cv_center = h->cv_center;
   h->vm.cv_grad = h->cv_grad;
+  h->bm.cv_center = h->cv_center;
+  h->bm.cv_grad = h->cv_grad;
   h->has_center = true;
   return SGMCMC_OK;
 }
@@ -325,6 +424,11 @@ int sgmcmc_init(sgmcmc_handle* h, sgmcmc_state* st, const uint32_t* keys, int32_
   if (rc != SGMCMC_OK) return rc;
   if (!keys) return fail(SGMCMC_E_INVALID, "keys must not be null");
   if (sampler_mode && !st->key) return fail(SGMCMC_E_INVALID, "state.key is required in sampler mode");
+  if (h->big) {
+    sg::BigRun run{};
+    run.st = *st; run.mode = sampler_mode ? 2 : 1; run.init_keys = keys;
+    return dispatch_big(h, run, st->n_chains, (cudaStream_t)stream);
+  }
   sg::VecRun run{};
   run.st = *st; run.mode = sampler_mode ? 2 : 1; run.init_keys = keys;
   return dispatch_vec(h, run, (cudaStream_t)stream);
@@ -338,6 +442,12 @@ int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const 
   if (!coef || (coef_stride != 0 && coef_stride != 1)) return fail(SGMCMC_E_INVALID, "bad step coefficients");
   if (!st->key) return fail(SGMCMC_E_INVALID, "state.key is required");
   if (k == 0) return SGMCMC_OK;
+  if (h->big) {
+    sg::BigRun run{};
+    run.st = *st; run.i0 = i0; run.K = k; run.coef = coef; run.coef_stride = coef_stride; run.samples = samples;
+    run.sample_chain_stride = sample_chain_stride > 0 ? (size_t)sample_chain_stride : (size_t)k * h->P;
+    return dispatch_big(h, run, st->n_chains, (cudaStream_t)stream);
+  }
   sg::VecRun run{};
   run.st = *st; run.i0 = i0; run.K = k; run.coef = coef; run.coef_stride = coef_stride; run.samples = samples;
   run.sample_chain_stride = sample_chain_stride > 0 ? (size_t)sample_chain_stride : (size_t)k * h->P;
@@ -349,6 +459,11 @@ int sgmcmc_kernel_step(sgmcmc_handle* h, sgmcmc_state* st, int32_t i, const uint
   int rc = check_state(h, st);
   if (rc != SGMCMC_OK) return rc;
   if (!keys || !coef || i < 0) return fail(SGMCMC_E_INVALID, "bad argument");
+  if (h->big) {
+    sg::BigRun run{};
+    run.st = *st; run.i0 = i; run.K = 1; run.coef = coef; run.coef_stride = 0; run.step_keys = keys;
+    return dispatch_big(h, run, st->n_chains, (cudaStream_t)stream);
+  }
   sg::VecRun run{};
   run.st = *st; run.i0 = i; run.K = 1; run.coef = coef; run.coef_stride = 0; run.step_keys = keys;
   return dispatch_vec(h, run, (cudaStream_t)stream);

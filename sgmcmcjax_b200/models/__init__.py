@@ -1,4 +1,4 @@
 """Registered model families.  The native path consumes (loglikelihood, logprior) pairs
 created here; arbitrary Python log-densities are out of scope (BASELINE.json north_star)."""
-from . import gaussian_mean, logistic_regression  # noqa: F401
+from . import bayesian_mlp, gaussian_mean, logistic_regression, pmf  # noqa: F401
 from ._family import FamilySpec, resolve_family  # noqa: F401

@@ -33,8 +33,8 @@ def test_library_builds_loads_and_exports_header_symbols():
 def test_ctypes_struct_layout_matches_header():
     from sgmcmcjax_b200 import _native
 
-    # sgmcmc_config: 4*i32, i64, 2*i32, 8*i32, 4*i32, 8*f32, 8*f32, 4*f32
-    assert ctypes.sizeof(_native.Config) == 16 + 8 + 8 + 32 + 16 + 32 + 32 + 16
+    # sgmcmc_config: 4*i32, i64, 2*i32, 8*i32, 4*i32, 8*f32, 8*f32, 4*f32, 8*i32
+    assert ctypes.sizeof(_native.Config) == 16 + 8 + 8 + 32 + 16 + 32 + 32 + 16 + 32
     assert ctypes.sizeof(_native.State) == 8 + 8 * 8
     assert _native.Config.n_data.offset == 16 and _native.Config.leaf_size.offset == 32
 
@@ -50,8 +50,16 @@ def test_argument_validation_without_gpu():
     assert lib.sgmcmc_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"ABI" in lib.sgmcmc_last_error()
     cfg.abi_version = _native.ABI_VERSION
-    cfg.family = _native.FAMILY_PMF
+    cfg.family = 99
     assert lib.sgmcmc_create(ctypes.byref(cfg), ctypes.byref(h)) == -2
+    cfg.family, cfg.n_data, cfg.batch, cfg.n_leaves, cfg.data_dim = _native.FAMILY_PMF, 10, 2, 2, 2
+    assert lib.sgmcmc_create(ctypes.byref(cfg), ctypes.byref(h)) == -1      # leaf sizes / dims missing
+    assert b"leaf" in lib.sgmcmc_last_error() or b"pmf" in lib.sgmcmc_last_error()
+    cfg.family, cfg.data_dim, cfg.n_leaves = _native.FAMILY_MLP, 4, 2
+    cfg.leaf_size[0], cfg.leaf_size[1] = 12, 3
+    cfg.dims[0], cfg.dims[1], cfg.dims[2] = 1, 4, 200                       # width 200 > 128
+    assert lib.sgmcmc_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"mlp" in lib.sgmcmc_last_error()
     assert lib.sgmcmc_ksd_imq_partial(None, None, 0, 0, 0, 0, None, None) == -1
 
 
