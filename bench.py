@@ -187,6 +187,107 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+# ------------------------------------------------------------------------------------------ other configs
+def _time_engine(torch, eng, lib, keys_host, theta0, K, steps, warmup, with_samples=True):
+    """Device-resident timing of `steps` launches of K chain transitions each; returns (ms per launch, launches)."""
+    from sgmcmcjax_b200._engine import keys_to_device
+
+    keys_dev, _ = keys_to_device(keys_host)
+    st = eng.new_state(theta0)
+    eng.init(st, keys_dev, sampler_mode=True)
+    C = theta0.shape[0]
+    samples = torch.empty((C, K, eng.P), dtype=torch.float32, device="cuda") if with_samples else None
+    i0 = 0
+    for _ in range(warmup):
+        eng.run(st, i0, K, samples); i0 += K
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.sgmcmc_launch_count()
+    a.record()
+    for _ in range(steps):
+        eng.run(st, i0, K, samples); i0 += K
+    b.record()
+    torch.cuda.synchronize()
+    assert torch.isfinite(st["theta"]).all(), "non-finite chain state"
+    return a.elapsed_time(b) / steps, lib.sgmcmc_launch_count() - l0
+
+
+def extra_workloads(args, torch, lib, hbm_peak, X, y, theta_true):
+    """The other BASELINE.json configs on one GPU (parity-tested in tests/, reported here for SURVEY.md 8d):
+    C1 README Gaussian (latency), C2 at batch 1e3 and with SGLD-CV, C3 Bayesian MLP, C4 PMF."""
+    from sgmcmcjax_b200 import random, samplers
+    from sgmcmcjax_b200.models import bayesian_mlp as B
+    from sgmcmcjax_b200.models import gaussian_mean as G
+    from sgmcmcjax_b200.models import logistic_regression as L
+    from sgmcmcjax_b200.models import pmf as F
+
+    out = []
+
+    def report(name, ms, C, K, grads_per_step, bytes_per_chain_step, launches, note=""):
+        cs = C * K * grads_per_step / (ms * 1e-3)
+        gbs = bytes_per_chain_step * cs / 1e9
+        out.append({"config": name, "value": cs, "unit": UNIT, "ms_per_launch": ms, "chains": C, "steps_per_launch": K,
+                    "algorithmic_bytes_per_chain_step": bytes_per_chain_step, "achieved_gbs": gbs,
+                    "hbm_frac": gbs / hbm_peak, "gpu_launches": int(launches), "note": note})
+
+    th = theta_true.cpu().numpy()
+    C = args.chains
+    keys = random.split(random.PRNGKey(0), C)
+    th0 = torch.from_numpy(np.tile(th, (C, 1)).astype(np.float32)).cuda()
+    # ---- C2 variants
+    s = samplers.build_sgld_sampler(DT, L.loglikelihood, L.logprior, (X, y), 1000, pbar=False)
+    ms, nl = _time_engine(torch, s.engine, lib, keys, th0, 100, 5, 3)
+    report("C2 logreg SGLD batch=1000 (BASELINE metric string)", ms, C, 100, 1, algorithmic_bytes_per_chain_step(1000), nl)
+    s = samplers.build_sgldCV_sampler(1e-4, L.loglikelihood, L.logprior, (X, y), BATCH, th, pbar=False)
+    ms, nl = _time_engine(torch, s.engine, lib, keys, th0, 10, 5, 3)
+    report("C2 logreg SGLD-CV batch=10000", ms, C, 10, 1, algorithmic_bytes_per_chain_step(BATCH) + 8 * DIM, nl)
+    del s
+    # ---- C1 README Gaussian: one chain, latency-bound (4 MB table lives in L2)
+    Xg = random.normal(random.PRNGKey(0), (10000, 100))
+    s = samplers.build_sgld_sampler(1e-5, G.loglikelihood, G.logprior, (Xg,), 1000, pbar=False)
+    ms, nl = _time_engine(torch, s.engine, lib, random.split(random.PRNGKey(0), 1), torch.zeros(1, 100, device="cuda"),
+                          1000, 5, 3)
+    report("C1 README gaussian N=1e4 D=100 batch=1000, 1 chain", ms, 1, 1000, 1, 1000 * 400 + 1200, nl,
+           note=f"latency-bound: {ms:.3f} us per chain-step")
+    # ---- C3 Bayesian MLP 784-100-10, N=60k, batch=100, 256 chains
+    Cm, sizes = 256, [784, 100, 10]
+    Xm = torch.rand(60000, 784, device="cuda")
+    ym = torch.nn.functional.one_hot(torch.randint(0, 10, (60000,), device="cuda"), 10).float()
+    params = B.init_network(random.PRNGKey(1), sizes)
+    Pm = sum(w.numel() + b.numel() for w, b in params)
+    flat = torch.cat([t.reshape(-1) for wb in params for t in wb])
+    thm = flat[None].repeat(Cm, 1).contiguous()
+    keys_m = random.split(random.PRNGKey(2), Cm)
+    row_bytes = 100 * (784 * 4 + 40)
+    s = samplers.build_sghmc_sampler(1e-6, 4, B.loglikelihood, B.logprior, (Xm, ym), 100, pbar=False)
+    s.engine.flatten_params(params, None)
+    ms, nl = _time_engine(torch, s.engine, lib, keys_m, thm, 2, 3, 3)
+    report("C3 bayesian MLP 784-100-10 SGHMC L=4 batch=100", ms, Cm, 2, 4, row_bytes + 16 * Pm + Pm, nl,
+           note="one sample = 4 chain-steps (gradient evaluations)")
+    s = samplers.build_psgld_sampler(1e-3, B.loglikelihood, B.logprior, (Xm, ym), 100, pbar=False)
+    s.engine.flatten_params(params, None)
+    ms, nl = _time_engine(torch, s.engine, lib, keys_m, thm, 4, 3, 3)
+    report("C3 bayesian MLP 784-100-10 pSGLD batch=100", ms, Cm, 4, 1, row_bytes + 16 * Pm + 4 * Pm, nl)
+    del s, Xm, ym, thm
+    # ---- C4 PMF 943 x 1682, rank 20, N=1e5, batch=1000, 512 chains
+    Cp, nu, ni, r, Np = 512, 943, 1682, 20, 100_000
+    ij = torch.stack([torch.randint(0, nu, (Np,), device="cuda"), torch.randint(0, ni, (Np,), device="cuda")], 1).int()
+    rt = torch.randint(1, 6, (Np,), device="cuda").float()
+    U = 0.1 * random.normal(random.PRNGKey(3), (nu, r)); V = 0.1 * random.normal(random.PRNGKey(4), (ni, r))
+    Pp = (nu + ni) * r
+    thp = torch.cat([U.reshape(-1), V.reshape(-1)])[None].repeat(Cp, 1).contiguous()
+    keys_p = random.split(random.PRNGKey(5), Cp)
+    pmf_bytes = 1000 * 12 + 2 * 1000 * 4 * r + 16 * Pp + 4 * Pp
+    s = samplers.build_sgnht_sampler(1e-5, F.loglikelihood, F.logprior, (ij, rt), 1000, pbar=False)
+    s.engine.flatten_params((U, V), None)
+    ms, nl = _time_engine(torch, s.engine, lib, keys_p, thp, 4, 3, 3)
+    report("C4 PMF 943x1682 rank 20 SGNHT batch=1000", ms, Cp, 4, 1, pmf_bytes, nl)
+    s = samplers.build_badodabCV_sampler(1e-3, F.loglikelihood, F.logprior, (ij, rt), 1000, (U, V), pbar=False)
+    ms, nl = _time_engine(torch, s.engine, lib, keys_p, thp, 4, 3, 3)
+    report("C4 PMF 943x1682 rank 20 BADODAB-CV batch=1000", ms, Cp, 4, 1, pmf_bytes + 8 * Pp, nl)
+    return out
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -316,7 +417,19 @@ def gpu_arm(args):
         flops = 6.0 * DIM * pairs                                     # 3 Gram contractions, 2 flops per MAC
         ksd_line = {"metric": "imq_KSD pairs/sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n": n, "d": DIM,
                     "ms": ms, "ksd": float(val), "equiv_tflops": flops / (ms * 1e-3) / 1e12,
-                    "rows_this_rank": [r0, r1]}
+                    "method": "tcgen05 3xTF32 Gram tiles (upper triangle, dealt round-robin to ranks)",
+                    "roofline": {"bound": "tensor", "achieved": 1.5 * flops / (ms * 1e-3) / 1e12,
+                                 "peak": 0.5 * bf16_peak, "unit": "TFLOP/s",
+                                 "frac": 1.5 * flops / (ms * 1e-3) / 1e12 / (0.5 * bf16_peak),
+                                 "note": "achieved = ISSUED tf32 flops (3 split products per dot, half the tiles by "
+                                         "symmetry: 1.5 x the algorithmic 6*D*N^2); peak = 0.5 x measured bf16 "
+                                         "(no TF32 peak was measured)"}}
+
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del sampler, eng, st, samples
+        torch.cuda.empty_cache()
+        extras = extra_workloads(args, torch, lib, hbm_peak, X, y, theta_true)
 
     if rank == 0:
         line = {
@@ -327,7 +440,7 @@ def gpu_arm(args):
                        "every step (inputs larger than L2; no explicit flush)", "chains_total": world * C,
                        "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clk, "ksd": ksd_line,
+            "clocks": clk, "ksd": ksd_line, "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -349,6 +462,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of host work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ksd", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1/C3/C4 and C2-variant lines (N=1 only)")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch from the committed ncu --set full capture (profiles/)")
     args = ap.parse_args()

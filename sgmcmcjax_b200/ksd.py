@@ -93,6 +93,8 @@ def imq_KSD(samples, grads, distributed: bool = False, method: str = "tc"):
     else:
         raise ValueError("method must be 'tc' or 'simt'")
     if distributed:
-        dist.all_reduce(part)
+        from . import parallel
+
+        parallel.allreduce_scalar(part)
     val = (torch.sqrt(part[0]) / n).to(torch.float32)
     return _like(val, samples)

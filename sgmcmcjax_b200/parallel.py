@@ -1,0 +1,68 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, torch.distributed.
+
+* Sampling: chains are independent units.  Chain c of the job always uses ``split(key, C_total)[c]``, rank r
+  owns the contiguous block ``chain_shard(C_total, r, world)``; data is replicated per GPU and there is NO
+  collective inside the sampling loop.  ``gather_chains`` is the optional all-gather of the samples at the end.
+* KSD: the symmetric Gram tile list is dealt round-robin to ranks (``ksd_tile_partition`` mirrors
+  csrc/ksd_tc.cuh), each rank produces one fp64 partial, ONE all-reduce of a double (``allreduce_scalar``).
+
+Nothing here computes on the CPU: the callers pass in the per-rank partial results (from the CUDA path in the
+product, from the oracle in the gloo CPU tests of this host logic).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+KSD_TILE = 128     # csrc/ksd_tc.cuh TILE
+
+
+def chain_shard(n_chains: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of the job's chains owned by `rank` (sizes differ by at most one)."""
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    base, extra = divmod(int(n_chains), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def ksd_tile_count(n: int) -> int:
+    t = (int(n) + KSD_TILE - 1) // KSD_TILE
+    return t * (t + 1) // 2
+
+
+def ksd_tile_of(t: int, n: int) -> Tuple[int, int]:
+    """Index t of the row-major upper-triangular tile list -> (I, J >= I)  (csrc/ksd_tc.cuh tile_of)."""
+    T = (int(n) + KSD_TILE - 1) // KSD_TILE
+    i, start = 0, 0
+    while t >= start + (T - i):
+        start += T - i
+        i += 1
+    return i, i + (t - start)
+
+
+def ksd_tile_partition(n: int, part: int, nparts: int) -> List[Tuple[int, int]]:
+    """Tiles summed by partition `part` of `nparts`: list indices part, part + nparts, ..."""
+    return [ksd_tile_of(t, n) for t in range(part, ksd_tile_count(n), nparts)]
+
+
+def allreduce_scalar(value, group=None):
+    """SUM all-reduce of a one-element float64 tensor (in place) - the only KSD collective."""
+    import torch.distributed as dist
+
+    dist.all_reduce(value, op=dist.ReduceOp.SUM, group=group)
+    return value
+
+
+def gather_chains(local, n_chains_total: int, group=None):
+    """All-gather per-rank sample blocks [c_local, ...] (chain_shard order) into [n_chains_total, ...]."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    sizes = [chain_shard(n_chains_total, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
