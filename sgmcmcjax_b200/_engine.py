@@ -245,6 +245,9 @@ class Engine:
 
     def fullbatch_grad(self, thetas):
         torch = _native.require_cuda()
+        if self.leaf_shapes is None:
+            raise _native.NativeError("the parameter geometry is not bound yet: call init_fn / sampler / "
+                                      "flatten_params with a parameter pytree first")
         out = torch.empty_like(thetas)
         _native.check(self.lib.sgmcmc_fullbatch_grad(self._handle, _vp(thetas), int(thetas.shape[0]), _vp(out),
                                                      self._stream()))

@@ -25,7 +25,7 @@
 namespace sg {
 
 template <int FAMILY> struct BigThreads { static constexpr int value = 1024; };
-template <> struct BigThreads<SGMCMC_FAMILY_MLP> { static constexpr int value = 512; };   // 8x8 register tiles need > 64 registers
+template <> struct BigThreads<SGMCMC_FAMILY_MLP> { static constexpr int value = 512; };   // 16 warps: 4 per TMEM lane quarter
 
 struct BigModel {
   int family, estimator, diffusion, flags;
@@ -79,26 +79,64 @@ __device__ __forceinline__ float big_block_sum(float v, float* red) {
   return t;
 }
 
-// f(e, xi) for every element e of an n-element leaf with its N(0,1) draw xi = normal(key, (n,))[e]
-template <class F>
-__device__ __forceinline__ void for_leaf_normals(unsigned n, Key key, F f) {
+// One element of a leaf in flight: x, up to two auxiliary values and the (finalised) gradient.
+struct Elt { float x, a, b, g; };
+
+// For every element e of an n-element leaf: v = ld(e) ... st(e, v, xi) with xi = normal(key, (n,))[e].
+// One threefry block feeds elements m and m + ceil(n/2) (jax's half-split counter layout).  U blocks per
+// thread are staged per iteration so that 2U independent sets of global loads are in flight: these passes
+// run one CTA per chain and are latency-bound otherwise.
+template <int U, class LD, class ST>
+__device__ __forceinline__ void leaf_pass(unsigned n, Key key, LD ld, ST st) {
   const unsigned h = (n + 1u) >> 1;
-  for (unsigned m = threadIdx.x; m < h; m += blockDim.x) {
-    uint32_t w0, w1;
-    stream_block(key, m, n, w0, w1);
-    f(m, bits_to_normal(w0));
-    if (m + h < n) f(m + h, bits_to_normal(w1));
+#pragma unroll 1
+  for (unsigned m0 = threadIdx.x; m0 < h; m0 += U * blockDim.x) {
+    Elt e0[U], e1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned m = m0 + u * blockDim.x;
+      if (m < h) { e0[u] = ld(m); if (m + h < n) e1[u] = ld(m + h); }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned m = m0 + u * blockDim.x;
+      if (m < h) {
+        uint32_t w0, w1;
+        stream_block(key, m, n, w0, w1);
+        st(m, e0[u], bits_to_normal(w0));
+        if (m + h < n) st(m + h, e1[u], bits_to_normal(w1));
+      }
+    }
   }
 }
+
+// Same staging without noise: v = ld(e) ... st(e, v).
+template <int U, class LD, class ST>
+__device__ __forceinline__ void plain_pass(unsigned n, LD ld, ST st) {
+#pragma unroll 1
+  for (unsigned e0 = threadIdx.x; e0 < n; e0 += U * blockDim.x) {
+    Elt v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const unsigned e = e0 + u * blockDim.x; if (e < n) v[u] = ld(e); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const unsigned e = e0 + u * blockDim.x; if (e < n) st(e, v[u]); }
+  }
+}
+
+template <int FAMILY> struct BigUnroll { static constexpr int value = 2; };                  // 1024 threads: 64 registers
+template <> struct BigUnroll<SGMCMC_FAMILY_MLP> { static constexpr int value = 2; };       // 512 threads: 128 registers
 
 // ---------------------------------------------------------------------------------------
 // PMF likelihood pass
 template <>
 struct FamilyGrad<SGMCMC_FAMILY_PMF> {
   static constexpr size_t smem_bytes(const BigModel&) { return 0; }
+  __device__ static void cta_init(const BigModel&, void*) {}
+  __device__ static void cta_fini(const BigModel&, void*) {}
 
   __device__ static void lik_pass(const BigModel& m, void* /*fam_smem*/, const float* theta, const float* center,
-                                  bool sequential, const RandintPlan& plan, unsigned seq_base, unsigned count, float* g) {
+                                  bool sequential, const RandintPlan& plan, unsigned seq_base, unsigned count, float* g,
+                                  bool /*fresh*/) {
     const int r = m.dims[2];
     const int offV = m.leaf_off[1];
     const int4* __restrict__ rat = reinterpret_cast<const int4*>(m.data0);
@@ -140,17 +178,34 @@ struct FamilyGrad<SGMCMC_FAMILY_PMF> {
 // ---------------------------------------------------------------------------------------
 template <int FAMILY>
 struct BigCtx {
+  static constexpr int U = BigUnroll<FAMILY>::value;
   const BigModel& m;
   BigSmem& s;
   void* fam_smem;
   float *theta, *aux1, *aux2, *grad;      // this chain's rows of the state arrays
   const float *center, *fb;                // CV: shared model buffers; SVRG: this chain's rows
   float *svrg_center, *svrg_fb;
+  // Between an estimate and the next diffusion update the gradient buffer holds the RAW likelihood sum
+  // S = sum_i grad loglik_i(theta) [- the same at the centre]; the consumer applies  gscale * S - prior * theta
+  // [+ fb + prior * centre] on the fly and zeroes the buffer for the next accumulation (no separate finalise
+  // and zero passes over the P-vector).  At launch boundaries the buffer holds the finalised param_grad.
+  bool grad_raw = false;
+  float gscale = 1.0f;
 
   __device__ BigCtx(const BigModel& mm, BigSmem& ss, void* fs) : m(mm), s(ss), fam_smem(fs) {}
 
+  __device__ __forceinline__ bool is_cv() const { return m.estimator != SGMCMC_EST_STANDARD; }
+
+  // finalised gradient of global element ge from the buffer value `raw` and the parameter value x it was taken at
+  __device__ __forceinline__ float gfin(float raw, float x, unsigned ge) const {
+    if (!grad_raw) return raw;
+    const float prior = m.coef[1];
+    if (is_cv()) return fb[ge] + (gscale * raw - prior * (x - center[ge]));   // gradient_estimation.py:72, no cancellation
+    return gscale * raw - prior * x;
+  }
+
   __device__ void zero(float* g) {
-    for (int e = threadIdx.x; e < m.P; e += blockDim.x) g[e] = 0.f;
+    plain_pass<U>((unsigned)m.P, [&](unsigned) { return Elt{}; }, [&](unsigned e, const Elt&) { g[e] = 0.f; });
     __syncthreads();
   }
 
@@ -158,44 +213,57 @@ struct BigCtx {
   __device__ void full_grad(const float* th, float* out) {
     zero(out);
     RandintPlan dummy{};
-    FamilyGrad<FAMILY>::lik_pass(m, fam_smem, th, nullptr, true, dummy, 0u, m.n_data, out);
+    FamilyGrad<FAMILY>::lik_pass(m, fam_smem, th, nullptr, true, dummy, 0u, m.n_data, out, true);
     __syncthreads();
     const float prior = m.coef[1];
-    // __ldcg: the sums were accumulated with L2 atomics, so read them at L2
-    for (int e = threadIdx.x; e < m.P; e += blockDim.x) out[e] = __ldcg(out + e) - prior * th[e];
+    // __ldcg: the sums may have been accumulated with L2 atomics, so read them at L2
+    plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v; v.g = __ldcg(out + e); v.x = th[e]; return v; },
+                  [&](unsigned e, const Elt& v) { out[e] = v.g - prior * v.x; });
     __syncthreads();
   }
 
-  __device__ void estimate(int i, Key k2, bool is_init) {
-    const bool cv = m.estimator != SGMCMC_EST_STANDARD;
+  // turn a raw buffer into the finalised gradient (launch end, init_fn)
+  __device__ void finalize() {
+    if (!grad_raw) return;
+    plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v; v.g = __ldcg(grad + e); v.x = theta[e]; return v; },
+                  [&](unsigned e, const Elt& v) { grad[e] = gfin(v.g, v.x, e); });
+    __syncthreads();
+    grad_raw = false;
+  }
+
+  // estimate_gradient: on entry the gradient buffer is all zero unless is_init
+  __device__ __noinline__ void estimate(int i, Key k2, bool is_init) {
+    const bool cv = is_cv();
     if (m.estimator == SGMCMC_EST_SVRG) {
       if (is_init) {                                       // gradient_estimation.py:124-128
         full_grad(theta, svrg_fb);
-        for (int e = threadIdx.x; e < m.P; e += blockDim.x) { svrg_center[e] = theta[e]; grad[e] = svrg_fb[e]; }
+        plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v; v.x = theta[e]; v.g = svrg_fb[e]; return v; },
+                      [&](unsigned e, const Elt& v) { svrg_center[e] = v.x; grad[e] = v.g; });
         __syncthreads();
+        grad_raw = false;
         return;
       }
       if (i % m.update_rate == 0) {                        // gradient_estimation.py:134-139
         full_grad(theta, svrg_fb);
-        for (int e = threadIdx.x; e < m.P; e += blockDim.x) svrg_center[e] = theta[e];
+        plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v; v.x = theta[e]; return v; },
+                      [&](unsigned e, const Elt& v) { svrg_center[e] = v.x; });
         __syncthreads();
       }
-    } else if (m.estimator == SGMCMC_EST_STANDARD && m.full_batch && !is_init) {
-      full_grad(theta, grad);                              // gradient_estimation.py:41-42
-      return;
     }
-    zero(grad);
-    const RandintPlan plan = randint_plan(k2, m.n_data, m.batch);
-    FamilyGrad<FAMILY>::lik_pass(m, fam_smem, theta, cv ? center : nullptr, false, plan, 0u, m.batch, grad);
-    __syncthreads();
-    const float prior = m.coef[1], scale = m.scale;
-    if (cv) {   // fb + (g(theta) - g(centre)): gradient_estimation.py:72 without the fp32 cancellation
-      for (int e = threadIdx.x; e < m.P; e += blockDim.x)
-        grad[e] = fb[e] + (scale * __ldcg(grad + e) - prior * (theta[e] - center[e]));
+    if (is_init) zero(grad);
+    RandintPlan plan{};
+    if (m.estimator == SGMCMC_EST_STANDARD && m.full_batch && !is_init) {
+      // static full-batch bypass, gradient_estimation.py:41-42 (init_gradient still subsamples, :31-35)
+      FamilyGrad<FAMILY>::lik_pass(m, fam_smem, theta, nullptr, true, plan, 0u, m.n_data, grad, true);
+      gscale = 1.0f;
     } else {
-      for (int e = threadIdx.x; e < m.P; e += blockDim.x) grad[e] = scale * __ldcg(grad + e) - prior * theta[e];
+      plan = randint_plan(k2, m.n_data, m.batch);
+      FamilyGrad<FAMILY>::lik_pass(m, fam_smem, theta, cv ? center : nullptr, false, plan, 0u, m.batch, grad, true);
+      gscale = m.scale;
     }
     __syncthreads();
+    grad_raw = true;
+    if (is_init) finalize();
   }
 
   __device__ __forceinline__ Key leaf_key(int slot, int leaf) const {
@@ -215,65 +283,78 @@ struct BigCtx {
     __syncthreads();
   }
 
-  __device__ void diffuse(int phase, int i, const sgmcmc_step_coef& cf, int key_slot) {
+  // phase 1 = `update` (consumes the carried gradient, leaves the buffer zeroed for the next estimate and
+  // emits the sample if `sample` is set); phase 2 = `update2` of the palindromes (gradient stays in the buffer).
+  __device__ __noinline__ void diffuse(int phase, int i, const sgmcmc_step_coef& cf, int key_slot, float* sample) {
     const bool bug = (m.flags & SGMCMC_FLAG_BADODABCV_REFERENCE_BUG) && m.diffusion == SGMCMC_DIFF_BADODAB;
     if (phase == 2 || bug) {                      // baoab / badodab update2: v += dt/2 * g
-      for (int e = threadIdx.x; e < m.P; e += blockDim.x) aux1[e] = fmaf(cf.hh, grad[e], aux1[e]);
+      const bool consume = phase == 1;
+      plain_pass<U>((unsigned)m.P,
+                    [&](unsigned e) { Elt v; v.x = theta[e]; v.a = aux1[e]; v.g = gfin(__ldcg(grad + e), v.x, e); return v; },
+                    [&](unsigned e, const Elt& v) {
+                      aux1[e] = fmaf(cf.hh, v.g, v.a);
+                      if (consume) { grad[e] = 0.f; if (sample) __stcs(sample + e, v.x); }
+                    });
       __syncthreads();
+      if (consume) grad_raw = false;
       return;
     }
     for (int leaf = 0; leaf < m.n_leaves; ++leaf) {
       const Key lk = leaf_key(key_slot, leaf);
-      const int off = m.leaf_off[leaf];
-      const unsigned n = (unsigned)(m.leaf_off[leaf + 1] - off);
+      const unsigned off = (unsigned)m.leaf_off[leaf];
+      const unsigned n = (unsigned)(m.leaf_off[leaf + 1] - m.leaf_off[leaf]);
       float* x = theta + off;
       float* v = aux1 ? aux1 + off : nullptr;
       float* v2 = aux2 ? aux2 + off : nullptr;
-      const float* g = grad + off;
+      float* g = grad + off;
+      float* smp = sample ? sample + off : nullptr;
+      // loaders: x, gradient (finalised on the fly), optionally the auxiliaries
+      auto ld_xg = [&](unsigned e) { Elt t; t.x = x[e]; t.a = 0.f; t.b = 0.f; t.g = gfin(__ldcg(g + e), t.x, off + e); return t; };
+      auto ld_xvg = [&](unsigned e) { Elt t; t.x = x[e]; t.a = v[e]; t.b = 0.f; t.g = gfin(__ldcg(g + e), t.x, off + e); return t; };
+      auto ld_xvvg = [&](unsigned e) { Elt t; t.x = x[e]; t.a = v[e]; t.b = v2[e]; t.g = gfin(__ldcg(g + e), t.x, off + e); return t; };
+      auto emit = [&](unsigned e, float xn) { x[e] = xn; g[e] = 0.f; if (smp) __stcs(smp + e, xn); };
       switch (m.diffusion) {
         case SGMCMC_DIFF_SGLD:
-          for_leaf_normals(n, lk, [&](unsigned e, float xi) { x[e] = fmaf(cf.ca, xi, fmaf(cf.h, g[e], x[e])); });
+          leaf_pass<U>(n, lk, ld_xg, [&](unsigned e, const Elt& t, float xi) { emit(e, fmaf(cf.ca, xi, fmaf(cf.h, t.g, t.x))); });
           break;
         case SGMCMC_DIFF_PSGLD: {
           const float alpha = m.hyper[0], eps = m.hyper[1];
-          for_leaf_normals(n, lk, [&](unsigned e, float xi) {
-            const float ge = g[e];
-            const float vv = alpha * v[e] + (1.0f - alpha) * (ge * ge);
-            const float G = 1.0f / (sqrtf(vv) + eps);
+          leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
+            const float vv = alpha * t.a + (1.0f - alpha) * (t.g * t.g);
+            const float G = fast_rcp(fast_sqrt(vv) + eps);
             v[e] = vv;
-            x[e] = x[e] + cf.hh * G * ge + sqrtf(cf.h * G) * xi;
+            emit(e, t.x + cf.hh * G * t.g + fast_sqrt(cf.h * G) * xi);
           });
           break;
         }
         case SGMCMC_DIFF_SGLDADAM: {
           const float b1 = m.hyper[0], b2 = m.hyper[1], eps = m.hyper[2];
-          for_leaf_normals(n, lk, [&](unsigned e, float xi) {
-            const float ge = g[e];
-            const float mm = b1 * v[e] + (1.0f - b1) * ge;
-            const float vv = b2 * v2[e] + (1.0f - b2) * (ge * ge);
-            const float mh = mm / cf.ca, vh = vv / cf.cb;
-            const float a = cf.h / (sqrtf(vh) + eps);
+          leaf_pass<U>(n, lk, ld_xvvg, [&](unsigned e, const Elt& t, float xi) {
+            const float mm = b1 * t.a + (1.0f - b1) * t.g;
+            const float vv = b2 * t.b + (1.0f - b2) * (t.g * t.g);
+            const float mh = mm * fast_rcp(cf.ca), vh = vv * fast_rcp(cf.cb);
+            const float a = cf.h * fast_rcp(fast_sqrt(vh) + eps);
             v[e] = mm; v2[e] = vv;
-            x[e] = x[e] + a * 0.5f * mh + sqrtf(a) * xi;
+            emit(e, t.x + a * 0.5f * mh + fast_sqrt(a) * xi);
           });
           break;
         }
         case SGMCMC_DIFF_SGHMC: {
           const float alpha = m.hyper[0];
-          for_leaf_normals(n, lk, [&](unsigned e, float xi) {
-            const float ve = v[e];
-            x[e] += ve;
-            v[e] = ve + cf.h * g[e] - alpha * ve + cf.ca * xi;
+          leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
+            v[e] = t.a + cf.h * t.g - alpha * t.a + cf.ca * xi;
+            emit(e, t.x + t.a);
           });
           break;
         }
         case SGMCMC_DIFF_BAOAB:
-          for_leaf_normals(n, lk, [&](unsigned e, float xi) {
-            float ve = fmaf(cf.hh, g[e], v[e]);
-            float xe = x[e] + ve * cf.h * 0.5f;
+          leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
+            float ve = fmaf(cf.hh, t.g, t.a);
+            float xe = t.x + ve * cf.h * 0.5f;
             ve = cf.ca * ve + cf.cb * xi;
             xe = xe + ve * cf.h * 0.5f;
-            v[e] = ve; x[e] = xe;
+            v[e] = ve;
+            emit(e, xe);
           });
           break;
         case SGMCMC_DIFF_SGNHT: {
@@ -281,21 +362,14 @@ struct BigCtx {
           const float alpha = s.alpha[leaf];
           const bool first = (i == 0);
           if (first) split2(lk, kn, sub);               // diffusions.py:268-278
-          const unsigned h = (n + 1u) >> 1;
           float ss = 0.f;
-          for (unsigned mm = threadIdx.x; mm < h; mm += blockDim.x) {
-            uint32_t w0, w1, s0 = 0u, s1 = 0u;
-            stream_block(kn, mm, n, w0, w1);
-            if (first) stream_block(sub, mm, n, s0, s1);
-            const int cnt = (mm + h < n) ? 2 : 1;
-            for (int t = 0; t < cnt; ++t) {
-              const unsigned e = t ? mm + h : mm;
-              float ve = first ? cf.cb * bits_to_normal(t ? s1 : s0) : v[e];
-              ve = ve - alpha * ve + cf.h * g[e] + cf.ca * bits_to_normal(t ? w1 : w0);
-              v[e] = ve; x[e] += ve;
-              ss = fmaf(ve, ve, ss);
-            }
-          }
+          leaf_pass<U>(n, kn, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
+            float ve = first ? cf.cb * normal_at(sub, e, n) : t.a;
+            ve = ve - alpha * ve + cf.h * t.g + cf.ca * xi;
+            v[e] = ve;
+            emit(e, t.x + ve);
+            ss = fmaf(ve, ve, ss);
+          });
           const float nrm = sqrtf(big_block_sum(ss, s.red));
           if (threadIdx.x == 0) s.alpha[leaf] = alpha + (nrm * nrm) / (float)n - cf.h;
           break;
@@ -303,31 +377,25 @@ struct BigCtx {
         case SGMCMC_DIFF_BADODAB: {
           float alpha = s.alpha[leaf];
           float ss = 0.f;
-          for (unsigned e = threadIdx.x; e < n; e += blockDim.x) {
-            const float ve = fmaf(cf.hh, g[e], v[e]);
-            v[e] = ve; x[e] = fmaf(cf.hh, ve, x[e]);
+          plain_pass<U>(n, ld_xvg, [&](unsigned e, const Elt& t) {
+            const float ve = fmaf(cf.hh, t.g, t.a);
+            v[e] = ve; x[e] = fmaf(cf.hh, ve, t.x); g[e] = 0.f;
             ss = fmaf(ve, ve, ss);
-          }
+          });
           alpha = alpha + cf.hh * (sqrtf(big_block_sum(ss, s.red)) - (float)n);
           const float c1 = (float)exp((double)(-alpha * cf.h));     // correctly rounded, see vec_sampler.cuh
           const float c2 = (alpha == 0.0f) ? cf.ca : sqrtf(fabsf((1.0f - c1 * c1) / (2.0f * alpha)));
           __syncthreads();
           float ss2 = 0.f;
-          {
-            const unsigned h = (n + 1u) >> 1;
-            for (unsigned mm = threadIdx.x; mm < h; mm += blockDim.x) {
-              uint32_t w0, w1;
-              stream_block(lk, mm, n, w0, w1);
-              const int cnt = (mm + h < n) ? 2 : 1;
-              for (int t = 0; t < cnt; ++t) {
-                const unsigned e = t ? mm + h : mm;
-                const float ve = c1 * v[e] + c2 * bits_to_normal(t ? w1 : w0);
-                v[e] = ve; ss2 = fmaf(ve, ve, ss2);
-              }
-            }
-          }
+          leaf_pass<U>(n, lk, [&](unsigned e) { Elt t; t.x = x[e]; t.a = v[e]; t.b = 0.f; t.g = 0.f; return t; },
+                       [&](unsigned e, const Elt& t, float xi) {
+                         const float ve = c1 * t.a + c2 * xi;
+                         v[e] = ve; ss2 = fmaf(ve, ve, ss2);
+                         const float xn = fmaf(cf.hh, ve, t.x);      // second half step of x with the new v
+                         x[e] = xn;
+                         if (smp) __stcs(smp + e, xn);
+                       });
           alpha = alpha + cf.hh * (sqrtf(big_block_sum(ss2, s.red)) - (float)n);
-          for (unsigned e = threadIdx.x; e < n; e += blockDim.x) x[e] = fmaf(cf.hh, v[e], x[e]);
           __syncthreads();
           if (threadIdx.x == 0) s.alpha[leaf] = alpha;
           break;
@@ -335,33 +403,36 @@ struct BigCtx {
       }
     }
     __syncthreads();
+    grad_raw = false;                             // consumed: the buffer is all zero now
   }
 
-  __device__ void langevin(int i, Key key, const sgmcmc_step_coef& cf) {
+  __device__ void langevin(int i, Key key, const sgmcmc_step_coef& cf, float* sample) {
     expand_step_keys(key);
     Key k2; k2.a = s.keys[2]; k2.b = s.keys[3];
-    diffuse(1, i, cf, 4);
+    diffuse(1, i, cf, 4, sample);
     estimate(i, k2, false);
-    if (m.diffusion == SGMCMC_DIFF_BAOAB || m.diffusion == SGMCMC_DIFF_BADODAB) diffuse(2, i, cf, 4);
+    if (m.diffusion == SGMCMC_DIFF_BAOAB || m.diffusion == SGMCMC_DIFF_BADODAB) diffuse(2, i, cf, 4, nullptr);
   }
 
-  __device__ void transition(int i, Key key, const sgmcmc_step_coef& cf) {
-    if (m.diffusion != SGMCMC_DIFF_SGHMC) { langevin(i, key, cf); return; }
+  __device__ void transition(int i, Key key, const sgmcmc_step_coef& cf, float* sample) {
+    if (m.diffusion != SGMCMC_DIFF_SGHMC) { langevin(i, key, cf, sample); return; }
     Key k1, k2;
     split2(key, k1, k2);
     for (int leaf = 0; leaf < m.n_leaves; ++leaf) {          // resample_momentum, diffusions.py:197-199
       const Key lk = split_at(k1, m.n_leaves, leaf);
       const int off = m.leaf_off[leaf];
       float* v = aux1 + off;
-      for_leaf_normals((unsigned)(m.leaf_off[leaf + 1] - off), lk, [&](unsigned e, float xi) { v[e] = cf.cb * xi; });
+      leaf_pass<U>((unsigned)(m.leaf_off[leaf + 1] - off), lk, [&](unsigned) { return Elt{}; },
+                   [&](unsigned e, const Elt&, float xi) { v[e] = cf.cb * xi; });
     }
     __syncthreads();
-    for (int l = 0; l < m.leapfrog; ++l) langevin(i, split_at(k2, m.leapfrog, l), cf);
+    for (int l = 0; l < m.leapfrog; ++l)
+      langevin(i, split_at(k2, m.leapfrog, l), cf, l == m.leapfrog - 1 ? sample : nullptr);
   }
 };
 
 template <int FAMILY>
-__global__ void __launch_bounds__(BigThreads<FAMILY>::value, 1) big_sampler_kernel(const BigModel m, const BigRun run) {
+__global__ void __launch_bounds__(BigThreads<FAMILY>::value, 1) big_sampler_kernel(const __grid_constant__ BigModel m, const __grid_constant__ BigRun run) {
   extern __shared__ __align__(16) uint8_t big_smem_raw[];
   BigSmem& s = *reinterpret_cast<BigSmem*>(big_smem_raw);
   void* fam_smem = big_smem_raw + ((sizeof(BigSmem) + 127) & ~(size_t)127);
@@ -369,9 +440,11 @@ __global__ void __launch_bounds__(BigThreads<FAMILY>::value, 1) big_sampler_kern
   const size_t P = (size_t)m.P;
   const sgmcmc_state& st = run.st;
   BigCtx<FAMILY> ctx(m, s, fam_smem);
+  FamilyGrad<FAMILY>::cta_init(m, fam_smem);                 // MLP: mbarriers + TMEM allocation
 
   if (run.mode == 3) {                                       // K2: full-batch gradient at fg_thetas[c]
     ctx.full_grad(run.fg_thetas + c * P, run.fg_out + c * P);
+    FamilyGrad<FAMILY>::cta_fini(m, fam_smem);
     return;
   }
 
@@ -411,18 +484,17 @@ __global__ void __launch_bounds__(BigThreads<FAMILY>::value, 1) big_sampler_kern
       Key sub;
       if (run.step_keys) { sub.a = run.step_keys[2 * c]; sub.b = run.step_keys[2 * c + 1]; }
       else { Key nk; split2(carry, nk, sub); carry = nk; }      // samplers.py:49
-      ctx.transition(i, sub, cf);
-      if (run.samples) {
-        float* dst = run.samples + (size_t)c * run.sample_chain_stride + (size_t)sidx * P;
-        for (size_t e = threadIdx.x; e < P; e += blockDim.x) __stcs(dst + e, ctx.theta[e]);
-      }
+      // get_params after the transition: the sample is written by the diffusion pass that produces it
+      ctx.transition(i, sub, cf, run.samples ? run.samples + (size_t)c * run.sample_chain_stride + (size_t)sidx * P : nullptr);
     }
+    ctx.finalize();                                             // the state's param_grad is the finalised gradient
   }
   __syncthreads();
   if (st.alpha && threadIdx.x < m.n_leaves) st.alpha[(size_t)c * m.n_leaves + threadIdx.x] = s.alpha[threadIdx.x];
   if (threadIdx.x == 0 && st.key && (run.mode == 2 || (run.mode == 0 && run.step_keys == nullptr))) {
     st.key[2 * c] = carry.a; st.key[2 * c + 1] = carry.b;
   }
+  FamilyGrad<FAMILY>::cta_fini(m, fam_smem);
 }
 
 }  // namespace sg

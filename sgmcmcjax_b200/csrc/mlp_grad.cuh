@@ -5,18 +5,94 @@
 //   loglikelihood = sum_k y_k predict_k (:48-50);  logprior = sum N(0,1).logpdf (:53-58) -> grad = -w
 //
 // lik_pass ADDS  sign * sum_i grad_theta loglik(theta, x_i, y_i)  into the gradient buffer, in sub-batches
-// of <= 128 rows.  Everything is fp32 on the CUDA cores in this round (the two layer-1 GEMMs,
-// Z1 = X W1^T (B x s1 x s0) and dW1 = dZ1^T X (s1 x s0 x B), are register-tiled 8x8 SGEMMs with
-// shared-memory staging; 2 groups of 256 threads split K (forward) or the output columns (backward)).
-// Shapes supported: n_layers <= 3, hidden / output widths <= 128, any input width.
+// of <= 128 rows.  The two layer-1 contractions carry ~99 % of the flops and run on the tensor cores
+// (tcgen05, fp32 accumulators in TMEM) as 3xTF32:  a = a_hi + a_lo,  a_hi = rna_tf32(a),
+// a_lo = rna_tf32(a - a_hi);  a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi  (error ~2^-21 |a||b|).
+//
+//   forward   Z1[b][n]  = sum_k X[b][k] W1[n][k]          M = b (128), N = n (s1 -> 16), K = k
+//             A = gathered rows of X, B = W1, both K-major, 32-float K chunks in 128-byte-swizzled rows;
+//             2-stage smem pipeline: all threads load (registers) -> split hi/lo -> st.shared, one thread
+//             issues 12 MMAs per chunk, tcgen05.commit frees the stage.
+//   backward  dW1^T[k][n] = sum_b X[b][k] dZ1[b][n]       M = k (128-wide tiles), N = n, K = b
+//             A = the same gathered rows, B = dZ1: both MN-major (the row-major [b][k] / [b][n] data as it
+//             lies, in 4-row x 128-byte SWIZZLE_128B_BASE32B atoms); 4 M-tiles (<= 512 TMEM columns) per pass; dZ1 hi/lo
+//             is staged once, X streams through a 2-stage pipeline; the epilogue adds the TMEM tiles into
+//             the chain's gradient (coalesced: lane = k).
+// The small layers (softmax, layers >= 2, their backward) stay fp32 SIMT.  Shapes: n_layers <= 3,
+// hidden / output widths <= 128, any input width; the shared-memory need is checked at create time.
 #pragma once
 #include "big_sampler.cuh"
+#include "ksd_tc.cuh"   // PTX wrappers: mbarrier, tcgen05 alloc / mma / commit / ld, tf32 rounding
 
 namespace sg {
 
-constexpr int MLP_ROWS = 128;     // sub-batch rows
-constexpr int MLP_KT = 16;        // staging depth
-constexpr int MLP_GROUPS = 2;     // 2 x 256 threads (512-thread CTA: 128 registers per thread for the 8x8 tiles)
+constexpr int MLP_ROWS = 128;      // largest sub-batch (MMA M of the forward contraction)
+constexpr int MLP_THREADS = 512;
+constexpr int MLP_KC = 32;         // forward K chunk (floats): one 128-byte swizzled row
+constexpr size_t MLP_SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
+
+__host__ __device__ inline int mlp_stride(int w) { return w | 1; }   // odd row stride: conflict-free row-per-lane access
+__host__ __device__ inline int mlp_n16(int w) { return (w + 15) & ~15; }
+
+struct MlpSmem {
+  uint64_t bar[2];             // stage-free barriers (tcgen05.commit arrives)
+  uint32_t parity[2];          // their next phase parity, carried from one GEMM to the next
+  uint32_t tmem_base;
+  uint32_t pad;
+  int idx[MLP_ROWS];
+};
+
+// Shared-memory plan: [region | xs | fp32 activations] after a 1024-byte aligned base.
+struct MlpPlan {
+  int L, s1n;                  // s1n = layer-1 width rounded up to 16 (MMA N)
+  int rows;                    // sub-batch capacity: min(128, batch rounded up to 8)
+  int tmem_cols;
+  size_t region_bytes;         // forward stages (2 x [Xhi | Xlo | Whi | Wlo]) / backward dZ1 hi + lo
+  size_t xs_bytes;             // backward X stages: 2 x [hi | lo] of 8 rows x 256 columns (also: bias-gradient scratch)
+  int act_off1, act_off2, act_off3;   // float offsets of act[1..L]
+  int dz_off0, dz_off1;        // float offsets of the two ping-pong dZ buffers (layers >= 2; layer 1 if L == 1)
+  int dz_w0, dz_w1;
+  size_t total_bytes;
+  __host__ __device__ int act_off(int l) const { return l == 1 ? act_off1 : l == 2 ? act_off2 : act_off3; }
+  __host__ __device__ int dz_off(int k) const { return k ? dz_off1 : dz_off0; }
+  __host__ __device__ int dz_w(int k) const { return k ? dz_w1 : dz_w0; }
+};
+
+__host__ __device__ inline MlpPlan mlp_plan_rows(const int* dims, int rows) {
+  MlpPlan p{};
+  p.L = dims[0];
+  const int* sz = dims + 1;
+  p.s1n = mlp_n16(sz[1]);
+  p.rows = rows;
+  int cols = 32;
+  while (cols < 4 * p.s1n && cols < 512) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t fwd_stage = 2 * (size_t)MLP_ROWS * 128 + 2 * (size_t)p.s1n * 128;
+  const size_t bwd_b = 2 * (size_t)(p.rows / 8) * 4096;
+  p.region_bytes = 2 * fwd_stage > bwd_b ? 2 * fwd_stage : bwd_b;
+  p.xs_bytes = 2 * 2 * 8 * 256 * sizeof(float);
+  int f = 0;
+  p.act_off1 = f; f += p.rows * mlp_stride(sz[1]);
+  p.act_off2 = f; if (p.L >= 2) f += p.rows * mlp_stride(sz[2]);
+  p.act_off3 = f; if (p.L >= 3) f += p.rows * mlp_stride(sz[3]);
+  // dZ_l lives in buffer (L - l) & 1; layer 1 only needs one when it is the output layer (L == 1)
+  int w0 = 1, w1 = 1;
+  for (int l = (p.L == 1 ? 1 : 2); l <= p.L; ++l) {
+    if ((p.L - l) & 1) { if (sz[l] > w1) w1 = sz[l]; } else { if (sz[l] > w0) w0 = sz[l]; }
+  }
+  p.dz_w0 = w0; p.dz_off0 = f; f += p.rows * mlp_stride(w0);
+  p.dz_w1 = w1; p.dz_off1 = f; f += p.rows * mlp_stride(w1);
+  p.total_bytes = 1024 + p.region_bytes + p.xs_bytes + (size_t)f * sizeof(float);
+  return p;
+}
+
+// sub-batch capacity: min(128, batch rounded up to 8), lowered in steps of 8 until the plan fits in shared memory
+__host__ __device__ inline MlpPlan mlp_plan(const int* dims, unsigned batch) {
+  int rows = batch >= (unsigned)MLP_ROWS ? MLP_ROWS : (int)((batch + 7u) & ~7u);
+  MlpPlan p = mlp_plan_rows(dims, rows);
+  while (rows > 8 && p.total_bytes + 4096 > MLP_SMEM_LIMIT) { rows -= 8; p = mlp_plan_rows(dims, rows); }
+  return p;
+}
 
 inline const char* mlp_validate(const sgmcmc_config* cfg) {
   const int L = cfg->dims[0];
@@ -30,156 +106,335 @@ inline const char* mlp_validate(const sgmcmc_config* cfg) {
       return "mlp: leaf sizes do not match the layer sizes";
   }
   if (cfg->data_dim != cfg->dims[1]) return "mlp: data[0] must have size_0 columns";
+  if (mlp_plan(cfg->dims, (unsigned)cfg->batch).total_bytes + 4096 > MLP_SMEM_LIMIT)
+    return "mlp: these layer widths need more than 227 KB of shared memory per chain";
   return nullptr;
 }
 
-__host__ __device__ inline int mlp_stride(int w) { return w | 1; }   // odd row stride: conflict-free row-per-lane access
+namespace mlptc {
+using namespace ksdtc;
 
-struct MlpSmem {
-  int idx[MLP_ROWS];
-  float ysum[MLP_ROWS];
-};
-
-// shared-memory floats: activations of layers 1..L, two ping-pong dZ buffers, staging for the 4 groups
-__host__ __device__ inline size_t mlp_smem_floats(const int* dims) {
-  const int L = dims[0];
-  size_t f = 0;
-  int wmax_even = 0, wmax_odd = 0;
-  for (int l = 1; l <= L; ++l) {
-    f += (size_t)MLP_ROWS * mlp_stride(dims[1 + l]);
-    int& w = ((L - l) & 1) ? wmax_odd : wmax_even;
-    if (dims[1 + l] > w) w = dims[1 + l];
-  }
-  f += (size_t)MLP_ROWS * mlp_stride(wmax_even) + (size_t)MLP_ROWS * mlp_stride(wmax_odd > 0 ? wmax_odd : 1);
-  f += (size_t)MLP_GROUPS * 2 * MLP_KT * 128;
-  return f;
+// K-major, 128-byte swizzle: rows of 32 floats, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
 }
-
-// acc[i][j] += sum_{k < kt} A[k * lda + i0 + i] * B[k * 128 + j0 + j]
-template <bool A_VEC>
-__device__ __forceinline__ void mlp_microkernel(float (&acc)[8][8], const float* __restrict__ A, int lda, int i0,
-                                                const float* __restrict__ B, int j0, int kt) {
-#pragma unroll 4
-  for (int k = 0; k < kt; ++k) {
-    float a[8], b[8];
-    if (A_VEC) {
-      const float4 a0 = *reinterpret_cast<const float4*>(A + k * lda + i0);
-      const float4 a1 = *reinterpret_cast<const float4*>(A + k * lda + i0 + 4);
-      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = A[k * lda + i0 + i];
-    }
-    const float4 b0 = *reinterpret_cast<const float4*>(B + k * 128 + j0);
-    const float4 b1 = *reinterpret_cast<const float4*>(B + k * 128 + j0 + 4);
-    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-  }
+// MN-major tf32 operands have ONE legal smem layout (cutlass sm100_smem_selector: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout"): SWIZZLE_128B_BASE32B, atoms of 4 K-rows x 32 MN-elements (512 B),
+// the 32-byte chunk index of a row XORed with the K-row (Swizzle<2,5,2>); consecutive MN atoms lbo bytes apart,
+// consecutive 4-row K groups sbo bytes apart (one K = 8 MMA reads two groups).
+__device__ __forceinline__ uint64_t desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                    // SWIZZLE_128B_BASE32B
+  return d;
 }
+// byte offset of the 16-byte chunk c16 (0..7) of K-row r (0..7) inside an 8-row x 128-byte block of that layout
+__device__ __forceinline__ uint32_t mn_chunk_off(int r, int c16) {
+  return (uint32_t)(r >> 2) * 512u + (uint32_t)(r & 3) * 128u + (uint32_t)(((c16 >> 1) ^ (r & 3)) << 5) + (uint32_t)(c16 & 1) * 16u;
+}
+// cute::UMMA::InstrDescriptor: fp32 accumulate, tf32 x tf32, M = 128, N = n; bits 15 / 16 select MN-major A / B
+__host__ __device__ constexpr uint32_t idesc_tf32(int n, bool mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+  hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+  lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+}
+// 4 consecutive floats of a row that is only guaranteed 4-byte aligned; elements at or beyond `valid` read as 0
+__device__ __forceinline__ float4 load4(const float* src, int valid, bool a16, bool a8, bool read_only) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid >= 4 && a16) {
+    v = read_only ? __ldg(reinterpret_cast<const float4*>(src)) : *reinterpret_cast<const float4*>(src);
+  } else if (valid >= 4 && a8) {
+    const float2 p = *reinterpret_cast<const float2*>(src), q = *(reinterpret_cast<const float2*>(src) + 1);
+    v = make_float4(p.x, p.y, q.x, q.y);
+  } else {
+    if (valid > 0) v.x = src[0];
+    if (valid > 1) v.y = src[1];
+    if (valid > 2) v.z = src[2];
+    if (valid > 3) v.w = src[3];
+  }
+  return v;
+}
+}  // namespace mlptc
 
 template <>
 struct FamilyGrad<SGMCMC_FAMILY_MLP> {
-  static size_t smem_bytes(const BigModel& m) { return sizeof(MlpSmem) + 16 + mlp_smem_floats(m.dims) * sizeof(float); }
+  static size_t smem_bytes(const BigModel& m) { return sizeof(MlpSmem) + 16 + mlp_plan(m.dims, m.batch).total_bytes; }
 
-  // one sub-batch of nb <= 128 rows whose table indices are in ms.idx[0..nb)
-  __device__ __noinline__ static void sub_batch(const BigModel& m, MlpSmem& ms, float* fbase, const float* th, float sign, int nb, float* g) {
-    const int L = m.dims[0];
-    const int* sz = m.dims + 1;                       // sz[0..L]
-    const float* X = reinterpret_cast<const float*>(m.data0);
-    const float* Y = reinterpret_cast<const float*>(m.data1);
+  __device__ static void cta_init(const BigModel& m, void* fam_smem) {
+    MlpSmem& ms = *reinterpret_cast<MlpSmem*>(fam_smem);
+    if (threadIdx.x == 0) {
+      mlptc::mbar_init(&ms.bar[0], 1); mlptc::mbar_init(&ms.bar[1], 1);
+      ms.parity[0] = ms.parity[1] = 0;
+      mlptc::fence_barrier_init();
+    }
+    if (threadIdx.x < 32) { mlptc::tmem_alloc(&ms.tmem_base, (uint32_t)mlp_plan(m.dims, m.batch).tmem_cols); mlptc::tmem_relinquish(); }
+    mlptc::tc_fence_before();
+    __syncthreads();
+    mlptc::tc_fence_after();
+  }
+  __device__ static void cta_fini(const BigModel& m, void* fam_smem) {
+    MlpSmem& ms = *reinterpret_cast<MlpSmem*>(fam_smem);
+    mlptc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) mlptc::tmem_dealloc(ms.tmem_base, (uint32_t)mlp_plan(m.dims, m.batch).tmem_cols);
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // Z1 = X W1^T + b1 into act1 (fp32, [rows][zs]); rows >= nb come out as b1.
+  __device__ __noinline__ static void layer1_forward(const BigModel& m, MlpSmem& ms, uint8_t* region, const float* th, int nb,
+                                        int rows, float* Z, int zs) {
+    using namespace mlptc;
+    const int s0 = m.dims[1], s1 = m.dims[2];
+    const int s1n = mlp_n16(s1);
     const int tid = threadIdx.x;
-    const int grp = tid >> 8, gt = tid & 255;         // groups of 256 threads
-    const int tx = gt & 15, ty = gt >> 4;             // 16 x 16 threads, 8 x 8 outputs each
+    const float* X = reinterpret_cast<const float*>(m.data0);
+    const float* W1 = th + m.leaf_off[0];
+    const float* b1 = th + m.leaf_off[1];
+    const bool x16 = (s0 & 3) == 0;                                        // cudaMalloc'd table: rows 16-B aligned
+    const bool w16 = x16 && (reinterpret_cast<uintptr_t>(W1) & 15) == 0;   // [C, P] state rows: 4-B aligned in general
+    const bool w8 = (s0 & 1) == 0 && (reinterpret_cast<uintptr_t>(W1) & 7) == 0;
+    const size_t stage_bytes = 2 * (size_t)MLP_ROWS * 128 + 2 * (size_t)s1n * 128;
+    const int n_chunks = (s0 + MLP_KC - 1) / MLP_KC;
+    const int s0p8 = (s0 + 7) & ~7;
+    const uint32_t idesc = idesc_tf32(s1n, false);
+    const uint32_t tmem = ms.tmem_base;
+    uint32_t par[2] = {ms.parity[0], ms.parity[1]};
 
-    // ---- carve shared memory
-    float* act[4];
-    int astr[4];
-    float* p = fbase;
-    for (int l = 1; l <= L; ++l) { act[l] = p; astr[l] = mlp_stride(sz[l]); p += (size_t)MLP_ROWS * astr[l]; }
-    int wmax_even = 0, wmax_odd = 0;
-    for (int l = 1; l <= L; ++l) { int& w = ((L - l) & 1) ? wmax_odd : wmax_even; if (sz[l] > w) w = sz[l]; }
-    float* dzbuf[2];
-    dzbuf[0] = p; p += (size_t)MLP_ROWS * mlp_stride(wmax_even);
-    dzbuf[1] = p; p += (size_t)MLP_ROWS * mlp_stride(wmax_odd > 0 ? wmax_odd : 1);
-    p = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
-    float* stA = p + (size_t)grp * 2 * MLP_KT * 128;  // [KT][128]
-    float* stB = stA + MLP_KT * 128;                  // [KT][128]
+    // this thread's items: rows tid >> 3 and (tid >> 3) + 64 of X and of W1 (if in range); 16-byte chunk tid & 7
+    const int ch = tid & 7;
+    const int r0 = tid >> 3, r1 = r0 + 64;
+    const float* xsrc0 = r0 < nb ? X + (size_t)ms.idx[r0] * s0 : nullptr;
+    const float* xsrc1 = r1 < nb ? X + (size_t)ms.idx[r1] * s0 : nullptr;
+    const float* wsrc0 = r0 < s1 ? W1 + (size_t)r0 * s0 : nullptr;
+    const float* wsrc1 = r1 < s1 ? W1 + (size_t)r1 * s0 : nullptr;
+    const bool w0_in = r0 < s1n, w1_in = r1 < s1n;
+    const uint32_t off0 = (uint32_t)r0 * 128u + (uint32_t)((ch ^ (r0 & 7)) << 4);
+    const uint32_t off1 = (uint32_t)r1 * 128u + (uint32_t)((ch ^ (r1 & 7)) << 4);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // =================================================================== layer 1 forward: Z1 = X W1^T + b1
-    {
-      const int s0 = sz[0], s1 = sz[1];
-      const float* W1 = th + m.leaf_off[0];
-      const float* b1 = th + m.leaf_off[1];
-      float acc[8][8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-      const int n_kt = (s0 + MLP_KT - 1) / MLP_KT;
-      const int per = (n_kt + MLP_GROUPS - 1) / MLP_GROUPS;
-      const int kt_lo = grp * per, kt_hi = min(n_kt, kt_lo + per);
-      const int lrow = gt & 127, lhalf = gt >> 7;     // loader mapping: row, 8-float half of the KT slab
-      const bool vec_ok = (s0 & 3) == 0;
-      // the [C, P] state rows are only 4-byte aligned in general (P = 79,510 for 784-100-10)
-      const bool vec_w = vec_ok && (reinterpret_cast<uintptr_t>(W1) & 15) == 0;
-      for (int t = kt_lo; t < kt_hi; ++t) {
-        const int k0 = t * MLP_KT + lhalf * 8;
-        float xa[8], wb[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xa[j] = wb[j] = 0.f;
-        if (lrow < nb) {
-          const float* src = X + (size_t)ms.idx[lrow] * s0 + k0;
-          if (vec_ok && k0 + 8 <= s0) {
-            const float4 q0 = __ldg(reinterpret_cast<const float4*>(src)), q1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-            xa[0] = q0.x; xa[1] = q0.y; xa[2] = q0.z; xa[3] = q0.w; xa[4] = q1.x; xa[5] = q1.y; xa[6] = q1.z; xa[7] = q1.w;
-          } else {
-            for (int j = 0; j < 8; ++j) if (k0 + j < s0) xa[j] = __ldg(src + j);
-          }
+    float4 xv0, xv1, wv0, wv1;
+    auto fetch = [&](int c) {
+      const int k = c * MLP_KC + ch * 4;
+      const int valid = s0 - k;
+      xv0 = xsrc0 ? load4(xsrc0 + k, valid, x16, x16, true) : zero4;
+      xv1 = xsrc1 ? load4(xsrc1 + k, valid, x16, x16, true) : zero4;
+      wv0 = wsrc0 ? load4(wsrc0 + k, valid, w16, w8, false) : zero4;
+      wv1 = wsrc1 ? load4(wsrc1 + k, valid, w16, w8, false) : zero4;
+    };
+    fetch(0);
+    int uses[2] = {0, 0};
+    for (int c = 0; c < n_chunks; ++c) {
+      const int st = c & 1;
+      uint8_t* sb = region + (size_t)st * stage_bytes;
+      uint8_t* xhi = sb;
+      uint8_t* xlo = sb + MLP_ROWS * 128;
+      uint8_t* whi = sb + 2 * MLP_ROWS * 128;
+      uint8_t* wlo = whi + (size_t)s1n * 128;
+      if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }   // MMAs of chunk c - 2 retired
+      float4 hi, lo;
+      split4(xv0, hi, lo); *reinterpret_cast<float4*>(xhi + off0) = hi; *reinterpret_cast<float4*>(xlo + off0) = lo;
+      split4(xv1, hi, lo); *reinterpret_cast<float4*>(xhi + off1) = hi; *reinterpret_cast<float4*>(xlo + off1) = lo;
+      if (w0_in) { split4(wv0, hi, lo); *reinterpret_cast<float4*>(whi + off0) = hi; *reinterpret_cast<float4*>(wlo + off0) = lo; }
+      if (w1_in) { split4(wv1, hi, lo); *reinterpret_cast<float4*>(whi + off1) = hi; *reinterpret_cast<float4*>(wlo + off1) = lo; }
+      if (c + 1 < n_chunks) fetch(c + 1);                                    // in flight while the MMAs of chunk c run
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const int slices = min(MLP_KC, s0p8 - c * MLP_KC) / 8;
+        const uint64_t dxh = desc_k_sw128(smem_u32(xhi)), dxl = desc_k_sw128(smem_u32(xlo));
+        const uint64_t dwh = desc_k_sw128(smem_u32(whi)), dwl = desc_k_sw128(smem_u32(wlo));
+        for (int s = 0; s < slices; ++s) {
+          const uint64_t adv = (uint64_t)(s * 2);                            // 32 bytes of K per tf32 MMA
+          umma_tf32(tmem, dxl + adv, dwh + adv, idesc, (c | s) ? 1u : 0u);
+          umma_tf32(tmem, dxh + adv, dwl + adv, idesc, 1u);
+          umma_tf32(tmem, dxh + adv, dwh + adv, idesc, 1u);
         }
-        if (lrow < s1) {
-          const float* src = W1 + (size_t)lrow * s0 + k0;
-          if (vec_w && k0 + 8 <= s0) {
-            const float4 q0 = *reinterpret_cast<const float4*>(src), q1 = *(reinterpret_cast<const float4*>(src) + 1);
-            wb[0] = q0.x; wb[1] = q0.y; wb[2] = q0.z; wb[3] = q0.w; wb[4] = q1.x; wb[5] = q1.y; wb[6] = q1.z; wb[7] = q1.w;
-          } else {
-            for (int j = 0; j < 8; ++j) if (k0 + j < s0) wb[j] = src[j];
-          }
-        }
-        asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");      // previous slab fully consumed
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { stA[(lhalf * 8 + j) * 128 + lrow] = xa[j]; stB[(lhalf * 8 + j) * 128 + lrow] = wb[j]; }
-        asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
-        if (ty * 8 < nb && tx * 8 < s1) mlp_microkernel<true>(acc, stA, 128, ty * 8, stB, tx * 8, MLP_KT);
+        tc_commit(&ms.bar[st]);
       }
-      // fold the 4 split-K partials into act[1] (bias added by group 0), fixed order -> deterministic
-      float* Z = act[1];
-      const int zs = astr[1];
-      for (int gsel = 0; gsel < MLP_GROUPS; ++gsel) {
-        if (grp == gsel) {
+      ++uses[st];
+    }
+    for (int st = 0; st < 2; ++st)
+      if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }
+    tc_fence_after();
+    // epilogue: warp w reads TMEM lanes 32 (w & 3) .. + 31 (= batch rows), columns 32 (w >> 2) .. + 31
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      const int row = (warp & 3) * 32 + lane;
+      const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+      const int c_end = min(s1n, (warp >> 2) * 32 + 32);
+      for (int c0 = (warp >> 2) * 32; c0 < c_end; c0 += 8) {
+        uint32_t v[8];
+        tmem_ld8(tl + c0, v);
+        tmem_ld_wait();
+        if (row < rows) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = ty * 8 + i;
-            if (r < MLP_ROWS) {
+          for (int e = 0; e < 8; ++e)
+            if (c0 + e < s1) Z[row * zs + c0 + e] = __uint_as_float(v[e]) + b1[c0 + e];
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) { ms.parity[0] = par[0]; ms.parity[1] = par[1]; }
+    __syncthreads();
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // dZ1 element (b, j) -> hi / lo copies of the MN-major B operand: K group b / 8, MN atom j / 32
+  __device__ static __forceinline__ void put_dz1(uint8_t* bhi, uint8_t* blo, int b, int j, float v) {
+    const uint32_t off = (uint32_t)(b >> 3) * 4096u + (uint32_t)(j >> 5) * 1024u + mlptc::mn_chunk_off(b & 7, (j & 31) >> 2) +
+                         (uint32_t)(j & 3) * 4u;
+    const float hi = mlptc::tf32_rna(v);
+    *reinterpret_cast<float*>(bhi + off) = hi;
+    *reinterpret_cast<float*>(blo + off) = mlptc::tf32_rna(v - hi);
+  }
+
+  // gW1[n][k] += sign * sum_b dZ1[b][n] X[b][k]   (dZ1 hi / lo already staged in `region`)
+  __device__ __noinline__ static void layer1_backward(const BigModel& m, MlpSmem& ms, uint8_t* region, uint8_t* xs, float sign,
+                                         int nb, int rows, float* gW, bool overwrite) {
+    using namespace mlptc;
+    const int s0 = m.dims[1], s1 = m.dims[2];
+    const int s1n = mlp_n16(s1);
+    const int tid = threadIdx.x;
+    const float* X = reinterpret_cast<const float*>(m.data0);
+    const bool x16 = (s0 & 3) == 0;
+    const int G = (nb + 7) >> 3;                                  // K groups of 8 batch rows
+    const int n_tiles = (s0 + 127) >> 7;                          // M tiles of 128 input columns
+    const int tiles_per_pass = 4;                                 // 4 s1n <= 512 TMEM columns
+    const uint32_t idesc = idesc_tf32(s1n, true);
+    const uint32_t tmem = ms.tmem_base;
+    const uint8_t* bhi = region;
+    const uint8_t* blo = region + (size_t)(rows / 8) * 4096;
+    uint32_t par[2] = {ms.parity[0], ms.parity[1]};
+    const size_t stage_bytes = 2 * 8 * 256 * sizeof(float);      // [hi 8 KB | lo 8 KB]
+
+    // loader mapping for one unit = 8 batch rows x 256 columns: row tid >> 6, 16-byte chunk tid & 63
+    const int lr = tid >> 6, c4 = tid & 63;
+    const uint32_t soff = (uint32_t)(c4 >> 3) * 1024u + mn_chunk_off(lr, c4 & 7);
+
+    for (int t0 = 0; t0 < n_tiles; t0 += tiles_per_pass) {
+      const int pass_tiles = min(tiles_per_pass, n_tiles - t0);
+      const int npp = (pass_tiles + 1) >> 1;                      // tile pairs in this pass
+      const int units = G * npp;
+      float4 xv;
+      auto fetch = [&](int u) {
+        const int g = u / npp, p = u - g * npp;
+        const int b = g * 8 + lr;
+        const int k = (t0 + 2 * p) * 128 + c4 * 4;
+        xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < nb && k < s0) xv = load4(X + (size_t)ms.idx[b] * s0 + k, s0 - k, x16, x16, true);
+      };
+      fetch(0);
+      int uses[2] = {0, 0};
+      for (int u = 0; u < units; ++u) {
+        const int st = u & 1;
+        uint8_t* sb = xs + (size_t)st * stage_bytes;
+        if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }
+        float4 hi, lo;
+        split4(xv, hi, lo);
+        *reinterpret_cast<float4*>(sb + soff) = hi;
+        *reinterpret_cast<float4*>(sb + 8192 + soff) = lo;
+        if (u + 1 < units) fetch(u + 1);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          const int g = u / npp, p = u - g * npp;
+          const uint64_t dbh = desc_mn_sw128_32b(smem_u32(bhi) + (uint32_t)g * 4096u, 1024u, 512u);
+          const uint64_t dbl = desc_mn_sw128_32b(smem_u32(blo) + (uint32_t)g * 4096u, 1024u, 512u);
+          for (int t = 0; t < 2; ++t) {
+            if (2 * p + t >= pass_tiles) break;
+            const uint64_t dah = desc_mn_sw128_32b(smem_u32(sb) + (uint32_t)t * 4096u, 1024u, 512u);
+            const uint64_t dal = desc_mn_sw128_32b(smem_u32(sb) + 8192u + (uint32_t)t * 4096u, 1024u, 512u);
+            const uint32_t acc = tmem + (uint32_t)((2 * p + t) * s1n);
+            umma_tf32(acc, dal, dbh, idesc, g ? 1u : 0u);
+            umma_tf32(acc, dah, dbl, idesc, 1u);
+            umma_tf32(acc, dah, dbh, idesc, 1u);
+          }
+          tc_commit(&ms.bar[st]);
+        }
+        ++uses[st];
+      }
+      for (int st = 0; st < 2; ++st)
+        if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }
+      tc_fence_after();
+      // epilogue: warp group (warp >> 2) owns tile t0 + (warp >> 2); lane = input column k, TMEM column = unit n
+      {
+        const int warp = tid >> 5, lane = tid & 31;
+        const int tq = warp >> 2;
+        const int k = (t0 + tq) * 128 + (warp & 3) * 32 + lane;
+        if (tq < pass_tiles) {
+          const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tq * s1n);
+          for (int n0 = 0; n0 < s1n; n0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tl + n0, v);
+            tmem_ld_wait();
+            if (k < s0) {
+              if (overwrite) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int c = tx * 8 + j;
-                if (c < s1) Z[r * zs + c] = (gsel == 0 ? b1[c] : Z[r * zs + c]) + acc[i][j];
+                for (int e = 0; e < 16; ++e)
+                  if (n0 + e < s1) gW[(size_t)(n0 + e) * s0 + k] = sign * __uint_as_float(v[e]);
+              } else {
+                float old[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) old[e] = n0 + e < s1 ? __ldcg(gW + (size_t)(n0 + e) * s0 + k) : 0.f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  if (n0 + e < s1) gW[(size_t)(n0 + e) * s0 + k] = fmaf(sign, __uint_as_float(v[e]), old[e]);
               }
             }
           }
         }
-        __syncthreads();
       }
+      tc_fence_before();
+      __syncthreads();                                            // TMEM tiles are free for the next pass
     }
+    if (tid == 0) { ms.parity[0] = par[0]; ms.parity[1] = par[1]; }
+    __syncthreads();
+  }
+
+  // ---------------------------------------------------------------------------------------------------
+  // one sub-batch of nb <= plan.rows rows whose table indices are in ms.idx[0..nb)
+  __device__ __noinline__ static void sub_batch(const BigModel& m, MlpSmem& ms, uint8_t* base, const float* th, float sign,
+                                                int nb, float* g, bool overwrite) {
+    const int L = m.dims[0];
+    const int* sz = m.dims + 1;                       // sz[0..L]
+    const float* Y = reinterpret_cast<const float*>(m.data1);
+    const int tid = threadIdx.x;
+    const MlpPlan plan = mlp_plan(m.dims, m.batch);
+    const int R = plan.rows;
+    uint8_t* region = base;
+    uint8_t* xs = base + plan.region_bytes;
+    float* fbase = reinterpret_cast<float*>(xs + plan.xs_bytes);
+    auto act = [&](int l) { return fbase + plan.act_off(l); };
+    auto astr = [&](int l) { return mlp_stride(sz[l]); };
+    auto dzbuf = [&](int k) { return fbase + plan.dz_off(k); };
+    auto dzstr = [&](int k) { return mlp_stride(plan.dz_w(k)); };
+
+    layer1_forward(m, ms, region, th, nb, R, act(1), astr(1));
 
     // =================================================================== softmax + small layers forward
     for (int l = 1; l < L; ++l) {
-      float* A = act[l];
-      const int as = astr[l], w = sz[l];
-      if (tid < MLP_ROWS) {                             // a_l = softmax(z_l), one thread per row
+      float* A = act(l);
+      const int as = astr(l), w = sz[l];
+      if (tid < R) {                                    // a_l = softmax(z_l), one thread per row
         float mx = -INFINITY;
         for (int c = 0; c < w; ++c) mx = fmaxf(mx, A[tid * as + c]);
         float sum = 0.f;
@@ -188,12 +443,12 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         for (int c = 0; c < w; ++c) A[tid * as + c] *= inv;
       }
       __syncthreads();
-      float* Zn = act[l + 1];
-      const int zs = astr[l + 1], wn = sz[l + 1];
+      float* Zn = act(l + 1);
+      const int zs = astr(l + 1), wn = sz[l + 1];
       const float* Wn = th + m.leaf_off[2 * l];
       const float* bn = th + m.leaf_off[2 * l + 1];
-      for (int o = tid; o < MLP_ROWS * wn; o += blockDim.x) {     // z_{l+1}[b][n] = a_l[b] . W[n] + b[n]
-        const int b = o % MLP_ROWS, n = o / MLP_ROWS;
+      for (int o = tid; o < R * wn; o += blockDim.x) {            // z_{l+1}[b][n] = a_l[b] . W[n] + b[n]
+        const int b = o % R, n = o / R;
         float accv = 0.f;
         const float* wr = Wn + (size_t)n * w;
         for (int k = 0; k < w; ++k) accv = fmaf(A[b * as + k], wr[k], accv);
@@ -203,12 +458,12 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     }
 
     // =================================================================== output layer: dZ_L = y - sum(y) softmax(z_L)
-    float* dz = dzbuf[0];
-    int dzs = mlp_stride(wmax_even);
+    float* dz = dzbuf(0);
+    int dzs = dzstr(0);
     {
-      const int w = sz[L], zs = astr[L];
-      const float* Z = act[L];
-      if (tid < MLP_ROWS) {
+      const int w = sz[L], zs = astr(L);
+      const float* Z = act(L);
+      if (tid < R) {
         if (tid < nb) {
           const float* yr = Y + (size_t)ms.idx[tid] * w;
           float mx = -INFINITY, ys = 0.f;
@@ -224,12 +479,18 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       __syncthreads();
     }
 
+    uint8_t* bhi = region;
+    uint8_t* blo = region + (size_t)(R / 8) * 4096;
+    const int s1 = sz[1], s1n = mlp_n16(s1);
+    float* gb1 = g + m.leaf_off[1];
+    float* red = reinterpret_cast<float*>(xs);          // [16 warps][128]: free until layer1_backward streams X
+
     // =================================================================== backward through layers L .. 2
     int cur = 0;
     for (int l = L; l >= 2; --l) {
       const int w = sz[l], wp = sz[l - 1];
-      const float* A = act[l - 1];
-      const int as = astr[l - 1];
+      const float* A = act(l - 1);
+      const int as = astr(l - 1);
       const float* Wl = th + m.leaf_off[2 * (l - 1)];
       float* gW = g + m.leaf_off[2 * (l - 1)];
       float* gb = g + m.leaf_off[2 * (l - 1) + 1];
@@ -244,92 +505,85 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         for (int b = 0; b < nb; ++b) accv += dz[b * dzs + n];
         gb[n] += sign * accv;
       }
-      // dA_{l-1} = dz W_l ; dZ_{l-1} = a (dA - sum_k a dA)   (softmax Jacobian)
-      float* dn = dzbuf[cur ^ 1];
-      const int dns = mlp_stride(cur ? wmax_even : (wmax_odd > 0 ? wmax_odd : 1));
-      for (int o = tid; o < MLP_ROWS * wp; o += blockDim.x) {
-        const int b = o % MLP_ROWS, k = o / MLP_ROWS;
-        float accv = 0.f;
-        for (int n = 0; n < w; ++n) accv = fmaf(dz[b * dzs + n], Wl[(size_t)n * wp + k], accv);
-        dn[b * dns + k] = accv;
-      }
-      __syncthreads();
-      if (tid < MLP_ROWS) {
+      if (l > 2) {
+        // dA_{l-1} = dz W_l ; dZ_{l-1} = a (dA - sum_k a dA)   (softmax Jacobian)
+        float* dn = dzbuf(cur ^ 1);
+        const int dns = dzstr(cur ^ 1);
+        for (int o = tid; o < R * wp; o += blockDim.x) {
+          const int b = o % R, k = o / R;
+          float accv = 0.f;
+          for (int n = 0; n < w; ++n) accv = fmaf(dz[b * dzs + n], Wl[(size_t)n * wp + k], accv);
+          dn[b * dns + k] = accv;
+        }
+        __syncthreads();
+        if (tid < R) {
+          float dotv = 0.f;
+          for (int k = 0; k < wp; ++k) dotv = fmaf(A[tid * as + k], dn[tid * dns + k], dotv);
+          for (int k = 0; k < wp; ++k) dn[tid * dns + k] = tid < nb ? A[tid * as + k] * (dn[tid * dns + k] - dotv) : 0.f;
+        }
+        __syncthreads();
+        dz = dn; dzs = dns; cur ^= 1;
+      } else {
+        // l == 2: dZ_1 of row b by a quad of threads (columns j = q, q + 4, ...), written straight into the
+        // tensor-core operand (hi / lo); bias gradient by fixed-order shuffles + a per-warp fold.
+        const int b = tid >> 2, q = tid & 3;
+        const bool live = b < nb;
+        const int warp = tid >> 5, lane = tid & 31;
+        auto dA = [&](int j) {                                      // (dz W_2)[b][j]
+          float accv = 0.f;
+          for (int n = 0; n < w; ++n) accv = fmaf(dz[b * dzs + n], Wl[(size_t)n * wp + j], accv);
+          return accv;
+        };
         float dotv = 0.f;
-        for (int k = 0; k < wp; ++k) dotv = fmaf(A[tid * as + k], dn[tid * dns + k], dotv);
-        for (int k = 0; k < wp; ++k) dn[tid * dns + k] = tid < nb ? A[tid * as + k] * (dn[tid * dns + k] - dotv) : 0.f;
+        if (live)
+          for (int j = q; j < wp; j += 4) dotv = fmaf(A[b * as + j], dA(j), dotv);
+        dotv += __shfl_xor_sync(FULL, dotv, 1);
+        dotv += __shfl_xor_sync(FULL, dotv, 2);
+        for (int j = q; j < s1n; j += 4) {                          // trip count is warp-uniform (s1n % 4 == 0)
+          float v = (live && j < wp) ? A[b * as + j] * (dA(j) - dotv) : 0.f;
+          if (b < R) put_dz1(bhi, blo, b, j, v);
+          v += __shfl_xor_sync(FULL, v, 4);
+          v += __shfl_xor_sync(FULL, v, 8);
+          v += __shfl_xor_sync(FULL, v, 16);
+          if (lane < 4) red[warp * 128 + j] = v;
+        }
+        __syncthreads();
+        for (int n = tid; n < s1; n += blockDim.x) {
+          float accv = 0.f;
+          for (int w16 = 0; w16 < 16; ++w16) accv += red[w16 * 128 + n];
+          gb1[n] += sign * accv;
+        }
       }
-      __syncthreads();
-      dz = dn; dzs = dns; cur ^= 1;
     }
-
-    // =================================================================== layer 1 backward: dW1 = dZ1^T X, db1
-    {
-      const int s0 = sz[0], s1 = sz[1];
-      float* gW = g + m.leaf_off[0];
-      float* gb = g + m.leaf_off[1];
+    if (L == 1) {                                                   // the output layer is layer 1: convert its fp32 dZ
       for (int n = tid; n < s1; n += blockDim.x) {
         float accv = 0.f;
         for (int b = 0; b < nb; ++b) accv += dz[b * dzs + n];
-        gb[n] += sign * accv;
+        gb1[n] += sign * accv;
       }
-      const int n_ct = (s0 + 127) / 128;                 // 128-column tiles of dW1, dealt to the 4 groups
-      const bool vec_ok = (s0 & 3) == 0;
-      const int lk = gt >> 4, lc = (gt & 15) * 8;        // loader mapping: batch row in the slab, 8 columns
-      for (int ct = grp; ct < n_ct; ct += MLP_GROUPS) {
-        const int c0 = ct * 128;
-        float acc[8][8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-        for (int b0 = 0; b0 < nb; b0 += MLP_KT) {
-          float xv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xv[j] = 0.f;
-          if (b0 + lk < nb) {
-            const float* src = X + (size_t)ms.idx[b0 + lk] * s0 + c0 + lc;
-            if (vec_ok && c0 + lc + 8 <= s0) {
-              const float4 q0 = __ldg(reinterpret_cast<const float4*>(src)), q1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-              xv[0] = q0.x; xv[1] = q0.y; xv[2] = q0.z; xv[3] = q0.w; xv[4] = q1.x; xv[5] = q1.y; xv[6] = q1.z; xv[7] = q1.w;
-            } else {
-              for (int j = 0; j < 8; ++j) if (c0 + lc + j < s0) xv[j] = __ldg(src + j);
-            }
-          }
-          asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
-          *reinterpret_cast<float4*>(stB + lk * 128 + lc) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-          *reinterpret_cast<float4*>(stB + lk * 128 + lc + 4) = make_float4(xv[4], xv[5], xv[6], xv[7]);
-          asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory");
-          const int kt = min(MLP_KT, nb - b0);
-          // rows of the output = hidden units (ty), A operand = dZ1[b][n] read straight from its buffer
-          if (ty * 8 < s1 && c0 + tx * 8 < s0) mlp_microkernel<false>(acc, dz + (size_t)b0 * dzs, dzs, ty * 8, stB, tx * 8, kt);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = ty * 8 + i;
-          if (n < s1) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = c0 + tx * 8 + j;
-              if (c < s0) gW[(size_t)n * s0 + c] += sign * acc[i][j];
-            }
-          }
-        }
+      for (int e = tid; e < R * s1n; e += blockDim.x) {
+        const int b = e / s1n, j = e - b * s1n;
+        put_dz1(bhi, blo, b, j, (j < s1 && b < nb) ? dz[b * dzs + j] : 0.f);
       }
     }
+    mlptc::fence_proxy_async();
     __syncthreads();
+
+    layer1_backward(m, ms, region, xs, sign, nb, R, g + m.leaf_off[0], overwrite);
   }
 
   __device__ static void lik_pass(const BigModel& m, void* fam_smem, const float* theta, const float* center,
-                                  bool sequential, const RandintPlan& plan, unsigned seq_base, unsigned count, float* g) {
+                                  bool sequential, const RandintPlan& plan, unsigned seq_base, unsigned count, float* g,
+                                  bool fresh) {
     MlpSmem& ms = *reinterpret_cast<MlpSmem*>(fam_smem);
-    float* fbase = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(&ms + 1) + 15) & ~(uintptr_t)15);
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(&ms + 1) + 1023) & ~(uintptr_t)1023);
+    const unsigned rows = (unsigned)mlp_plan(m.dims, m.batch).rows;
     const unsigned h = (count + 1u) >> 1;
-    for (unsigned base = 0; base < count; base += MLP_ROWS) {
-      const int nb = (int)min((unsigned)MLP_ROWS, count - base);
+    for (unsigned base_row = 0; base_row < count; base_row += rows) {
+      const int nb = (int)min(rows, count - base_row);
       __syncthreads();
       if (threadIdx.x < (unsigned)nb) {
-        const unsigned pos = base + threadIdx.x;
+        const unsigned pos = base_row + threadIdx.x;
         unsigned id;
         if (sequential) {
           id = seq_base + pos;
@@ -341,8 +595,9 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         ms.idx[threadIdx.x] = (int)id;
       }
       __syncthreads();
-      sub_batch(m, ms, fbase, theta, 1.0f, nb, g);
-      if (center) sub_batch(m, ms, fbase, center, -1.0f, nb, g);
+      // the first sub-batch into an all-zero buffer stores dW1 instead of read-modify-writing it
+      sub_batch(m, ms, base, theta, 1.0f, nb, g, fresh && base_row == 0);
+      if (center) sub_batch(m, ms, base, center, -1.0f, nb, g, false);
     }
   }
 };

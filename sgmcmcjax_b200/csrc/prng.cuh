@@ -62,20 +62,44 @@ __device__ __forceinline__ void split2(Key k, Key& first, Key& second) {
   first.a = a0; first.b = b0; second.a = a1; second.b = b1;
 }
 
+// 1-instruction MUFU approximations (max relative error ~2^-22): far inside the 1e-5 parity bar, and they
+// take the IEEE slow paths (10-30 instructions each) out of the per-element noise / preconditioner math.
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // XLA's fp32 ErfInv (Giles 2010) - NOT CUDA's erfinvf, which differs by ~6e-6 relative.
+//   w = -log1p(-x*x) is evaluated as -ln(1 - rn(x*x)) with the MUFU logarithm (the product is rounded FIRST,
+//   as XLA does: for |x| -> 1 that rounding dominates w, and a fused 1 - x*x would be "too accurate" to match;
+//   1 - rn(x*x) itself is exact for x*x >= 1/2): the absolute error of w is
+//   <= ~2e-7 in the central branch (|d ln p / dw| ~ 0.2 -> ~4e-8 relative in the result) and <= ~3 ulp of w in
+//   the tail branch (w >= 5, 0.3 % of draws; sqrt halves it).  The two polynomial branches are a real branch:
+//   the tail is rare, so a warp almost always runs only the 9 central FMAs.
 __device__ __forceinline__ float erfinv_xla(float x) {
-  float w = -log1pf(-x * x);
-  const bool central = w < 5.0f;
-  w = central ? w - 2.5f : sqrtf(w) - 3.0f;
-  float p = central ? 2.81022636e-08f : -0.000200214257f;
-  p = fmaf(p, w, central ? 3.43273939e-07f : 0.000100950558f);
-  p = fmaf(p, w, central ? -3.5233877e-06f : 0.00134934322f);
-  p = fmaf(p, w, central ? -4.39150654e-06f : -0.00367342844f);
-  p = fmaf(p, w, central ? 0.00021858087f : 0.00573950773f);
-  p = fmaf(p, w, central ? -0.00125372503f : -0.0076224613f);
-  p = fmaf(p, w, central ? -0.00417768164f : 0.00943887047f);
-  p = fmaf(p, w, central ? 0.246640727f : 1.00167406f);
-  p = fmaf(p, w, central ? 1.50140941f : 2.83297682f);
+  const float w = -__logf(__fsub_rn(1.0f, __fmul_rn(x, x)));
+  float p;
+  if (w < 5.0f) {
+    const float t = w - 2.5f;
+    p = 2.81022636e-08f;
+    p = fmaf(p, t, 3.43273939e-07f);
+    p = fmaf(p, t, -3.5233877e-06f);
+    p = fmaf(p, t, -4.39150654e-06f);
+    p = fmaf(p, t, 0.00021858087f);
+    p = fmaf(p, t, -0.00125372503f);
+    p = fmaf(p, t, -0.00417768164f);
+    p = fmaf(p, t, 0.246640727f);
+    p = fmaf(p, t, 1.50140941f);
+  } else {
+    const float t = fast_sqrt(w) - 3.0f;
+    p = -0.000200214257f;
+    p = fmaf(p, t, 0.000100950558f);
+    p = fmaf(p, t, 0.00134934322f);
+    p = fmaf(p, t, -0.00367342844f);
+    p = fmaf(p, t, 0.00573950773f);
+    p = fmaf(p, t, -0.0076224613f);
+    p = fmaf(p, t, 0.00943887047f);
+    p = fmaf(p, t, 1.00167406f);
+    p = fmaf(p, t, 2.83297682f);
+  }
   return fabsf(x) == 1.0f ? copysignf(INFINITY, x) : p * x;
 }
 
