@@ -294,9 +294,10 @@ struct BigCtx {
                     [&](unsigned e, const Elt& v) {
                       aux1[e] = fmaf(cf.hh, v.g, v.a);
                       if (consume) { grad[e] = 0.f; if (sample) __stcs(sample + e, v.x); }
+                      else grad[e] = v.g;          // keep the finalised value: the next update reads it as is
                     });
       __syncthreads();
-      if (consume) grad_raw = false;
+      grad_raw = false;
       return;
     }
     for (int leaf = 0; leaf < m.n_leaves; ++leaf) {

@@ -465,7 +465,7 @@ struct ChainCtx {
 };
 
 template <int FAMILY, bool CV, int NCH>
-__global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const __grid_constant__ VecModel m, const __grid_constant__ VecRun run) {
+__global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel m, const VecRun run) {
   extern __shared__ __align__(16) float smem_raw[];
   const int W = blockDim.x >> 5;
   const int PP = ((m.P > m.DS ? m.P : m.DS) + 3) & ~3;
