@@ -52,7 +52,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # SGMCMC_B200_LIB: load an alternative build of the same ABI (kernel-variant experiments)
+    return os.environ.get("SGMCMC_B200_LIB") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = True):
@@ -61,7 +62,7 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if build_if_missing and _build.is_stale():
+    if build_if_missing and path == _build.LIB_PATH and _build.is_stale():
         try:
             _build.build()
         except Exception as e:  # stale-but-present library is still usable

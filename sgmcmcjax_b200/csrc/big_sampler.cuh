@@ -80,7 +80,7 @@ __device__ __forceinline__ float big_block_sum(float v, float* red) {
 }
 
 // One element of a leaf in flight: x, up to two auxiliary values and the (finalised) gradient.
-struct Elt { float x, a, b, g; };
+struct Elt { float x, a, b, g, fb, cen; };   // fb / cen: full-batch gradient and centre of the CV / SVRG estimators
 
 // For every element e of an n-element leaf: v = ld(e) ... st(e, v, xi) with xi = normal(key, (n,))[e].
 // One threefry block feeds elements m and m + ceil(n/2) (jax's half-split counter layout).  U blocks per
@@ -89,42 +89,58 @@ struct Elt { float x, a, b, g; };
 template <int U, class LD, class ST>
 __device__ __forceinline__ void leaf_pass(unsigned n, Key key, LD ld, ST st) {
   const unsigned h = (n + 1u) >> 1;
+  const unsigned hf = n - h;                     // blocks m < hf have both elements m and m + h in range
+  const unsigned bd = blockDim.x;
+  unsigned m0 = threadIdx.x;
+  // main loop: no guards, so the 2U loads of an iteration issue back to back
 #pragma unroll 1
-  for (unsigned m0 = threadIdx.x; m0 < h; m0 += U * blockDim.x) {
+  for (; m0 + (U - 1) * bd < hf; m0 += U * bd) {
     Elt e0[U], e1[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned m = m0 + u * blockDim.x;
-      if (m < h) { e0[u] = ld(m); if (m + h < n) e1[u] = ld(m + h); }
-    }
+    for (int u = 0; u < U; ++u) { e0[u] = ld(m0 + u * bd); e1[u] = ld(m0 + u * bd + h); }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const unsigned m = m0 + u * blockDim.x;
-      if (m < h) {
-        uint32_t w0, w1;
-        stream_block(key, m, n, w0, w1);
-        st(m, e0[u], bits_to_normal(w0));
-        if (m + h < n) st(m + h, e1[u], bits_to_normal(w1));
-      }
+      const unsigned m = m0 + u * bd;
+      uint32_t w0, w1;
+      stream_block(key, m, n, w0, w1);
+      st(m, e0[u], bits_to_normal(w0));
+      st(m + h, e1[u], bits_to_normal(w1));
     }
+  }
+#pragma unroll 1
+  for (; m0 < h; m0 += bd) {                     // tail (and the unpaired middle element of an odd leaf)
+    const bool two = m0 + h < n;
+    const Elt a = ld(m0);
+    const Elt b = two ? ld(m0 + h) : Elt{};
+    uint32_t w0, w1;
+    stream_block(key, m0, n, w0, w1);
+    st(m0, a, bits_to_normal(w0));
+    if (two) st(m0 + h, b, bits_to_normal(w1));
   }
 }
 
 // Same staging without noise: v = ld(e) ... st(e, v).
 template <int U, class LD, class ST>
 __device__ __forceinline__ void plain_pass(unsigned n, LD ld, ST st) {
+  const unsigned bd = blockDim.x;
+  unsigned e0 = threadIdx.x;
 #pragma unroll 1
-  for (unsigned e0 = threadIdx.x; e0 < n; e0 += U * blockDim.x) {
-    Elt v[U];
+  for (; e0 + (2 * U - 1) * bd < n; e0 += 2 * U * bd) {
+    Elt v[2 * U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) { const unsigned e = e0 + u * blockDim.x; if (e < n) v[u] = ld(e); }
+    for (int u = 0; u < 2 * U; ++u) v[u] = ld(e0 + u * bd);
 #pragma unroll
-    for (int u = 0; u < U; ++u) { const unsigned e = e0 + u * blockDim.x; if (e < n) st(e, v[u]); }
+    for (int u = 0; u < 2 * U; ++u) st(e0 + u * bd, v[u]);
   }
+#pragma unroll 1
+  for (; e0 < n; e0 += bd) { const Elt v = ld(e0); st(e0, v); }
 }
 
 template <int FAMILY> struct BigUnroll { static constexpr int value = 2; };                  // 1024 threads: 64 registers
-template <> struct BigUnroll<SGMCMC_FAMILY_MLP> { static constexpr int value = 2; };       // 512 threads: 128 registers
+#ifndef SG_BIG_UNROLL_MLP
+#define SG_BIG_UNROLL_MLP 4
+#endif
+template <> struct BigUnroll<SGMCMC_FAMILY_MLP> { static constexpr int value = SG_BIG_UNROLL_MLP; };       // 512 threads: 128 registers
 
 // ---------------------------------------------------------------------------------------
 // PMF likelihood pass
@@ -204,6 +220,22 @@ struct BigCtx {
     return gscale * raw - prior * x;
   }
 
+  // Gradient consumption in the diffusion passes, specialised at compile time so that the loaders are straight-line
+  // batches of independent loads (a branch between two loads serialises them on their memory latency):
+  //   MODE 0: the buffer holds the finalised gradient; 1: raw sum, standard estimator; 2: raw sum, CV / SVRG.
+  template <int MODE>
+  __device__ __forceinline__ void ld_grad(Elt& t, const float* gbuf, unsigned e, unsigned ge) const {
+    t.g = __ldcg(gbuf + e);
+    if (MODE == 2) { t.fb = fb[ge]; t.cen = center[ge]; }
+  }
+  template <int MODE>
+  __device__ __forceinline__ float gval(const Elt& t) const {
+    if (MODE == 0) return t.g;
+    const float prior = m.coef[1];
+    if (MODE == 2) return t.fb + (gscale * t.g - prior * (t.x - t.cen));        // gradient_estimation.py:72, no cancellation
+    return gscale * t.g - prior * t.x;
+  }
+
   __device__ void zero(float* g) {
     plain_pass<U>((unsigned)m.P, [&](unsigned) { return Elt{}; }, [&](unsigned e, const Elt&) { g[e] = 0.f; });
     __syncthreads();
@@ -217,7 +249,7 @@ struct BigCtx {
     __syncthreads();
     const float prior = m.coef[1];
     // __ldcg: the sums may have been accumulated with L2 atomics, so read them at L2
-    plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v; v.g = __ldcg(out + e); v.x = th[e]; return v; },
+    plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v{}; v.g = __ldcg(out + e); v.x = th[e]; return v; },
                   [&](unsigned e, const Elt& v) { out[e] = v.g - prior * v.x; });
     __syncthreads();
   }
@@ -225,7 +257,7 @@ struct BigCtx {
   // turn a raw buffer into the finalised gradient (launch end, init_fn)
   __device__ void finalize() {
     if (!grad_raw) return;
-    plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v; v.g = __ldcg(grad + e); v.x = theta[e]; return v; },
+    plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v{}; v.g = __ldcg(grad + e); v.x = theta[e]; return v; },
                   [&](unsigned e, const Elt& v) { grad[e] = gfin(v.g, v.x, e); });
     __syncthreads();
     grad_raw = false;
@@ -237,7 +269,7 @@ struct BigCtx {
     if (m.estimator == SGMCMC_EST_SVRG) {
       if (is_init) {                                       // gradient_estimation.py:124-128
         full_grad(theta, svrg_fb);
-        plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v; v.x = theta[e]; v.g = svrg_fb[e]; return v; },
+        plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v{}; v.x = theta[e]; v.g = svrg_fb[e]; return v; },
                       [&](unsigned e, const Elt& v) { svrg_center[e] = v.x; grad[e] = v.g; });
         __syncthreads();
         grad_raw = false;
@@ -245,7 +277,7 @@ struct BigCtx {
       }
       if (i % m.update_rate == 0) {                        // gradient_estimation.py:134-139
         full_grad(theta, svrg_fb);
-        plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v; v.x = theta[e]; return v; },
+        plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v{}; v.x = theta[e]; return v; },
                       [&](unsigned e, const Elt& v) { svrg_center[e] = v.x; });
         __syncthreads();
       }
@@ -285,16 +317,24 @@ struct BigCtx {
 
   // phase 1 = `update` (consumes the carried gradient, leaves the buffer zeroed for the next estimate and
   // emits the sample if `sample` is set); phase 2 = `update2` of the palindromes (gradient stays in the buffer).
-  __device__ __noinline__ void diffuse(int phase, int i, const sgmcmc_step_coef& cf, int key_slot, float* sample) {
+  __device__ void diffuse(int phase, int i, const sgmcmc_step_coef& cf, int key_slot, float* sample) {
+    if (!grad_raw) diffuse_mode<0>(phase, i, cf, key_slot, sample);
+    else if (!is_cv()) diffuse_mode<1>(phase, i, cf, key_slot, sample);
+    else diffuse_mode<2>(phase, i, cf, key_slot, sample);
+  }
+
+  template <int MODE>
+  __device__ __noinline__ void diffuse_mode(int phase, int i, const sgmcmc_step_coef& cf, int key_slot, float* sample) {
     const bool bug = (m.flags & SGMCMC_FLAG_BADODABCV_REFERENCE_BUG) && m.diffusion == SGMCMC_DIFF_BADODAB;
     if (phase == 2 || bug) {                      // baoab / badodab update2: v += dt/2 * g
       const bool consume = phase == 1;
       plain_pass<U>((unsigned)m.P,
-                    [&](unsigned e) { Elt v; v.x = theta[e]; v.a = aux1[e]; v.g = gfin(__ldcg(grad + e), v.x, e); return v; },
-                    [&](unsigned e, const Elt& v) {
-                      aux1[e] = fmaf(cf.hh, v.g, v.a);
-                      if (consume) { grad[e] = 0.f; if (sample) __stcs(sample + e, v.x); }
-                      else grad[e] = v.g;          // keep the finalised value: the next update reads it as is
+                    [&](unsigned e) { Elt t{}; t.x = theta[e]; t.a = aux1[e]; ld_grad<MODE>(t, grad, e, e); return t; },
+                    [&](unsigned e, const Elt& t) {
+                      const float gg = gval<MODE>(t);
+                      aux1[e] = fmaf(cf.hh, gg, t.a);
+                      if (consume) { grad[e] = 0.f; if (sample) __stcs(sample + e, t.x); }
+                      else grad[e] = gg;           // keep the finalised value: the next update reads it as is
                     });
       __syncthreads();
       grad_raw = false;
@@ -309,30 +349,32 @@ struct BigCtx {
       float* v2 = aux2 ? aux2 + off : nullptr;
       float* g = grad + off;
       float* smp = sample ? sample + off : nullptr;
-      // loaders: x, gradient (finalised on the fly), optionally the auxiliaries
-      auto ld_xg = [&](unsigned e) { Elt t; t.x = x[e]; t.a = 0.f; t.b = 0.f; t.g = gfin(__ldcg(g + e), t.x, off + e); return t; };
-      auto ld_xvg = [&](unsigned e) { Elt t; t.x = x[e]; t.a = v[e]; t.b = 0.f; t.g = gfin(__ldcg(g + e), t.x, off + e); return t; };
-      auto ld_xvvg = [&](unsigned e) { Elt t; t.x = x[e]; t.a = v[e]; t.b = v2[e]; t.g = gfin(__ldcg(g + e), t.x, off + e); return t; };
+      // loaders: pure loads of x, the gradient buffer (+ CV terms) and optionally the auxiliaries
+      auto ld_xg = [&](unsigned e) { Elt t{}; t.x = x[e]; ld_grad<MODE>(t, g, e, off + e); return t; };
+      auto ld_xvg = [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; ld_grad<MODE>(t, g, e, off + e); return t; };
+      auto ld_xvvg = [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; t.b = v2[e]; ld_grad<MODE>(t, g, e, off + e); return t; };
       auto emit = [&](unsigned e, float xn) { x[e] = xn; g[e] = 0.f; if (smp) __stcs(smp + e, xn); };
       switch (m.diffusion) {
         case SGMCMC_DIFF_SGLD:
-          leaf_pass<U>(n, lk, ld_xg, [&](unsigned e, const Elt& t, float xi) { emit(e, fmaf(cf.ca, xi, fmaf(cf.h, t.g, t.x))); });
+          leaf_pass<U>(n, lk, ld_xg, [&](unsigned e, const Elt& t, float xi) { emit(e, fmaf(cf.ca, xi, fmaf(cf.h, gval<MODE>(t), t.x))); });
           break;
         case SGMCMC_DIFF_PSGLD: {
           const float alpha = m.hyper[0], eps = m.hyper[1];
           leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
-            const float vv = alpha * t.a + (1.0f - alpha) * (t.g * t.g);
+            const float gg = gval<MODE>(t);
+            const float vv = alpha * t.a + (1.0f - alpha) * (gg * gg);
             const float G = fast_rcp(fast_sqrt(vv) + eps);
             v[e] = vv;
-            emit(e, t.x + cf.hh * G * t.g + fast_sqrt(cf.h * G) * xi);
+            emit(e, t.x + cf.hh * G * gg + fast_sqrt(cf.h * G) * xi);
           });
           break;
         }
         case SGMCMC_DIFF_SGLDADAM: {
           const float b1 = m.hyper[0], b2 = m.hyper[1], eps = m.hyper[2];
           leaf_pass<U>(n, lk, ld_xvvg, [&](unsigned e, const Elt& t, float xi) {
-            const float mm = b1 * t.a + (1.0f - b1) * t.g;
-            const float vv = b2 * t.b + (1.0f - b2) * (t.g * t.g);
+            const float gg = gval<MODE>(t);
+            const float mm = b1 * t.a + (1.0f - b1) * gg;
+            const float vv = b2 * t.b + (1.0f - b2) * (gg * gg);
             const float mh = mm * fast_rcp(cf.ca), vh = vv * fast_rcp(cf.cb);
             const float a = cf.h * fast_rcp(fast_sqrt(vh) + eps);
             v[e] = mm; v2[e] = vv;
@@ -343,14 +385,14 @@ struct BigCtx {
         case SGMCMC_DIFF_SGHMC: {
           const float alpha = m.hyper[0];
           leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
-            v[e] = t.a + cf.h * t.g - alpha * t.a + cf.ca * xi;
+            v[e] = t.a + cf.h * gval<MODE>(t) - alpha * t.a + cf.ca * xi;
             emit(e, t.x + t.a);
           });
           break;
         }
         case SGMCMC_DIFF_BAOAB:
           leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
-            float ve = fmaf(cf.hh, t.g, t.a);
+            float ve = fmaf(cf.hh, gval<MODE>(t), t.a);
             float xe = t.x + ve * cf.h * 0.5f;
             ve = cf.ca * ve + cf.cb * xi;
             xe = xe + ve * cf.h * 0.5f;
@@ -366,7 +408,7 @@ struct BigCtx {
           float ss = 0.f;
           leaf_pass<U>(n, kn, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
             float ve = first ? cf.cb * normal_at(sub, e, n) : t.a;
-            ve = ve - alpha * ve + cf.h * t.g + cf.ca * xi;
+            ve = ve - alpha * ve + cf.h * gval<MODE>(t) + cf.ca * xi;
             v[e] = ve;
             emit(e, t.x + ve);
             ss = fmaf(ve, ve, ss);
@@ -379,7 +421,7 @@ struct BigCtx {
           float alpha = s.alpha[leaf];
           float ss = 0.f;
           plain_pass<U>(n, ld_xvg, [&](unsigned e, const Elt& t) {
-            const float ve = fmaf(cf.hh, t.g, t.a);
+            const float ve = fmaf(cf.hh, gval<MODE>(t), t.a);
             v[e] = ve; x[e] = fmaf(cf.hh, ve, t.x); g[e] = 0.f;
             ss = fmaf(ve, ve, ss);
           });
@@ -388,7 +430,7 @@ struct BigCtx {
           const float c2 = (alpha == 0.0f) ? cf.ca : sqrtf(fabsf((1.0f - c1 * c1) / (2.0f * alpha)));
           __syncthreads();
           float ss2 = 0.f;
-          leaf_pass<U>(n, lk, [&](unsigned e) { Elt t; t.x = x[e]; t.a = v[e]; t.b = 0.f; t.g = 0.f; return t; },
+          leaf_pass<U>(n, lk, [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; return t; },
                        [&](unsigned e, const Elt& t, float xi) {
                          const float ve = c1 * t.a + c2 * xi;
                          v[e] = ve; ss2 = fmaf(ve, ve, ss2);

@@ -229,8 +229,31 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     float4 xv0, xv1, wv0, wv1;
+    // Fast path (s0 % 4 == 0, W1 at least 8-byte aligned): every 16-byte chunk is wholly inside or outside a row, so
+    // the loads are unconditional (clamped address, result masked) and issue back to back; a branch between two
+    // loads would serialise them on the memory latency.
+    const bool fast = x16 && w8;
+    const float* xp0 = xsrc0 ? xsrc0 : X;
+    const float* xp1 = xsrc1 ? xsrc1 : X;
+    const float* wp0 = wsrc0 ? wsrc0 : W1;
+    const float* wp1 = wsrc1 ? wsrc1 : W1;
     auto fetch = [&](int c) {
       const int k = c * MLP_KC + ch * 4;
+      if (fast) {
+        const int kk = min(k, s0 - 4);
+        xv0 = __ldg(reinterpret_cast<const float4*>(xp0 + kk));
+        xv1 = __ldg(reinterpret_cast<const float4*>(xp1 + kk));
+        const float2 a0 = *reinterpret_cast<const float2*>(wp0 + kk), a1 = *reinterpret_cast<const float2*>(wp0 + kk + 2);
+        const float2 b0 = *reinterpret_cast<const float2*>(wp1 + kk), b1 = *reinterpret_cast<const float2*>(wp1 + kk + 2);
+        wv0 = make_float4(a0.x, a0.y, a1.x, a1.y);
+        wv1 = make_float4(b0.x, b0.y, b1.x, b1.y);
+        const bool in = k < s0;
+        if (!(in && xsrc0)) xv0 = zero4;
+        if (!(in && xsrc1)) xv1 = zero4;
+        if (!(in && wsrc0)) wv0 = zero4;
+        if (!(in && wsrc1)) wv1 = zero4;
+        return;
+      }
       const int valid = s0 - k;
       xv0 = xsrc0 ? load4(xsrc0 + k, valid, x16, x16, true) : zero4;
       xv1 = xsrc1 ? load4(xsrc1 + k, valid, x16, x16, true) : zero4;
@@ -338,6 +361,11 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         const int g = u / npp, p = u - g * npp;
         const int b = g * 8 + lr;
         const int k = (t0 + 2 * p) * 128 + c4 * 4;
+        if (x16) {                                             // unconditional load, clamped address, masked result
+          const float4 t = __ldg(reinterpret_cast<const float4*>(X + (size_t)ms.idx[min(b, nb - 1)] * s0 + min(k, s0 - 4)));
+          xv = (b < nb && k < s0) ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+          return;
+        }
         xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b < nb && k < s0) xv = load4(X + (size_t)ms.idx[b] * s0 + k, s0 - k, x16, x16, true);
       };
