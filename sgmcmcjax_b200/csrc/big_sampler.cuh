@@ -229,11 +229,10 @@ struct BigCtx {
     if (MODE == 2) { t.fb = fb[ge]; t.cen = center[ge]; }
   }
   template <int MODE>
-  __device__ __forceinline__ float gval(const Elt& t) const {
+  __device__ static __forceinline__ float gval(const Elt& t, float gs, float prior) {
     if (MODE == 0) return t.g;
-    const float prior = m.coef[1];
-    if (MODE == 2) return t.fb + (gscale * t.g - prior * (t.x - t.cen));        // gradient_estimation.py:72, no cancellation
-    return gscale * t.g - prior * t.x;
+    if (MODE == 2) return t.fb + (gs * t.g - prior * (t.x - t.cen));            // gradient_estimation.py:72, no cancellation
+    return gs * t.g - prior * t.x;
   }
 
   __device__ void zero(float* g) {
@@ -326,13 +325,16 @@ struct BigCtx {
   template <int MODE>
   __device__ __noinline__ void diffuse_mode(int phase, int i, const sgmcmc_step_coef& cf, int key_slot, float* sample) {
     const bool bug = (m.flags & SGMCMC_FLAG_BADODABCV_REFERENCE_BUG) && m.diffusion == SGMCMC_DIFF_BADODAB;
+    // scalars the per-element code needs, read once (the model lives in param space behind a reference)
+    const float gs = gscale, prior = m.coef[1];
+    const sgmcmc_step_coef cfv = cf;
     if (phase == 2 || bug) {                      // baoab / badodab update2: v += dt/2 * g
       const bool consume = phase == 1;
       plain_pass<U>((unsigned)m.P,
                     [&](unsigned e) { Elt t{}; t.x = theta[e]; t.a = aux1[e]; ld_grad<MODE>(t, grad, e, e); return t; },
                     [&](unsigned e, const Elt& t) {
-                      const float gg = gval<MODE>(t);
-                      aux1[e] = fmaf(cf.hh, gg, t.a);
+                      const float gg = gval<MODE>(t, gs, prior);
+                      aux1[e] = fmaf(cfv.hh, gg, t.a);
                       if (consume) { grad[e] = 0.f; if (sample) __stcs(sample + e, t.x); }
                       else grad[e] = gg;           // keep the finalised value: the next update reads it as is
                     });
@@ -356,27 +358,27 @@ struct BigCtx {
       auto emit = [&](unsigned e, float xn) { x[e] = xn; g[e] = 0.f; if (smp) __stcs(smp + e, xn); };
       switch (m.diffusion) {
         case SGMCMC_DIFF_SGLD:
-          leaf_pass<U>(n, lk, ld_xg, [&](unsigned e, const Elt& t, float xi) { emit(e, fmaf(cf.ca, xi, fmaf(cf.h, gval<MODE>(t), t.x))); });
+          leaf_pass<U>(n, lk, ld_xg, [&](unsigned e, const Elt& t, float xi) { emit(e, fmaf(cfv.ca, xi, fmaf(cfv.h, gval<MODE>(t, gs, prior), t.x))); });
           break;
         case SGMCMC_DIFF_PSGLD: {
           const float alpha = m.hyper[0], eps = m.hyper[1];
           leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
-            const float gg = gval<MODE>(t);
+            const float gg = gval<MODE>(t, gs, prior);
             const float vv = alpha * t.a + (1.0f - alpha) * (gg * gg);
             const float G = fast_rcp(fast_sqrt(vv) + eps);
             v[e] = vv;
-            emit(e, t.x + cf.hh * G * gg + fast_sqrt(cf.h * G) * xi);
+            emit(e, t.x + cfv.hh * G * gg + fast_sqrt(cfv.h * G) * xi);
           });
           break;
         }
         case SGMCMC_DIFF_SGLDADAM: {
           const float b1 = m.hyper[0], b2 = m.hyper[1], eps = m.hyper[2];
           leaf_pass<U>(n, lk, ld_xvvg, [&](unsigned e, const Elt& t, float xi) {
-            const float gg = gval<MODE>(t);
+            const float gg = gval<MODE>(t, gs, prior);
             const float mm = b1 * t.a + (1.0f - b1) * gg;
             const float vv = b2 * t.b + (1.0f - b2) * (gg * gg);
-            const float mh = mm * fast_rcp(cf.ca), vh = vv * fast_rcp(cf.cb);
-            const float a = cf.h * fast_rcp(fast_sqrt(vh) + eps);
+            const float mh = mm * fast_rcp(cfv.ca), vh = vv * fast_rcp(cfv.cb);
+            const float a = cfv.h * fast_rcp(fast_sqrt(vh) + eps);
             v[e] = mm; v2[e] = vv;
             emit(e, t.x + a * 0.5f * mh + fast_sqrt(a) * xi);
           });
@@ -385,17 +387,17 @@ struct BigCtx {
         case SGMCMC_DIFF_SGHMC: {
           const float alpha = m.hyper[0];
           leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
-            v[e] = t.a + cf.h * gval<MODE>(t) - alpha * t.a + cf.ca * xi;
+            v[e] = t.a + cfv.h * gval<MODE>(t, gs, prior) - alpha * t.a + cfv.ca * xi;
             emit(e, t.x + t.a);
           });
           break;
         }
         case SGMCMC_DIFF_BAOAB:
           leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
-            float ve = fmaf(cf.hh, gval<MODE>(t), t.a);
-            float xe = t.x + ve * cf.h * 0.5f;
-            ve = cf.ca * ve + cf.cb * xi;
-            xe = xe + ve * cf.h * 0.5f;
+            float ve = fmaf(cfv.hh, gval<MODE>(t, gs, prior), t.a);
+            float xe = t.x + ve * cfv.h * 0.5f;
+            ve = cfv.ca * ve + cfv.cb * xi;
+            xe = xe + ve * cfv.h * 0.5f;
             v[e] = ve;
             emit(e, xe);
           });
@@ -407,38 +409,38 @@ struct BigCtx {
           if (first) split2(lk, kn, sub);               // diffusions.py:268-278
           float ss = 0.f;
           leaf_pass<U>(n, kn, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
-            float ve = first ? cf.cb * normal_at(sub, e, n) : t.a;
-            ve = ve - alpha * ve + cf.h * gval<MODE>(t) + cf.ca * xi;
+            float ve = first ? cfv.cb * normal_at(sub, e, n) : t.a;
+            ve = ve - alpha * ve + cfv.h * gval<MODE>(t, gs, prior) + cfv.ca * xi;
             v[e] = ve;
             emit(e, t.x + ve);
             ss = fmaf(ve, ve, ss);
           });
           const float nrm = sqrtf(big_block_sum(ss, s.red));
-          if (threadIdx.x == 0) s.alpha[leaf] = alpha + (nrm * nrm) / (float)n - cf.h;
+          if (threadIdx.x == 0) s.alpha[leaf] = alpha + (nrm * nrm) / (float)n - cfv.h;
           break;
         }
         case SGMCMC_DIFF_BADODAB: {
           float alpha = s.alpha[leaf];
           float ss = 0.f;
           plain_pass<U>(n, ld_xvg, [&](unsigned e, const Elt& t) {
-            const float ve = fmaf(cf.hh, gval<MODE>(t), t.a);
-            v[e] = ve; x[e] = fmaf(cf.hh, ve, t.x); g[e] = 0.f;
+            const float ve = fmaf(cfv.hh, gval<MODE>(t, gs, prior), t.a);
+            v[e] = ve; x[e] = fmaf(cfv.hh, ve, t.x); g[e] = 0.f;
             ss = fmaf(ve, ve, ss);
           });
-          alpha = alpha + cf.hh * (sqrtf(big_block_sum(ss, s.red)) - (float)n);
-          const float c1 = (float)exp((double)(-alpha * cf.h));     // correctly rounded, see vec_sampler.cuh
-          const float c2 = (alpha == 0.0f) ? cf.ca : sqrtf(fabsf((1.0f - c1 * c1) / (2.0f * alpha)));
+          alpha = alpha + cfv.hh * (sqrtf(big_block_sum(ss, s.red)) - (float)n);
+          const float c1 = (float)exp((double)(-alpha * cfv.h));     // correctly rounded, see vec_sampler.cuh
+          const float c2 = (alpha == 0.0f) ? cfv.ca : sqrtf(fabsf((1.0f - c1 * c1) / (2.0f * alpha)));
           __syncthreads();
           float ss2 = 0.f;
           leaf_pass<U>(n, lk, [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; return t; },
                        [&](unsigned e, const Elt& t, float xi) {
                          const float ve = c1 * t.a + c2 * xi;
                          v[e] = ve; ss2 = fmaf(ve, ve, ss2);
-                         const float xn = fmaf(cf.hh, ve, t.x);      // second half step of x with the new v
+                         const float xn = fmaf(cfv.hh, ve, t.x);      // second half step of x with the new v
                          x[e] = xn;
                          if (smp) __stcs(smp + e, xn);
                        });
-          alpha = alpha + cf.hh * (sqrtf(big_block_sum(ss2, s.red)) - (float)n);
+          alpha = alpha + cfv.hh * (sqrtf(big_block_sum(ss2, s.red)) - (float)n);
           __syncthreads();
           if (threadIdx.x == 0) s.alpha[leaf] = alpha;
           break;

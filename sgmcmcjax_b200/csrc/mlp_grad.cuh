@@ -228,7 +228,6 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     const uint32_t off1 = (uint32_t)r1 * 128u + (uint32_t)((ch ^ (r1 & 7)) << 4);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    float4 xv0, xv1, wv0, wv1;
     // Fast path (s0 % 4 == 0, W1 at least 8-byte aligned): every 16-byte chunk is wholly inside or outside a row, so
     // the loads are unconditional (clamped address, result masked) and issue back to back; a branch between two
     // loads would serialise them on the memory latency.
@@ -237,7 +236,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     const float* xp1 = xsrc1 ? xsrc1 : X;
     const float* wp0 = wsrc0 ? wsrc0 : W1;
     const float* wp1 = wsrc1 ? wsrc1 : W1;
-    auto fetch = [&](int c) {
+    auto fetch = [&](int c, float4& xv0, float4& xv1, float4& wv0, float4& wv1) {
       const int k = c * MLP_KC + ch * 4;
       if (fast) {
         const int kk = min(k, s0 - 4);
@@ -245,13 +244,8 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         xv1 = __ldg(reinterpret_cast<const float4*>(xp1 + kk));
         const float2 a0 = *reinterpret_cast<const float2*>(wp0 + kk), a1 = *reinterpret_cast<const float2*>(wp0 + kk + 2);
         const float2 b0 = *reinterpret_cast<const float2*>(wp1 + kk), b1 = *reinterpret_cast<const float2*>(wp1 + kk + 2);
-        wv0 = make_float4(a0.x, a0.y, a1.x, a1.y);
-        wv1 = make_float4(b0.x, b0.y, b1.x, b1.y);
-        const bool in = k < s0;
-        if (!(in && xsrc0)) xv0 = zero4;
-        if (!(in && xsrc1)) xv1 = zero4;
-        if (!(in && wsrc0)) wv0 = zero4;
-        if (!(in && wsrc1)) wv1 = zero4;
+        wv0 = make_float4(a0.x, a0.y, a1.x, a1.y);      // NO use of the loaded values here: masking happens in step(),
+        wv1 = make_float4(b0.x, b0.y, b1.x, b1.y);      // a use right after the load would stall the thread on it
         return;
       }
       const int valid = s0 - k;
@@ -260,9 +254,9 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       wv0 = wsrc0 ? load4(wsrc0 + k, valid, w16, w8, false) : zero4;
       wv1 = wsrc1 ? load4(wsrc1 + k, valid, w16, w8, false) : zero4;
     };
-    fetch(0);
     int uses[2] = {0, 0};
-    for (int c = 0; c < n_chunks; ++c) {
+    // one pipeline step: registers of chunk c -> stage c & 1, refill the registers with chunk c + 2, issue the MMAs
+    auto step = [&](int c, float4& xv0, float4& xv1, float4& wv0, float4& wv1) {
       const int st = c & 1;
       uint8_t* sb = region + (size_t)st * stage_bytes;
       uint8_t* xhi = sb;
@@ -270,12 +264,19 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       uint8_t* whi = sb + 2 * MLP_ROWS * 128;
       uint8_t* wlo = whi + (size_t)s1n * 128;
       if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }   // MMAs of chunk c - 2 retired
+      if (fast) {                                                            // out-of-range rows / columns read as zero
+        const bool in = c * MLP_KC + ch * 4 < s0;
+        if (!(in && xsrc0)) xv0 = zero4;
+        if (!(in && xsrc1)) xv1 = zero4;
+        if (!(in && wsrc0)) wv0 = zero4;
+        if (!(in && wsrc1)) wv1 = zero4;
+      }
       float4 hi, lo;
       split4(xv0, hi, lo); *reinterpret_cast<float4*>(xhi + off0) = hi; *reinterpret_cast<float4*>(xlo + off0) = lo;
       split4(xv1, hi, lo); *reinterpret_cast<float4*>(xhi + off1) = hi; *reinterpret_cast<float4*>(xlo + off1) = lo;
       if (w0_in) { split4(wv0, hi, lo); *reinterpret_cast<float4*>(whi + off0) = hi; *reinterpret_cast<float4*>(wlo + off0) = lo; }
       if (w1_in) { split4(wv1, hi, lo); *reinterpret_cast<float4*>(whi + off1) = hi; *reinterpret_cast<float4*>(wlo + off1) = lo; }
-      if (c + 1 < n_chunks) fetch(c + 1);                                    // in flight while the MMAs of chunk c run
+      if (c + 2 < n_chunks) fetch(c + 2, xv0, xv1, wv0, wv1);               // two chunks of loads stay in flight
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
@@ -292,6 +293,16 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         tc_commit(&ms.bar[st]);
       }
       ++uses[st];
+    };
+    {
+      float4 ax0, ax1, aw0, aw1, bx0, bx1, bw0, bw1;
+      fetch(0, ax0, ax1, aw0, aw1);
+      if (n_chunks > 1) fetch(1, bx0, bx1, bw0, bw1);
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; c += 2) {
+        step(c, ax0, ax1, aw0, aw1);
+        if (c + 1 < n_chunks) step(c + 1, bx0, bx1, bw0, bw1);
+      }
     }
     for (int st = 0; st < 2; ++st)
       if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }
@@ -356,30 +367,32 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       const int pass_tiles = min(tiles_per_pass, n_tiles - t0);
       const int npp = (pass_tiles + 1) >> 1;                      // tile pairs in this pass
       const int units = G * npp;
-      float4 xv;
-      auto fetch = [&](int u) {
+      auto fetch = [&](int u, float4& xv) {
         const int g = u / npp, p = u - g * npp;
         const int b = g * 8 + lr;
         const int k = (t0 + 2 * p) * 128 + c4 * 4;
-        if (x16) {                                             // unconditional load, clamped address, masked result
-          const float4 t = __ldg(reinterpret_cast<const float4*>(X + (size_t)ms.idx[min(b, nb - 1)] * s0 + min(k, s0 - 4)));
-          xv = (b < nb && k < s0) ? t : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x16) {                                             // unconditional load, clamped address; masked in step()
+          xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)ms.idx[min(b, nb - 1)] * s0 + min(k, s0 - 4)));
           return;
         }
         xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b < nb && k < s0) xv = load4(X + (size_t)ms.idx[b] * s0 + k, s0 - k, x16, x16, true);
       };
-      fetch(0);
       int uses[2] = {0, 0};
-      for (int u = 0; u < units; ++u) {
+      // one pipeline step: registers of unit u -> stage u & 1, refill them with unit u + 4, issue the MMAs
+      auto step = [&](int u, float4& xv) {
         const int st = u & 1;
         uint8_t* sb = xs + (size_t)st * stage_bytes;
         if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }
+        if (x16) {
+          const int g = u / npp, p = u - g * npp;
+          if (!(g * 8 + lr < nb && (t0 + 2 * p) * 128 + c4 * 4 < s0)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float4 hi, lo;
         split4(xv, hi, lo);
         *reinterpret_cast<float4*>(sb + soff) = hi;
         *reinterpret_cast<float4*>(sb + 8192 + soff) = lo;
-        if (u + 1 < units) fetch(u + 1);
+        if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -399,6 +412,20 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           tc_commit(&ms.bar[st]);
         }
         ++uses[st];
+      };
+      {
+        float4 x0, x1, x2, x3;
+        fetch(0, x0);
+        if (units > 1) fetch(1, x1);
+        if (units > 2) fetch(2, x2);
+        if (units > 3) fetch(3, x3);
+#pragma unroll 1
+        for (int u = 0; u < units; u += 4) {
+          step(u, x0);
+          if (u + 1 < units) step(u + 1, x1);
+          if (u + 2 < units) step(u + 2, x2);
+          if (u + 3 < units) step(u + 3, x3);
+        }
       }
       for (int st = 0; st < 2; ++st)
         if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }
@@ -557,23 +584,37 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         const int b = tid >> 2, q = tid & 3;
         const bool live = b < nb;
         const int warp = tid >> 5, lane = tid & 31;
-        auto dA = [&](int j) {                                      // (dz W_2)[b][j]
-          float accv = 0.f;
-          for (int n = 0; n < w; ++n) accv = fmaf(dz[b * dzs + n], Wl[(size_t)n * wp + j], accv);
-          return accv;
-        };
+        // dA[b][j] = sum_n dz[b][n] W_2[n][j] for this thread's columns j = q + 4 i: one sweep over n, 32 accumulators
+        float da[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) da[i] = 0.f;
+        if (live) {
+#pragma unroll 1
+          for (int n = 0; n < w; ++n) {
+            const float dzn = dz[b * dzs + n];
+            const float* wrow = Wl + (size_t)n * wp + q;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (4 * i < s1n) da[i] = fmaf(dzn, 4 * i + q < wp ? wrow[4 * i] : 0.f, da[i]);
+          }
+        }
         float dotv = 0.f;
-        if (live)
-          for (int j = q; j < wp; j += 4) dotv = fmaf(A[b * as + j], dA(j), dotv);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (4 * i < s1n) dotv = fmaf((live && 4 * i + q < wp) ? A[b * as + 4 * i + q] : 0.f, da[i], dotv);
         dotv += __shfl_xor_sync(FULL, dotv, 1);
         dotv += __shfl_xor_sync(FULL, dotv, 2);
-        for (int j = q; j < s1n; j += 4) {                          // trip count is warp-uniform (s1n % 4 == 0)
-          float v = (live && j < wp) ? A[b * as + j] * (dA(j) - dotv) : 0.f;
-          if (b < R) put_dz1(bhi, blo, b, j, v);
-          v += __shfl_xor_sync(FULL, v, 4);
-          v += __shfl_xor_sync(FULL, v, 8);
-          v += __shfl_xor_sync(FULL, v, 16);
-          if (lane < 4) red[warp * 128 + j] = v;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int j = q + 4 * i;
+          if (4 * i < s1n) {                                       // warp-uniform
+            float v = (live && j < wp) ? A[b * as + j] * (da[i] - dotv) : 0.f;
+            if (b < R) put_dz1(bhi, blo, b, j, v);
+            v += __shfl_xor_sync(FULL, v, 4);
+            v += __shfl_xor_sync(FULL, v, 8);
+            v += __shfl_xor_sync(FULL, v, 16);
+            if (lane < 4) red[warp * 128 + j] = v;
+          }
         }
         __syncthreads();
         for (int n = tid; n < s1; n += blockDim.x) {
