@@ -363,8 +363,14 @@ def gpu_arm(args):
     kern_ms = float(statistics.mean(per_launch_ms))
     alg_bytes = algorithmic_bytes_per_chain_step(args.batch) * C * K
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = args.traffic
+    if traffic is None and args.batch == BATCH and C == CHAINS and K == 10:
+        try:      # dram bytes per launch of the same launch shape, from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["vec_sampler_logreg_c2"]["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": args.traffic, "kernel": "vec_sampler_kernel<LOGREG>", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "vec_sampler_kernel<LOGREG>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms}
 
     # ---- end to end through the public API: host keys + host params in, host samples out
