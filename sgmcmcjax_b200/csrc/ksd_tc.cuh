@@ -22,7 +22,7 @@
 // segment chunks into one 64 KB smem stage (64-byte swizzle, K-major); 12 segment products
 // (3 for x.x, 3 for g.g, 6 for the cross term) accumulate into three 128-column fp32
 // accumulators in TMEM.  Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc),
-// 2..5 = epilogue (tcgen05.ld -> IMQ formula -> fp64 partial sums).
+// 2..9 = epilogue (tcgen05.ld -> IMQ formula -> fp64 partial sums; two warps per TMEM lane quarter, 64 columns each).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -37,7 +37,7 @@ constexpr int KC = 16;             // K-chunk (floats) per smem stage = 64 bytes
 constexpr int STAGES = 3;
 constexpr int CHUNK_BYTES = TILE * KC * 4;           // 8 KB per (segment, side) chunk
 constexpr int STAGE_BYTES = 8 * CHUNK_BYTES;         // 64 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
 constexpr int TMEM_COLS = 512;     // 3 accumulators x 128 columns = 384 -> next power of two
 constexpr int UMMA_K = 8;          // tf32: 32 bytes of K per instruction
 
@@ -237,7 +237,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
     mbar_init(&tail->tmem_full, 1);
-    mbar_init(&tail->tmem_empty, 4);       // one arrival per epilogue warp
+    mbar_init(&tail->tmem_empty, 8);       // one arrival per epilogue warp
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(&tail->tmem_base, TMEM_COLS); tmem_relinquish(); }
@@ -301,10 +301,11 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       }
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+    // ===== epilogue: warps 2..9; warp w reads TMEM lanes 32*(w%4) .. +31, column half (w-2)/4 =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = q * 32 + lane;
-    const int et = threadIdx.x - 64;                           // 0..127
+    const int et = threadIdx.x - 64;                           // 0..255
     const float dim = (float)d;
     double acc = 0.0;
     uint32_t acc_phase = 0;
@@ -314,9 +315,9 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       tile_of(part + (long long)nparts * u, T, I, J);
       const int gi = I * TILE + row_in_tile;
       const int gjc = J * TILE + et;
-      tail->colterm[buf][et] = gjc < n ? rt[gjc] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (et < TILE) tail->colterm[buf][et] = gjc < n ? rt[gjc] : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 ri = gi < n ? rt[gi] : make_float4(0.f, 0.f, 0.f, 0.f);
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // colterm[buf] visible to the 4 epilogue warps
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // colterm[buf] visible to the 8 epilogue warps
       mbar_wait(&tail->tmem_full, acc_phase);
       tc_fence_after();
       float tsum = 0.f;
@@ -324,7 +325,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       const int jmax = min(TILE, n - J * TILE);
       const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int cb = 0; cb < TILE; cb += 16) {
+      for (int cb = half * (TILE / 2); cb < (half + 1) * (TILE / 2); cb += 16) {
         uint32_t p1[16], p2[16], p3[16];
         tmem_ld16(tl + cb, p1);
         tmem_ld16(tl + TILE + cb, p2);

@@ -150,10 +150,13 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
     }
   }
 
-  for (unsigned b0 = warp * 32u; b0 < h; b0 += W * 32u) {
+  // short streams (h < 32 W, e.g. one chain with batch 1000): spread the blocks over ALL warps instead of
+  // filling 32 lanes of the first few, so the row groups of a step run in parallel rather than back to back
+  const unsigned lpw = h < W * 32u ? (h + W - 1u) / W : 32u;
+  for (unsigned b0 = warp * lpw; b0 < h; b0 += W * lpw) {
     const unsigned b = b0 + lane;
     int jA = -1, jB = -1;
-    if (b < h) {
+    if ((unsigned)lane < lpw && b < h) {
       unsigned iA, iB;
       if (sequential) { iA = seq_base + b; iB = seq_base + b + h; } else { randint_block(plan, b, iA, iB); }
       jA = (int)iA;
