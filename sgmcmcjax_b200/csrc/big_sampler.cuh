@@ -144,6 +144,39 @@ template <> struct BigUnroll<SGMCMC_FAMILY_MLP> { static constexpr int value = S
 
 // ---------------------------------------------------------------------------------------
 // PMF likelihood pass
+// One rating (i, j, y) at rank 4 R4: g[U_i] += e V_j, g[V_j] += e U_i with e = alpha (y - U_i.V_j); the factor rows sit in
+// registers, every load of the rating issues back to back, accumulation by float4 L2 atomics.  The control-variate
+// term (minus the same at the centre) is a second round so that the live registers stay at 2 R4 float4.
+template <int R4>
+__device__ __forceinline__ void pmf_rating_half(const float* th, float* g, int offV, int i, int j, float y, float alpha, float sign) {
+  const int r = 4 * R4;
+  const float4* u = reinterpret_cast<const float4*>(th + (size_t)i * r);
+  const float4* v = reinterpret_cast<const float4*>(th + offV + (size_t)j * r);
+  float4 uu[R4], vv[R4];
+#pragma unroll
+  for (int k = 0; k < R4; ++k) { uu[k] = u[k]; vv[k] = v[k]; }
+  float dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < R4; ++k) {
+    dot = fmaf(uu[k].x, vv[k].x, dot); dot = fmaf(uu[k].y, vv[k].y, dot);
+    dot = fmaf(uu[k].z, vv[k].z, dot); dot = fmaf(uu[k].w, vv[k].w, dot);
+  }
+  const float e = sign * alpha * (y - dot);
+  float4* gu = reinterpret_cast<float4*>(g + (size_t)i * r);
+  float4* gv = reinterpret_cast<float4*>(g + offV + (size_t)j * r);
+#pragma unroll
+  for (int k = 0; k < R4; ++k) {
+    atomicAdd(gu + k, make_float4(e * vv[k].x, e * vv[k].y, e * vv[k].z, e * vv[k].w));
+    atomicAdd(gv + k, make_float4(e * uu[k].x, e * uu[k].y, e * uu[k].z, e * uu[k].w));
+  }
+}
+template <int R4>
+__device__ __forceinline__ void pmf_rating(const float* theta, const float* center, float* g, int offV, int i, int j, float y,
+                                           float alpha) {
+  pmf_rating_half<R4>(theta, g, offV, i, j, y, alpha, 1.0f);
+  if (center) pmf_rating_half<R4>(center, g, offV, i, j, y, alpha, -1.0f);
+}
+
 template <>
 struct FamilyGrad<SGMCMC_FAMILY_PMF> {
   static constexpr size_t smem_bytes(const BigModel&) { return 0; }
@@ -158,10 +191,30 @@ struct FamilyGrad<SGMCMC_FAMILY_PMF> {
     const int4* __restrict__ rat = reinterpret_cast<const int4*>(m.data0);
     const float alpha = m.coef[0];
     const unsigned h = (count + 1u) >> 1;
+    // rank <= 32, rows 16-byte aligned (rank % 4 == 0 and aligned chain rows): whole factor rows in registers, all
+    // loads of a rating issued back to back, float4 atomics
+    const bool vec = (r == 8 || r == 16 || r == 20 || r == 32) && (offV & 3) == 0 && ((reinterpret_cast<uintptr_t>(theta) | reinterpret_cast<uintptr_t>(g) |
+                      reinterpret_cast<uintptr_t>(center ? center : theta)) & 15) == 0;
+    const int r4 = r >> 2;
     for (unsigned b = threadIdx.x; b < h; b += blockDim.x) {
       unsigned idx[2];
       if (sequential) { idx[0] = seq_base + b; idx[1] = seq_base + b + h; } else { randint_block(plan, b, idx[0], idx[1]); }
       const int cnt = (b + h < count) ? 2 : 1;
+      if (vec) {
+        const int4 q0 = __ldg(rat + idx[0]);
+        const int4 q1 = __ldg(rat + idx[cnt - 1]);
+        for (int t = 0; t < cnt; ++t) {
+          const int4 q = t ? q1 : q0;
+          const float y = __int_as_float(q.z);
+          switch (r4) {
+            case 2: pmf_rating<2>(theta, center, g, offV, q.x, q.y, y, alpha); break;
+            case 4: pmf_rating<4>(theta, center, g, offV, q.x, q.y, y, alpha); break;
+            case 5: pmf_rating<5>(theta, center, g, offV, q.x, q.y, y, alpha); break;
+            default: pmf_rating<8>(theta, center, g, offV, q.x, q.y, y, alpha); break;
+          }
+        }
+        continue;
+      }
       for (int t = 0; t < cnt; ++t) {
         const int4 q = __ldg(rat + idx[t]);
         const float y = __int_as_float(q.z);
