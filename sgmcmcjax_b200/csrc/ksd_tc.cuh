@@ -20,8 +20,8 @@
 // (~1e-6 |x|^2 in dd) would otherwise be amplified by (gg/2 + 3D/2), so the diagonal uses dd = gd = 0, gg = |g_i|^2.
 // Per 128 x 128 tile and K-chunk of 16 columns, TMA brings the 4 row-side and 4 column-side
 // segment chunks into one 64 KB smem stage (64-byte swizzle, K-major); 12 segment products
-// (3 for x.x, 3 for g.g, 6 for the cross term) accumulate into three 128-column fp32
-// accumulators in TMEM.  Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc),
+// (3 for x.x, 3 for g.g, 6 for the cross term), issued as 6 N = 256 MMAs on adjacent column-side
+// segments, accumulate into four 128-column fp32 accumulators in TMEM.  Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc),
 // 2..9 = epilogue (tcgen05.ld -> IMQ formula -> fp64 partial sums; two warps per TMEM lane quarter, 64 columns each).
 #pragma once
 #include <cuda.h>
@@ -38,7 +38,7 @@ constexpr int STAGES = 3;
 constexpr int CHUNK_BYTES = TILE * KC * 4;           // 8 KB per (segment, side) chunk
 constexpr int STAGE_BYTES = 8 * CHUNK_BYTES;         // 64 KB
 constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
-constexpr int TMEM_COLS = 512;     // 3 accumulators x 128 columns = 384 -> next power of two
+constexpr int TMEM_COLS = 512;     // 4 accumulators x 128 columns
 constexpr int UMMA_K = 8;          // tf32: 32 bytes of K per instruction
 
 struct SmemTail {                  // after the stage buffers
@@ -137,6 +137,7 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
 // cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b format TF32 [7,10)/[10,13)=2, K-major both,
 // N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t IDESC_TF32_128x128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_TF32_128x256 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
@@ -213,12 +214,17 @@ __device__ __forceinline__ float imq_k0_tc(float dd, float gg, float gd, float d
   return gg * r + (gd + dim) * r3 - 3.0f * dd * r3 * r2;
 }
 
-// product table: (accumulator, row-side segment, column-side segment); segments 0 xh, 1 xl, 2 gh, 3 gl
-__constant__ int8_t PROD[12][3] = {
-    {0, 0, 0}, {0, 0, 1}, {0, 1, 0},                                  // x.x
-    {1, 2, 2}, {1, 2, 3}, {1, 3, 2},                                  // g.g
-    {2, 2, 0}, {2, 2, 1}, {2, 3, 0}, {2, 0, 2}, {2, 0, 3}, {2, 1, 2}  // g_i.x_j + x_i.g_j
+// Paired products.  The column-side chunks of a stage are laid out [xh_J | gh_J | xl_J | gl_J], so that one N = 256
+// MMA multiplies a row-side segment with TWO adjacent column-side segments and writes two adjacent TMEM
+// accumulators: half the MMA instructions, and the A operand is read from shared memory once per 256 columns
+// (12 KB of operand traffic per 128 tensor cycles instead of 8 KB per 64, the 128 B/clk shared-memory port).
+//   TMEM columns: [0,128) x_I.x_J   [128,256) x_I.g_J   [256,384) g_I.x_J   [384,512) g_I.g_J
+// table: (TMEM column of the pair, row-side segment 0 xh 1 xl 2 gh 3 gl, column-side pair 0 = [xh|gh], 1 = [xl|gl])
+__constant__ int16_t PROD[6][3] = {
+    {0, 0, 0}, {0, 0, 1}, {0, 1, 0},          // x_I . [x_J | g_J]  (3xTF32: hi.hi, hi.lo, lo.hi)
+    {256, 2, 0}, {256, 2, 1}, {256, 3, 0}     // g_I . [x_J | g_J]
 };
+__device__ __forceinline__ int col_slot(int seg) { return ((seg & 1) << 1) | (seg >> 1); }   // xh 0, gh 1, xl 2, gl 3
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict__ rt, int n, int d, int dp,
@@ -261,7 +267,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
 #pragma unroll
           for (int seg = 0; seg < 4; ++seg) {
             tma_load_2d(sbase + seg * CHUNK_BYTES, &zmap, seg * dp + c * KC, I * TILE, &tail->full[stage]);
-            tma_load_2d(sbase + (4 + seg) * CHUNK_BYTES, &zmap, seg * dp + c * KC, J * TILE, &tail->full[stage]);
+            tma_load_2d(sbase + (4 + col_slot(seg)) * CHUNK_BYTES, &zmap, seg * dp + c * KC, J * TILE, &tail->full[stage]);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -282,13 +288,13 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
           const int valid = min(KC, dp - c * KC);              // dp is a multiple of 8
           const int slices = valid / UMMA_K;
 #pragma unroll
-          for (int p = 0; p < 12; ++p) {
-            const int a = PROD[p][0];
+          for (int p = 0; p < 6; ++p) {
+            const int a = PROD[p][0] >> 8;                         // 0: columns [0,256), 1: columns [256,512)
             const uint64_t da = make_desc_sw64(sbase + PROD[p][1] * CHUNK_BYTES);
-            const uint64_t db = make_desc_sw64(sbase + (4 + PROD[p][2]) * CHUNK_BYTES);
+            const uint64_t db = make_desc_sw64(sbase + (4 + 2 * PROD[p][2]) * CHUNK_BYTES);
             for (int k = 0; k < slices; ++k) {
               // advancing K inside the swizzle atom = +32 bytes on the start address (>>4 => +2)
-              umma_tf32(tmem_base + a * TILE, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_TF32_128x128,
+              umma_tf32(tmem_base + PROD[p][0], da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_TF32_128x256,
                         (started >> a) & 1u);
               started |= 1u << a;
             }
@@ -326,17 +332,18 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cb = half * (TILE / 2); cb < (half + 1) * (TILE / 2); cb += 16) {
-        uint32_t p1[16], p2[16], p3[16];
-        tmem_ld16(tl + cb, p1);
-        tmem_ld16(tl + TILE + cb, p2);
-        tmem_ld16(tl + 2 * TILE + cb, p3);
+        uint32_t p1[16], p2[16], p3[16], p4[16];
+        tmem_ld16(tl + cb, p1);                 // x_I.x_J
+        tmem_ld16(tl + 3 * TILE + cb, p2);      // g_I.g_J
+        tmem_ld16(tl + TILE + cb, p3);          // x_I.g_J
+        tmem_ld16(tl + 2 * TILE + cb, p4);      // g_I.x_J
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float4 cj = tail->colterm[buf][cb + e];
           float dd = fmaf(-2.0f, __uint_as_float(p1[e]), ri.x + cj.x);
           float gg = __uint_as_float(p2[e]) + (ri.z + cj.z);
-          float gd = (ri.y + cj.y) - __uint_as_float(p3[e]);
+          float gd = (ri.y + cj.y) - (__uint_as_float(p3[e]) + __uint_as_float(p4[e]));
           if (diag_tile && cb + e == row_in_tile) { dd = 0.f; gd = 0.f; gg = ri.w; }   // i == j: exact
           const float k0 = imq_k0_tc(dd, gg, gd, dim);
           tsum += (gi < n && cb + e < jmax) ? k0 : 0.f;
