@@ -66,3 +66,31 @@ def gather_chains(local, n_chains_total: int, group=None):
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+def prior_grad(spec, leaf_size, thetas):
+    """grad logprior at flat parameter rows `thetas` [M, P] for a registered family (all priors are Gaussian:
+    gaussian_mean -2 c_l theta_l per leaf, the others -precision * theta)."""
+    from . import _native
+
+    out = thetas.clone()
+    if spec.family == _native.FAMILY_GAUSSIAN_MEAN:
+        off = 0
+        for c, n in zip(spec.prior_coef, leaf_size):
+            out[:, off:off + n] *= -2.0 * float(c)
+            off += n
+        return out
+    return out.mul_(-float(spec.prior_coef[0]))
+
+
+def sharded_fullbatch_grad(local_grad, prior, group=None):
+    """Full-batch grad_log_post (util.py:43-49 with all rows) when the ROWS of the data are sharded over ranks
+    (SURVEY.md section 8e, K2): every rank passes `local_grad` = grad_log_post over ITS rows (which includes the
+    prior once) and `prior` = grad logprior; one all-reduce of the [M, P] block, then the (world - 1) surplus
+    copies of the prior are removed:  sum_r (L_r + p) - (W - 1) p = sum_r L_r + p."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    total = local_grad.clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return total - (world - 1) * prior

@@ -51,7 +51,19 @@ def _worker(rank, world, port, out_dir):
             blk = sum(OK.k0_rows(Xs[i], Xs[c0:c1], G[i], G[c0:c1]).sum() for i in range(r0, r1))
             part += blk * (1.0 if I == J else 2.0)
         total = parallel.allreduce_scalar(torch.tensor([part], dtype=torch.float64))
-        np.savez(os.path.join(out_dir, f"r{rank}.npz"), full=full, total=total.numpy())
+        # ---- K2 with the rows sharded: local grad_log_post (prior included once per rank) + one all-reduce
+        from sgmcmcjax_b200.models import logistic_regression as L
+        rngl = np.random.default_rng(2)
+        Xl = rngl.normal(size=(101, 6)).astype(np.float32); yl = (rngl.random(101) < 0.5).astype(np.int32)
+        thetas = rngl.normal(size=(3, 6)).astype(np.float32)
+        lo_r, hi_r = parallel.chain_shard(101, rank, world)          # contiguous row shard
+        fam = M.LogisticRegression()
+        # grad_log_post over the local rows with Ndata = local rows: prior + sum of the local per-row gradients
+        local = np.stack([fam.grad_log_post([t], (Xl[lo_r:hi_r], yl[lo_r:hi_r]), hi_r - lo_r, np.float64)[0] for t in thetas])
+        spec = L.loglikelihood._sgmcmc_family
+        prior = parallel.prior_grad(spec, [6], torch.from_numpy(thetas.astype(np.float64)))
+        k2 = parallel.sharded_fullbatch_grad(torch.from_numpy(local), prior).numpy()
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), full=full, total=total.numpy(), k2=k2)
     finally:
         dist.destroy_process_group()
 
@@ -102,3 +114,9 @@ def test_two_rank_gloo_sharding_matches_single_process(tmp_path):
     Xs = rng.normal(size=(300, 4)); G = -Xs + 0.1 * rng.normal(size=(300, 4))
     ref = float(OK.imq_ksd_sum(Xs, G))
     assert abs(float(r0["total"][0]) - ref) <= 1e-10 * abs(ref)
+    rngl = np.random.default_rng(2)
+    Xl = rngl.normal(size=(101, 6)).astype(np.float32); yl = (rngl.random(101) < 0.5).astype(np.int32)
+    thetas = rngl.normal(size=(3, 6)).astype(np.float32)
+    want = np.stack([M.LogisticRegression().grad_log_post([t], (Xl, yl), 101, np.float64)[0] for t in thetas])
+    np.testing.assert_allclose(r0["k2"], want, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(r0["k2"], r1["k2"])
