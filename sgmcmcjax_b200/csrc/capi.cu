@@ -523,7 +523,7 @@ int sgmcmc_ksd_imq_tc(const float* x, const float* g, int32_t n, int32_t d, int3
   cudaStream_t s = (cudaStream_t)stream;
   const int dp = kt::padded_dim(d);
   uint8_t* w = (uint8_t*)workspace;
-  float* Z = (float*)w;                       w += kt::align_up((size_t)n * 4 * dp * sizeof(float), 256);
+  float* Z = (float*)w;                       w += kt::align_up(kt::z_floats(n, d) * sizeof(float), 256);
   float4* rt = (float4*)w;                    w += kt::align_up((size_t)n * sizeof(float4), 256);
   double* sums = (double*)w;
   CUDA_TRY(cudaMemsetAsync(partial_sum, 0, sizeof(double), s));
@@ -538,8 +538,8 @@ int sgmcmc_ksd_imq_tc(const float* x, const float* g, int32_t n, int32_t d, int3
   kt::EncodeTiledFn encode = kt::encode_tiled_fn();
   if (!encode) return fail(SGMCMC_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   CUtensorMap zmap;
-  const cuuint64_t gdim[2] = {(cuuint64_t)4 * dp, (cuuint64_t)n};
-  const cuuint64_t gstride[1] = {(cuuint64_t)4 * dp * sizeof(float)};
+  const cuuint64_t gdim[2] = {(cuuint64_t)kt::KC, (cuuint64_t)(kt::z_floats(n, d) / kt::KC)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)kt::KC * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)kt::KC, (cuuint32_t)kt::TILE};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult cr = encode(&zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Z, gdim, gstride, box, estr,

@@ -14,7 +14,8 @@
 // a_hi = rna_tf32(a), a_lo = rna_tf32(a - a_hi);  a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi
 // (error ~2^-21 |a||b|, fp32 accumulation in TMEM).  The N^2 sum is accumulated in fp64.
 //
-// Operand matrix  Z[n][4][Dp]  fp32 (Dp = D rounded up to 8, zero padded), segments
+// Operand matrix  Z[4][chunks][n][16]  fp32 (columns zero padded to whole 16-float chunks; chunk-major so that the
+// 128-row x 16-float TMA box of one (segment, chunk) is 8 KB of contiguous global memory), segments
 // 0 = xc_hi, 1 = xc_lo, 2 = gc_hi, 3 = gc_lo; row terms rt[n] = (xx, gx, r, |g|^2).
 // Exact diagonal: for i == j the reference has x_i - x_j = 0 exactly, k0 = |g_i|^2 + D; the 3xTF32 residual
 // (~1e-6 |x|^2 in dd) would otherwise be amplified by (gg/2 + 3D/2), so the diagonal uses dd = gd = 0, gg = |g_i|^2.
@@ -22,7 +23,7 @@
 // segment chunks into one 64 KB smem stage (64-byte swizzle, K-major); 12 segment products
 // (3 for x.x, 3 for g.g, 6 for the cross term), issued as 6 N = 256 MMAs on adjacent column-side
 // segments, accumulate into four 128-column fp32 accumulators in TMEM.  Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc),
-// 2..9 = epilogue (tcgen05.ld -> IMQ formula -> fp64 partial sums; two warps per TMEM lane quarter, 64 columns each).
+// 2..17 = epilogue (tcgen05.ld -> IMQ formula -> fp64 partial sums; four warps per TMEM lane quarter, 32 columns each).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -37,7 +38,7 @@ constexpr int KC = 16;             // K-chunk (floats) per smem stage = 64 bytes
 constexpr int STAGES = 3;
 constexpr int CHUNK_BYTES = TILE * KC * 4;           // 8 KB per (segment, side) chunk
 constexpr int STAGE_BYTES = 8 * CHUNK_BYTES;         // 64 KB
-constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
+constexpr int NUM_THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue (4 per TMEM lane quarter)
 constexpr int TMEM_COLS = 512;     // 4 accumulators x 128 columns
 constexpr int UMMA_K = 8;          // tf32: 32 bytes of K per instruction
 
@@ -121,6 +122,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 64-byte-swizzled operand tile of TILE rows x 16 floats: row pitch 64 B, 8-row groups 512 B apart.
@@ -167,8 +173,9 @@ __global__ void split_kernel(const float* __restrict__ X, const float* __restric
   if (row >= n) return;
   const double inv_n = 1.0 / (double)n;
   float xx = 0.f, gx = 0.f, r = 0.f, mm = 0.f, g2 = 0.f;
-  float* z = Z + (size_t)row * 4 * dp;
-  for (int c = lane; c < dp; c += 32) {
+  const int n_chunks = (dp + KC - 1) / KC;
+  const int dpc = n_chunks * KC;                 // columns incl. the zero pad of the last chunk
+  for (int c = lane; c < dpc; c += 32) {
     float xh = 0.f, xl = 0.f, gh = 0.f, gl = 0.f;
     if (c < d) {
       const float mx = (float)(sums[c] * inv_n), mg = (float)(sums[d + c] * inv_n);
@@ -180,7 +187,10 @@ __global__ void split_kernel(const float* __restrict__ X, const float* __restric
       gh = tf32_rna(gc); gl = tf32_rna(gc - gh);
       xx = fmaf(xc, xc, xx); gx = fmaf(gc, xc, gx); r = fmaf(mg, gc, r); mm = fmaf(mg, mg, mm);
     }
-    z[c] = xh; z[dp + c] = xl; z[2 * dp + c] = gh; z[3 * dp + c] = gl;
+    // chunk-major layout: every (segment, chunk) is one contiguous [n][KC] block, so a 128-row TMA box is 8 KB contiguous
+    const size_t blk = (size_t)n * KC;
+    float* z = Z + ((size_t)(c / KC) * n + row) * KC + (c % KC);
+    z[0] = xh; z[(size_t)n_chunks * blk] = xl; z[2 * (size_t)n_chunks * blk] = gh; z[3 * (size_t)n_chunks * blk] = gl;
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
@@ -243,7 +253,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
     mbar_init(&tail->tmem_full, 1);
-    mbar_init(&tail->tmem_empty, 8);       // one arrival per epilogue warp
+    mbar_init(&tail->tmem_empty, 16);      // one arrival per epilogue warp
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(&tail->tmem_base, TMEM_COLS); tmem_relinquish(); }
@@ -266,8 +276,9 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
           mbar_arrive_expect_tx(&tail->full[stage], STAGE_BYTES);
 #pragma unroll
           for (int seg = 0; seg < 4; ++seg) {
-            tma_load_2d(sbase + seg * CHUNK_BYTES, &zmap, seg * dp + c * KC, I * TILE, &tail->full[stage]);
-            tma_load_2d(sbase + (4 + col_slot(seg)) * CHUNK_BYTES, &zmap, seg * dp + c * KC, J * TILE, &tail->full[stage]);
+            const int blk_row = (seg * n_chunks + c) * n;          // first row of block (segment, chunk) in the [.., KC] view
+            tma_load_2d(sbase + seg * CHUNK_BYTES, &zmap, 0, blk_row + I * TILE, &tail->full[stage]);
+            tma_load_2d(sbase + (4 + col_slot(seg)) * CHUNK_BYTES, &zmap, 0, blk_row + J * TILE, &tail->full[stage]);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -307,11 +318,11 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       }
     }
   } else {
-    // ===== epilogue: warps 2..9; warp w reads TMEM lanes 32*(w%4) .. +31, column half (w-2)/4 =====
+    // ===== epilogue: warps 2..17; warp w reads TMEM lanes 32*(w%4) .. +31, columns 32*((w-2)/4) .. +31 =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int cgrp = (warp - 2) >> 2;                          // 0..3
     const int row_in_tile = q * 32 + lane;
-    const int et = threadIdx.x - 64;                           // 0..255
+    const int et = threadIdx.x - 64;                           // 0..511
     const float dim = (float)d;
     double acc = 0.0;
     uint32_t acc_phase = 0;
@@ -323,30 +334,42 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       const int gjc = J * TILE + et;
       if (et < TILE) tail->colterm[buf][et] = gjc < n ? rt[gjc] : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 ri = gi < n ? rt[gi] : make_float4(0.f, 0.f, 0.f, 0.f);
-      asm volatile("bar.sync 1, 256;" ::: "memory");          // colterm[buf] visible to the 8 epilogue warps
+      asm volatile("bar.sync 1, 512;" ::: "memory");          // colterm[buf] visible to the 16 epilogue warps
       mbar_wait(&tail->tmem_full, acc_phase);
       tc_fence_after();
       float tsum = 0.f;
       const bool diag_tile = I == J;
       const int jmax = min(TILE, n - J * TILE);
+      const bool interior = !diag_tile && (I + 1) * TILE <= n && jmax == TILE;   // no masks, no exact diagonal
       const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int cb = half * (TILE / 2); cb < (half + 1) * (TILE / 2); cb += 16) {
-        uint32_t p1[16], p2[16], p3[16], p4[16];
-        tmem_ld16(tl + cb, p1);                 // x_I.x_J
-        tmem_ld16(tl + 3 * TILE + cb, p2);      // g_I.g_J
-        tmem_ld16(tl + TILE + cb, p3);          // x_I.g_J
-        tmem_ld16(tl + 2 * TILE + cb, p4);      // g_I.x_J
+      for (int cb = cgrp * 32; cb < cgrp * 32 + 32; cb += 8) {
+        uint32_t p1[8], p2[8], p3[8], p4[8];
+        tmem_ld8(tl + cb, p1);                  // x_I.x_J
+        tmem_ld8(tl + 3 * TILE + cb, p2);       // g_I.g_J
+        tmem_ld8(tl + TILE + cb, p3);           // x_I.g_J
+        tmem_ld8(tl + 2 * TILE + cb, p4);       // g_I.x_J
         tmem_ld_wait();
+        if (interior) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float4 cj = tail->colterm[buf][cb + e];
-          float dd = fmaf(-2.0f, __uint_as_float(p1[e]), ri.x + cj.x);
-          float gg = __uint_as_float(p2[e]) + (ri.z + cj.z);
-          float gd = (ri.y + cj.y) - (__uint_as_float(p3[e]) + __uint_as_float(p4[e]));
-          if (diag_tile && cb + e == row_in_tile) { dd = 0.f; gd = 0.f; gg = ri.w; }   // i == j: exact
-          const float k0 = imq_k0_tc(dd, gg, gd, dim);
-          tsum += (gi < n && cb + e < jmax) ? k0 : 0.f;
+          for (int e = 0; e < 8; ++e) {
+            const float4 cj = tail->colterm[buf][cb + e];
+            const float dd = fmaf(-2.0f, __uint_as_float(p1[e]), ri.x + cj.x);
+            const float gg = __uint_as_float(p2[e]) + (ri.z + cj.z);
+            const float gd = (ri.y + cj.y) - (__uint_as_float(p3[e]) + __uint_as_float(p4[e]));
+            tsum += imq_k0_tc(dd, gg, gd, dim);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 cj = tail->colterm[buf][cb + e];
+            float dd = fmaf(-2.0f, __uint_as_float(p1[e]), ri.x + cj.x);
+            float gg = __uint_as_float(p2[e]) + (ri.z + cj.z);
+            float gd = (ri.y + cj.y) - (__uint_as_float(p3[e]) + __uint_as_float(p4[e]));
+            if (diag_tile && cb + e == row_in_tile) { dd = 0.f; gd = 0.f; gg = ri.w; }   // i == j: exact
+            const float k0 = imq_k0_tc(dd, gg, gd, dim);
+            tsum += (gi < n && cb + e < jmax) ? k0 : 0.f;
+          }
         }
       }
       tc_fence_before();
@@ -369,10 +392,10 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
 // ------------------------------------------------------------------------------------------ host
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int padded_dim(int d) { return (d + 7) & ~7; }
-// workspace: Z [n][4][dp] floats | row terms [n] float4 | column sums [2 d] doubles
+inline size_t z_floats(int n, int d) { return (size_t)4 * ((padded_dim(d) + KC - 1) / KC) * KC * (size_t)n; }
+// workspace: Z [4 segments][chunks][n][KC] floats | row terms [n] float4 | column sums [2 d] doubles
 inline size_t workspace_bytes(int n, int d) {
-  const size_t dp = padded_dim(d);
-  return align_up((size_t)n * 4 * dp * sizeof(float), 256) + align_up((size_t)n * sizeof(float4), 256) +
+  return align_up(z_floats(n, d) * sizeof(float), 256) + align_up((size_t)n * sizeof(float4), 256) +
          align_up((size_t)2 * d * sizeof(double), 256);
 }
 
