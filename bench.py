@@ -157,7 +157,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -173,7 +173,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        if not rows and self.rows:       # timed region shorter than the sampling period: the samples nearest to it
+            mid = 0.5 * (t0 + t1)
+            rows = [r for _, r in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]]
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
@@ -329,6 +332,7 @@ def gpu_arm(args):
     st = eng.new_state(torch.from_numpy(theta0_host).cuda())
     eng.init(st, keys_dev, sampler_mode=True)
     samples = torch.empty((C, K, P), dtype=torch.float32, device="cuda")
+    clocks = ClockSampler(local) if rank == 0 else None      # already streaming when the timed region starts
     i0 = 0
     for _ in range(args.warmup):
         eng.run(st, i0, K, samples); i0 += K
@@ -336,7 +340,6 @@ def gpu_arm(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local) if rank == 0 else None
     l0 = lib.sgmcmc_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_wall0 = time.perf_counter()

@@ -25,7 +25,14 @@
 namespace sg {
 
 template <int FAMILY> struct BigThreads { static constexpr int value = 1024; };
-template <> struct BigThreads<SGMCMC_FAMILY_MLP> { static constexpr int value = 512; };   // 16 warps: 4 per TMEM lane quarter
+// MLP: warps 0..15 run the gradient (4 per TMEM lane quarter).  SG_MLP_PRODUCER_WARPS > 0 adds warps that generate
+// the NEXT update's Gaussian noise in the shadow of the GEMM phase (all warps run the elementwise passes); measured
+// in round 1 with 8 producer warps: the 85-register cap of a 768-thread CTA costs the GEMM phase more than the
+// look-ahead saves (1.82 ms vs 1.34 ms per 4 pSGLD steps), so the default is 0.
+#ifndef SG_MLP_PRODUCER_WARPS
+#define SG_MLP_PRODUCER_WARPS 0
+#endif
+template <> struct BigThreads<SGMCMC_FAMILY_MLP> { static constexpr int value = 512 + 32 * SG_MLP_PRODUCER_WARPS; };
 
 struct BigModel {
   int family, estimator, diffusion, flags;
@@ -56,7 +63,12 @@ struct BigRun {
   const uint32_t* init_keys;
   const float* fg_thetas;    // [M, P] (mode 3)
   float* fg_out;             // [M, P]
+  float* noise;              // [C, P] scratch for noise generated one update ahead (families with producer warps), or nullptr
 };
+
+// Work for the noise-producer warps during a likelihood pass: normal(split(split(key)[0], n_leaves)[leaf], (n_leaf,))
+// for every leaf into dst[P] - the noise of the langevin step that will run with `key`.
+struct NoiseJob { Key key; float* dst; bool valid; };
 
 struct BigSmem {
   uint32_t keys[2 * (4 + 2 * MAXL)];
@@ -136,6 +148,35 @@ __device__ __forceinline__ void plain_pass(unsigned n, LD ld, ST st) {
   for (; e0 < n; e0 += bd) { const Elt v = ld(e0); st(e0, v); }
 }
 
+// Elementwise pass with the noise read from a buffer filled one update ahead: v = ld(e) ... st(e, v, xi[e]).
+template <int U, class LD, class ST>
+__device__ __forceinline__ void noise_pass(unsigned n, const float* xi, LD ld, ST st) {
+  const unsigned bd = blockDim.x;
+  unsigned e0 = threadIdx.x;
+#pragma unroll 1
+  for (; e0 + (2 * U - 1) * bd < n; e0 += 2 * U * bd) {
+    Elt v[2 * U];
+    float z[2 * U];
+#pragma unroll
+    for (int u = 0; u < 2 * U; ++u) { v[u] = ld(e0 + u * bd); z[u] = xi[e0 + u * bd]; }
+#pragma unroll
+    for (int u = 0; u < 2 * U; ++u) st(e0 + u * bd, v[u], z[u]);
+  }
+#pragma unroll 1
+  for (; e0 < n; e0 += bd) { const Elt v = ld(e0); const float z = xi[e0]; st(e0, v, z); }
+}
+
+// Producer side: the threads [t0, t0 + nt) of the CTA fill dst[0, n) with normal(key, (n,)).
+__device__ __forceinline__ void produce_leaf_noise(unsigned n, Key key, float* dst, unsigned t, unsigned nt) {
+  const unsigned h = (n + 1u) >> 1;
+  for (unsigned m = t; m < h; m += nt) {
+    uint32_t w0, w1;
+    stream_block(key, m, n, w0, w1);
+    dst[m] = bits_to_normal(w0);
+    if (m + h < n) dst[m + h] = bits_to_normal(w1);
+  }
+}
+
 template <int FAMILY> struct BigUnroll { static constexpr int value = 2; };                  // 1024 threads: 64 registers
 #ifndef SG_BIG_UNROLL_MLP
 #define SG_BIG_UNROLL_MLP 4
@@ -180,12 +221,13 @@ __device__ __forceinline__ void pmf_rating(const float* theta, const float* cent
 template <>
 struct FamilyGrad<SGMCMC_FAMILY_PMF> {
   static constexpr size_t smem_bytes(const BigModel&) { return 0; }
+  static constexpr bool kNoiseProducers = false;
   __device__ static void cta_init(const BigModel&, void*) {}
   __device__ static void cta_fini(const BigModel&, void*) {}
 
   __device__ static void lik_pass(const BigModel& m, void* /*fam_smem*/, const float* theta, const float* center,
                                   bool sequential, const RandintPlan& plan, unsigned seq_base, unsigned count, float* g,
-                                  bool /*fresh*/) {
+                                  bool /*fresh*/, const NoiseJob& /*job*/) {
     const int r = m.dims[2];
     const int offV = m.leaf_off[1];
     const int4* __restrict__ rat = reinterpret_cast<const int4*>(m.data0);
@@ -260,6 +302,8 @@ struct BigCtx {
   // and zero passes over the P-vector).  At launch boundaries the buffer holds the finalised param_grad.
   bool grad_raw = false;
   float gscale = 1.0f;
+  float* noise = nullptr;     // this chain's row of the look-ahead noise buffer (nullptr: generate in place)
+  bool noise_ready = false;   // noise[] holds the draws of the NEXT langevin step
 
   __device__ BigCtx(const BigModel& mm, BigSmem& ss, void* fs) : m(mm), s(ss), fam_smem(fs) {}
 
@@ -297,7 +341,7 @@ struct BigCtx {
   __device__ void full_grad(const float* th, float* out) {
     zero(out);
     RandintPlan dummy{};
-    FamilyGrad<FAMILY>::lik_pass(m, fam_smem, th, nullptr, true, dummy, 0u, m.n_data, out, true);
+    FamilyGrad<FAMILY>::lik_pass(m, fam_smem, th, nullptr, true, dummy, 0u, m.n_data, out, true, NoiseJob{});
     __syncthreads();
     const float prior = m.coef[1];
     // __ldcg: the sums may have been accumulated with L2 atomics, so read them at L2
@@ -316,8 +360,10 @@ struct BigCtx {
   }
 
   // estimate_gradient: on entry the gradient buffer is all zero unless is_init
-  __device__ __noinline__ void estimate(int i, Key k2, bool is_init) {
+  __device__ __noinline__ void estimate(int i, Key k2, bool is_init, Key next_key = Key{0u, 0u}, bool has_next = false) {
     const bool cv = is_cv();
+    // the producer warps generate the next step's noise during the first likelihood pass of this estimate
+    NoiseJob job{next_key, noise, has_next && noise != nullptr && FamilyGrad<FAMILY>::kNoiseProducers};
     if (m.estimator == SGMCMC_EST_SVRG) {
       if (is_init) {                                       // gradient_estimation.py:124-128
         full_grad(theta, svrg_fb);
@@ -338,15 +384,16 @@ struct BigCtx {
     RandintPlan plan{};
     if (m.estimator == SGMCMC_EST_STANDARD && m.full_batch && !is_init) {
       // static full-batch bypass, gradient_estimation.py:41-42 (init_gradient still subsamples, :31-35)
-      FamilyGrad<FAMILY>::lik_pass(m, fam_smem, theta, nullptr, true, plan, 0u, m.n_data, grad, true);
+      FamilyGrad<FAMILY>::lik_pass(m, fam_smem, theta, nullptr, true, plan, 0u, m.n_data, grad, true, job);
       gscale = 1.0f;
     } else {
       plan = randint_plan(k2, m.n_data, m.batch);
-      FamilyGrad<FAMILY>::lik_pass(m, fam_smem, theta, cv ? center : nullptr, false, plan, 0u, m.batch, grad, true);
+      FamilyGrad<FAMILY>::lik_pass(m, fam_smem, theta, cv ? center : nullptr, false, plan, 0u, m.batch, grad, true, job);
       gscale = m.scale;
     }
     __syncthreads();
     grad_raw = true;
+    noise_ready = job.valid;
     if (is_init) finalize();
   }
 
@@ -381,6 +428,7 @@ struct BigCtx {
     // scalars the per-element code needs, read once (the model lives in param space behind a reference)
     const float gs = gscale, prior = m.coef[1];
     const sgmcmc_step_coef cfv = cf;
+    const bool use_noise = noise_ready && phase == 1 && !bug;   // draws of this step were generated during the last estimate
     if (phase == 2 || bug) {                      // baoab / badodab update2: v += dt/2 * g
       const bool consume = phase == 1;
       plain_pass<U>((unsigned)m.P,
@@ -409,13 +457,18 @@ struct BigCtx {
       auto ld_xvg = [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; ld_grad<MODE>(t, g, e, off + e); return t; };
       auto ld_xvvg = [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; t.b = v2[e]; ld_grad<MODE>(t, g, e, off + e); return t; };
       auto emit = [&](unsigned e, float xn) { x[e] = xn; g[e] = 0.f; if (smp) __stcs(smp + e, xn); };
+      const float* xi_buf = noise + off;
+      // st(e, t, xi) for every element with its N(0,1) draw: from the look-ahead buffer, or generated in place
+      auto noisy = [&](Key key, auto ld, auto st) {
+        if (use_noise) noise_pass<U>(n, xi_buf, ld, st); else leaf_pass<U>(n, key, ld, st);
+      };
       switch (m.diffusion) {
         case SGMCMC_DIFF_SGLD:
-          leaf_pass<U>(n, lk, ld_xg, [&](unsigned e, const Elt& t, float xi) { emit(e, fmaf(cfv.ca, xi, fmaf(cfv.h, gval<MODE>(t, gs, prior), t.x))); });
+          noisy(lk, ld_xg, [&](unsigned e, const Elt& t, float xi) { emit(e, fmaf(cfv.ca, xi, fmaf(cfv.h, gval<MODE>(t, gs, prior), t.x))); });
           break;
         case SGMCMC_DIFF_PSGLD: {
           const float alpha = m.hyper[0], eps = m.hyper[1];
-          leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
+          noisy(lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
             const float gg = gval<MODE>(t, gs, prior);
             const float vv = alpha * t.a + (1.0f - alpha) * (gg * gg);
             const float G = fast_rcp(fast_sqrt(vv) + eps);
@@ -426,7 +479,7 @@ struct BigCtx {
         }
         case SGMCMC_DIFF_SGLDADAM: {
           const float b1 = m.hyper[0], b2 = m.hyper[1], eps = m.hyper[2];
-          leaf_pass<U>(n, lk, ld_xvvg, [&](unsigned e, const Elt& t, float xi) {
+          noisy(lk, ld_xvvg, [&](unsigned e, const Elt& t, float xi) {
             const float gg = gval<MODE>(t, gs, prior);
             const float mm = b1 * t.a + (1.0f - b1) * gg;
             const float vv = b2 * t.b + (1.0f - b2) * (gg * gg);
@@ -439,14 +492,14 @@ struct BigCtx {
         }
         case SGMCMC_DIFF_SGHMC: {
           const float alpha = m.hyper[0];
-          leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
+          noisy(lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
             v[e] = t.a + cfv.h * gval<MODE>(t, gs, prior) - alpha * t.a + cfv.ca * xi;
             emit(e, t.x + t.a);
           });
           break;
         }
         case SGMCMC_DIFF_BAOAB:
-          leaf_pass<U>(n, lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
+          noisy(lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
             float ve = fmaf(cfv.hh, gval<MODE>(t, gs, prior), t.a);
             float xe = t.x + ve * cfv.h * 0.5f;
             ve = cfv.ca * ve + cfv.cb * xi;
@@ -461,7 +514,7 @@ struct BigCtx {
           const bool first = (i == 0);
           if (first) split2(lk, kn, sub);               // diffusions.py:268-278
           float ss = 0.f;
-          leaf_pass<U>(n, kn, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
+          noisy(kn, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
             float ve = first ? cfv.cb * normal_at(sub, e, n) : t.a;
             ve = ve - alpha * ve + cfv.h * gval<MODE>(t, gs, prior) + cfv.ca * xi;
             v[e] = ve;
@@ -485,7 +538,7 @@ struct BigCtx {
           const float c2 = (alpha == 0.0f) ? cfv.ca : sqrtf(fabsf((1.0f - c1 * c1) / (2.0f * alpha)));
           __syncthreads();
           float ss2 = 0.f;
-          leaf_pass<U>(n, lk, [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; return t; },
+          noisy(lk, [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; return t; },
                        [&](unsigned e, const Elt& t, float xi) {
                          const float ve = c1 * t.a + c2 * xi;
                          v[e] = ve; ss2 = fmaf(ve, ve, ss2);
@@ -502,18 +555,29 @@ struct BigCtx {
     }
     __syncthreads();
     grad_raw = false;                             // consumed: the buffer is all zero now
+    noise_ready = false;
   }
 
-  __device__ void langevin(int i, Key key, const sgmcmc_step_coef& cf, float* sample) {
+  // `next_key` / `has_next`: the key of the NEXT langevin step of this chain, if it is already known (look-ahead noise)
+  __device__ void langevin(int i, Key key, const sgmcmc_step_coef& cf, float* sample, Key next_key, bool has_next) {
     expand_step_keys(key);
     Key k2; k2.a = s.keys[2]; k2.b = s.keys[3];
     diffuse(1, i, cf, 4, sample);
-    estimate(i, k2, false);
+    estimate(i, k2, false, next_key, has_next);
     if (m.diffusion == SGMCMC_DIFF_BAOAB || m.diffusion == SGMCMC_DIFF_BADODAB) diffuse(2, i, cf, 4, nullptr);
   }
 
-  __device__ void transition(int i, Key key, const sgmcmc_step_coef& cf, float* sample) {
-    if (m.diffusion != SGMCMC_DIFF_SGHMC) { langevin(i, key, cf, sample); return; }
+  // key of the first langevin step of the transition that runs with per-sample key `sub`
+  __device__ Key first_langevin_key(Key sub) const {
+    if (m.diffusion != SGMCMC_DIFF_SGHMC) return sub;
+    Key k1, k2;
+    split2(sub, k1, k2);
+    return split_at(k2, m.leapfrog, 0);
+  }
+
+  __device__ void transition(int i, Key key, const sgmcmc_step_coef& cf, float* sample, Key next_sub, bool has_next) {
+    const Key next_first = has_next ? first_langevin_key(next_sub) : Key{0u, 0u};
+    if (m.diffusion != SGMCMC_DIFF_SGHMC) { langevin(i, key, cf, sample, next_first, has_next); return; }
     Key k1, k2;
     split2(key, k1, k2);
     for (int leaf = 0; leaf < m.n_leaves; ++leaf) {          // resample_momentum, diffusions.py:197-199
@@ -524,8 +588,11 @@ struct BigCtx {
                    [&](unsigned e, const Elt&, float xi) { v[e] = cf.cb * xi; });
     }
     __syncthreads();
-    for (int l = 0; l < m.leapfrog; ++l)
-      langevin(i, split_at(k2, m.leapfrog, l), cf, l == m.leapfrog - 1 ? sample : nullptr);
+    for (int l = 0; l < m.leapfrog; ++l) {
+      const bool last = l == m.leapfrog - 1;
+      langevin(i, split_at(k2, m.leapfrog, l), cf, last ? sample : nullptr,
+               last ? next_first : split_at(k2, m.leapfrog, l + 1), last ? has_next : true);
+    }
   }
 };
 
@@ -554,6 +621,7 @@ __global__ void __launch_bounds__(BigThreads<FAMILY>::value, 1) big_sampler_kern
   ctx.svrg_fb = st.svrg_grad ? st.svrg_grad + c * P : nullptr;
   if (m.estimator == SGMCMC_EST_SVRG) { ctx.center = ctx.svrg_center; ctx.fb = ctx.svrg_fb; }
   else { ctx.center = m.cv_center; ctx.fb = m.cv_grad; }
+  ctx.noise = run.noise ? run.noise + c * P : nullptr;
 
   if (threadIdx.x < MAXL) {
     float a = 0.f;
@@ -579,11 +647,16 @@ __global__ void __launch_bounds__(BigThreads<FAMILY>::value, 1) big_sampler_kern
     for (int sidx = 0; sidx < run.K; ++sidx) {
       const int i = run.i0 + sidx;
       const sgmcmc_step_coef cf = run.coef[(size_t)sidx * run.coef_stride];
-      Key sub;
+      Key sub, next_sub{0u, 0u};
+      bool has_next = false;
       if (run.step_keys) { sub.a = run.step_keys[2 * c]; sub.b = run.step_keys[2 * c + 1]; }
-      else { Key nk; split2(carry, nk, sub); carry = nk; }      // samplers.py:49
+      else {
+        Key nk; split2(carry, nk, sub); carry = nk;             // samplers.py:49
+        if (sidx + 1 < run.K) { Key nk2; split2(carry, nk2, next_sub); has_next = true; }   // peek at the next iteration's key
+      }
       // get_params after the transition: the sample is written by the diffusion pass that produces it
-      ctx.transition(i, sub, cf, run.samples ? run.samples + (size_t)c * run.sample_chain_stride + (size_t)sidx * P : nullptr);
+      ctx.transition(i, sub, cf, run.samples ? run.samples + (size_t)c * run.sample_chain_stride + (size_t)sidx * P : nullptr,
+                     next_sub, has_next);
     }
     ctx.finalize();                                             // the state's param_grad is the finalised gradient
   }

@@ -46,6 +46,8 @@ struct sgmcmc_handle {
   float* cv_grad = nullptr;    // owned: [P]
   float* partial = nullptr;    // owned scratch for sgmcmc_fullbatch_grad
   size_t partial_elems = 0;
+  float* noise = nullptr;      // owned scratch [n_chains][P]: look-ahead Gaussian noise of the MLP sampler
+  size_t noise_elems = 0;
   int num_sms = 148;
   bool has_data = false, has_center = false;
 };
@@ -349,6 +351,7 @@ int sgmcmc_destroy(sgmcmc_handle* h) {
   if (h->cv_center) cudaFree(h->cv_center);
   if (h->cv_grad) cudaFree(h->cv_grad);
   if (h->partial) cudaFree(h->partial);
+  if (h->noise) cudaFree(h->noise);
   delete h;
   return SGMCMC_OK;
 }
@@ -446,6 +449,16 @@ int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const 
     sg::BigRun run{};
     run.st = *st; run.i0 = i0; run.K = k; run.coef = coef; run.coef_stride = coef_stride; run.samples = samples;
     run.sample_chain_stride = sample_chain_stride > 0 ? (size_t)sample_chain_stride : (size_t)k * h->P;
+    if (h->cfg.family == SGMCMC_FAMILY_MLP && k > 1 && !env_int("SGMCMC_NO_LOOKAHEAD", 0)) {       // look-ahead noise scratch (stream-ordered reuse: one stream per handle)
+      const size_t need = (size_t)st->n_chains * h->P;
+      if (need > h->noise_elems) {
+        if (h->noise) CUDA_TRY(cudaFree(h->noise));
+        h->noise = nullptr; h->noise_elems = 0;
+        CUDA_TRY(cudaMalloc(&h->noise, need * sizeof(float)));
+        h->noise_elems = need;
+      }
+      run.noise = h->noise;
+    }
     return dispatch_big(h, run, st->n_chains, (cudaStream_t)stream);
   }
   sg::VecRun run{};

@@ -27,7 +27,7 @@
 namespace sg {
 
 constexpr int MLP_ROWS = 128;      // largest sub-batch (MMA M of the forward contraction)
-constexpr int MLP_THREADS = 512;
+constexpr int MLP_THREADS = 512;   // gradient worker threads (warps 0..15); the CTA has 8 more noise-producer warps
 constexpr int MLP_KC = 32;         // forward K chunk (floats): one 128-byte swizzled row
 constexpr size_t MLP_SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
@@ -114,6 +114,9 @@ inline const char* mlp_validate(const sgmcmc_config* cfg) {
 namespace mlptc {
 using namespace ksdtc;
 
+// barrier of the 512 gradient worker threads (the noise-producer warps are elsewhere during a likelihood pass)
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
 // K-major, 128-byte swizzle: rows of 32 floats, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t desc_k_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -169,6 +172,7 @@ __device__ __forceinline__ float4 load4(const float* src, int valid, bool a16, b
 
 template <>
 struct FamilyGrad<SGMCMC_FAMILY_MLP> {
+  static constexpr bool kNoiseProducers = SG_MLP_PRODUCER_WARPS > 0;
   static size_t smem_bytes(const BigModel& m) { return sizeof(MlpSmem) + 16 + mlp_plan(m.dims, m.batch).total_bytes; }
 
   __device__ static void cta_init(const BigModel& m, void* fam_smem) {
@@ -273,7 +277,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       if (w1_in) { split4(wv1, hi, lo); *reinterpret_cast<float4*>(whi + off1) = hi; *reinterpret_cast<float4*>(wlo + off1) = lo; }
       if (c + 2 < n_chunks) fetch(c + 2, xv0, xv1, wv0, wv1);               // two chunks of loads stay in flight
       fence_proxy_async();
-      __syncthreads();
+      mlptc::worker_sync();
       if (tid == 0) {
         tc_fence_after();
         const int slices = min(MLP_KC, s0p8 - c * MLP_KC) / 8;
@@ -320,9 +324,9 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       }
     }
     tc_fence_before();
-    __syncthreads();
+    mlptc::worker_sync();
     if (tid == 0) { ms.parity[0] = par[0]; ms.parity[1] = par[1]; }
-    __syncthreads();
+    mlptc::worker_sync();
   }
 
   // ---------------------------------------------------------------------------------------------------
@@ -389,7 +393,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         *reinterpret_cast<float4*>(sb + 8192 + soff) = lo;
         if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
         fence_proxy_async();
-        __syncthreads();
+        mlptc::worker_sync();
         if (tid == 0) {
           tc_fence_after();
           const int g = u / npp, p = u - g * npp;
@@ -454,10 +458,10 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         }
       }
       tc_fence_before();
-      __syncthreads();                                            // TMEM tiles are free for the next pass
+      mlptc::worker_sync();                                            // TMEM tiles are free for the next pass
     }
     if (tid == 0) { ms.parity[0] = par[0]; ms.parity[1] = par[1]; }
-    __syncthreads();
+    mlptc::worker_sync();
   }
 
   // ---------------------------------------------------------------------------------------------------
@@ -492,19 +496,19 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         const float inv = 1.0f / sum;
         for (int c = 0; c < w; ++c) A[tid * as + c] *= inv;
       }
-      __syncthreads();
+      mlptc::worker_sync();
       float* Zn = act(l + 1);
       const int zs = astr(l + 1), wn = sz[l + 1];
       const float* Wn = th + m.leaf_off[2 * l];
       const float* bn = th + m.leaf_off[2 * l + 1];
-      for (int o = tid; o < R * wn; o += blockDim.x) {            // z_{l+1}[b][n] = a_l[b] . W[n] + b[n]
+      for (int o = tid; o < R * wn; o += MLP_THREADS) {            // z_{l+1}[b][n] = a_l[b] . W[n] + b[n]
         const int b = o % R, n = o / R;
         float accv = 0.f;
         const float* wr = Wn + (size_t)n * w;
         for (int k = 0; k < w; ++k) accv = fmaf(A[b * as + k], wr[k], accv);
         Zn[b * zs + n] = accv + bn[n];
       }
-      __syncthreads();
+      mlptc::worker_sync();
     }
 
     // =================================================================== output layer: dZ_L = y - sum(y) softmax(z_L)
@@ -526,7 +530,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           for (int c = 0; c < w; ++c) dz[tid * dzs + c] = 0.f;      // padded rows contribute nothing
         }
       }
-      __syncthreads();
+      mlptc::worker_sync();
     }
 
     uint8_t* bhi = region;
@@ -544,13 +548,13 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       const float* Wl = th + m.leaf_off[2 * (l - 1)];
       float* gW = g + m.leaf_off[2 * (l - 1)];
       float* gb = g + m.leaf_off[2 * (l - 1) + 1];
-      for (int o = tid; o < w * wp; o += blockDim.x) {             // dW_l[n][k] = sum_b dz[b][n] a_{l-1}[b][k]
+      for (int o = tid; o < w * wp; o += MLP_THREADS) {             // dW_l[n][k] = sum_b dz[b][n] a_{l-1}[b][k]
         const int k = o % wp, n = o / wp;
         float accv = 0.f;
         for (int b = 0; b < nb; ++b) accv = fmaf(dz[b * dzs + n], A[b * as + k], accv);
         gW[o] += sign * accv;
       }
-      for (int n = tid; n < w; n += blockDim.x) {
+      for (int n = tid; n < w; n += MLP_THREADS) {
         float accv = 0.f;
         for (int b = 0; b < nb; ++b) accv += dz[b * dzs + n];
         gb[n] += sign * accv;
@@ -559,19 +563,19 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         // dA_{l-1} = dz W_l ; dZ_{l-1} = a (dA - sum_k a dA)   (softmax Jacobian)
         float* dn = dzbuf(cur ^ 1);
         const int dns = dzstr(cur ^ 1);
-        for (int o = tid; o < R * wp; o += blockDim.x) {
+        for (int o = tid; o < R * wp; o += MLP_THREADS) {
           const int b = o % R, k = o / R;
           float accv = 0.f;
           for (int n = 0; n < w; ++n) accv = fmaf(dz[b * dzs + n], Wl[(size_t)n * wp + k], accv);
           dn[b * dns + k] = accv;
         }
-        __syncthreads();
+        mlptc::worker_sync();
         if (tid < R) {
           float dotv = 0.f;
           for (int k = 0; k < wp; ++k) dotv = fmaf(A[tid * as + k], dn[tid * dns + k], dotv);
           for (int k = 0; k < wp; ++k) dn[tid * dns + k] = tid < nb ? A[tid * as + k] * (dn[tid * dns + k] - dotv) : 0.f;
         }
-        __syncthreads();
+        mlptc::worker_sync();
         dz = dn; dzs = dns; cur ^= 1;
       } else {
         // l == 2: dZ_1 of row b by a quad of threads (columns j = q, q + 4, ...), written straight into the
@@ -611,8 +615,8 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
             if (lane < 4) red[warp * 128 + j] = v;
           }
         }
-        __syncthreads();
-        for (int n = tid; n < s1; n += blockDim.x) {
+        mlptc::worker_sync();
+        for (int n = tid; n < s1; n += MLP_THREADS) {
           float accv = 0.f;
           for (int w16 = 0; w16 < 16; ++w16) accv += red[w16 * 128 + n];
           gb1[n] += sign * accv;
@@ -620,32 +624,45 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       }
     }
     if (L == 1) {                                                   // the output layer is layer 1: convert its fp32 dZ
-      for (int n = tid; n < s1; n += blockDim.x) {
+      for (int n = tid; n < s1; n += MLP_THREADS) {
         float accv = 0.f;
         for (int b = 0; b < nb; ++b) accv += dz[b * dzs + n];
         gb1[n] += sign * accv;
       }
-      for (int e = tid; e < R * s1n; e += blockDim.x) {
+      for (int e = tid; e < R * s1n; e += MLP_THREADS) {
         const int b = e / s1n, j = e - b * s1n;
         put_dz1(bhi, blo, b, j, (j < s1 && b < nb) ? dz[b * dzs + j] : 0.f);
       }
     }
     mlptc::fence_proxy_async();
-    __syncthreads();
+    mlptc::worker_sync();
 
     layer1_backward(m, ms, region, xs, sign, nb, R, g + m.leaf_off[0], overwrite);
   }
 
   __device__ static void lik_pass(const BigModel& m, void* fam_smem, const float* theta, const float* center,
                                   bool sequential, const RandintPlan& plan, unsigned seq_base, unsigned count, float* g,
-                                  bool fresh) {
+                                  bool fresh, const NoiseJob& job) {
+    if (threadIdx.x >= MLP_THREADS) {
+      // noise-producer warps: the Gaussian draws of the NEXT diffusion update (its key tree is data independent,
+      // diffusion_util.py:66), generated while the worker warps run the GEMM phase; the caller's __syncthreads() after
+      // the pass publishes them
+      if (job.valid) {
+        Key k1, k2;
+        split2(job.key, k1, k2);
+        for (int leaf = 0; leaf < m.n_leaves; ++leaf)
+          produce_leaf_noise((unsigned)(m.leaf_off[leaf + 1] - m.leaf_off[leaf]), split_at(k1, m.n_leaves, leaf),
+                             job.dst + m.leaf_off[leaf], threadIdx.x - MLP_THREADS, blockDim.x - MLP_THREADS);
+      }
+      return;
+    }
     MlpSmem& ms = *reinterpret_cast<MlpSmem*>(fam_smem);
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(&ms + 1) + 1023) & ~(uintptr_t)1023);
     const unsigned rows = (unsigned)mlp_plan(m.dims, m.batch).rows;
     const unsigned h = (count + 1u) >> 1;
     for (unsigned base_row = 0; base_row < count; base_row += rows) {
       const int nb = (int)min(rows, count - base_row);
-      __syncthreads();
+      mlptc::worker_sync();
       if (threadIdx.x < (unsigned)nb) {
         const unsigned pos = base_row + threadIdx.x;
         unsigned id;
@@ -658,7 +675,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         }
         ms.idx[threadIdx.x] = (int)id;
       }
-      __syncthreads();
+      mlptc::worker_sync();
       // the first sub-batch into an all-zero buffer stores dW1 instead of read-modify-writing it
       sub_batch(m, ms, base, theta, 1.0f, nb, g, fresh && base_row == 0);
       if (center) sub_batch(m, ms, base, center, -1.0f, nb, g, false);
