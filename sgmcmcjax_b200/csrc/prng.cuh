@@ -15,7 +15,9 @@ namespace sg {
 
 struct Key { uint32_t a, b; };
 
-__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+// plain C rotate (ptxas emits SHF.L.W): __funnelshift_l is an `asm volatile` in the CUDA headers, and volatile asms
+// keep program order among themselves - independent threefry blocks could then never interleave (no ILP)
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
 
 // One Threefry-2x32-20 block.
 __device__ __forceinline__ void threefry(Key k, uint32_t& x0, uint32_t& x1) {
