@@ -11,7 +11,7 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libsgmcmc_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["prng.cuh", "vec_sampler.cuh", "ksd.cuh", "ksd_tc.cuh", "big_sampler.cuh", "mlp_grad.cuh"]
+HEADERS = ["prng.cuh", "vec_sampler.cuh", "ksd.cuh", "ksd_tc.cuh", "big_sampler.cuh", "mlp_grad.cuh", "k2_gemm.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC",

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "big_sampler.cuh"
+#include "k2_gemm.cuh"
 #include "ksd.cuh"
 #include "ksd_tc.cuh"
 #include "mlp_grad.cuh"
@@ -48,6 +49,10 @@ struct sgmcmc_handle {
   size_t partial_elems = 0;
   float* noise = nullptr;      // owned scratch [n_chains][P]: look-ahead Gaussian noise of the MLP sampler
   size_t noise_elems = 0;
+  float* k2_xs = nullptr;      // owned: X~ split K-major chunk-major (tensor-core K2, built on first use)
+  float* k2_xt = nullptr;      // owned: X~^T split
+  float* k2_scratch = nullptr; // owned: [theta split | G | W] of the current call
+  size_t k2_scratch_bytes = 0;
   int num_sms = 148;
   bool has_data = false, has_center = false;
 };
@@ -247,6 +252,86 @@ int fullgrad_impl(sgmcmc_handle* h, const float* thetas, int m, float* out, cuda
   return SGMCMC_OK;
 }
 
+int encode_rows16(CUtensorMap* map, float* base, size_t rows, int box_rows) {
+  namespace kt = sg::ksdtc;
+  kt::EncodeTiledFn encode = kt::encode_tiled_fn();
+  if (!encode) return fail(SGMCMC_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)kt::KC, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)kt::KC * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kt::KC, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(SGMCMC_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)cr));
+  return SGMCMC_OK;
+}
+
+// Tensor-core K2 for the logistic-regression family (csrc/k2_gemm.cuh).
+int fullgrad_tc(sgmcmc_handle* h, const float* thetas, int m, float* out, cudaStream_t s) {
+  namespace k2 = sg::k2;
+  namespace kt = sg::ksdtc;
+  const int d = h->cfg.data_dim, P = h->P, ds = h->DS;
+  const size_t n = (size_t)h->cfg.n_data;
+  const int dp = kt::padded_dim(d), chunks = k2::feat_chunks(d), dn = k2::feat_rows(d);
+  const size_t nic_all = (n + kt::KC - 1) / kt::KC;
+  const int blocks = h->num_sms * 8;
+  if (!h->k2_xs) {
+    CUDA_TRY(cudaMalloc(&h->k2_xs, (size_t)2 * chunks * n * kt::KC * sizeof(float)));
+    k2::split_rows_kernel<<<blocks, 256, 0, s>>>(h->rows, n, ds, d, chunks, h->k2_xs);
+    CUDA_TRY(cudaGetLastError()); ++g_launches;
+  }
+  if (!h->k2_xt) {
+    CUDA_TRY(cudaMalloc(&h->k2_xt, (size_t)2 * nic_all * dn * kt::KC * sizeof(float)));
+    k2::transpose_rows_kernel<<<blocks, 256, 0, s>>>(h->rows, n, ds, d, dn, h->k2_xt);
+    CUDA_TRY(cudaGetLastError()); ++g_launches;
+  }
+  // rows per pass: W (hi + lo) of one pass stays <= 1 GB; a multiple of 128 so that only the last pass is ragged
+  size_t nc_max = ((size_t)1 << 30) / ((size_t)8 * m);
+  nc_max = nc_max < 128 ? 128 : (nc_max & ~(size_t)127);
+  if (nc_max > n) nc_max = (n + 127) & ~(size_t)127;
+  const size_t nic_max = nc_max / kt::KC;
+  const size_t ts_bytes = kt::align_up((size_t)2 * chunks * m * kt::KC * sizeof(float), 256);
+  const size_t g_bytes = kt::align_up((size_t)m * P * sizeof(float), 256);
+  const size_t w_bytes = kt::align_up((size_t)2 * nic_max * m * kt::KC * sizeof(float), 256);
+  if (ts_bytes + g_bytes + w_bytes > h->k2_scratch_bytes) {
+    if (h->k2_scratch) CUDA_TRY(cudaFree(h->k2_scratch));
+    h->k2_scratch = nullptr; h->k2_scratch_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->k2_scratch, ts_bytes + g_bytes + w_bytes));
+    h->k2_scratch_bytes = ts_bytes + g_bytes + w_bytes;
+  }
+  float* Ts = h->k2_scratch;
+  float* G = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->k2_scratch) + ts_bytes);
+  float* W = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h->k2_scratch) + ts_bytes + g_bytes);
+  k2::split_thetas_kernel<<<std::min(blocks, (int)((size_t)m * chunks * kt::KC / 256 + 1)), 256, 0, s>>>(thetas, m, P, d, chunks, Ts);
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
+  CUDA_TRY(cudaMemsetAsync(G, 0, (size_t)m * P * sizeof(float), s));
+
+  CUtensorMap tmap, xmap, xtmap, wmap;
+  int rc;
+  if ((rc = encode_rows16(&tmap, Ts, (size_t)2 * chunks * m, kt::TILE)) != SGMCMC_OK) return rc;
+  if ((rc = encode_rows16(&xmap, h->k2_xs, (size_t)2 * chunks * n, kt::TILE)) != SGMCMC_OK) return rc;
+  if ((rc = encode_rows16(&xtmap, h->k2_xt, (size_t)2 * nic_all * dn, dn)) != SGMCMC_OK) return rc;
+  const size_t smem_b = k2::smem_b(dn);
+  CUDA_TRY(cudaFuncSetAttribute(k2::k2_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2::SMEM_A));
+  CUDA_TRY(cudaFuncSetAttribute(k2::k2_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+  const int MT = (m + kt::TILE - 1) / kt::TILE;
+  for (size_t i0 = 0; i0 < n; i0 += nc_max) {
+    const int nc = (int)std::min(nc_max, n - i0);
+    const int nic = (nc + kt::KC - 1) / kt::KC;
+    const long long tiles = (long long)MT * ((nc + kt::TILE - 1) / kt::TILE);
+    if ((rc = encode_rows16(&wmap, W, (size_t)2 * nic * m, kt::TILE)) != SGMCMC_OK) return rc;
+    k2::k2_scores_kernel<<<(int)std::min<long long>(tiles, h->num_sms), k2::THREADS, k2::SMEM_A, s>>>(tmap, xmap, m, (int)n, chunks, dp,
+                                                                                                    (int)i0, nc, W);
+    CUDA_TRY(cudaGetLastError()); ++g_launches;
+    int ksplit = std::max(1, std::min(nic, 2 * h->num_sms / MT));
+    k2::k2_accum_kernel<<<MT * ksplit, k2::THREADS, smem_b, s>>>(wmap, xtmap, m, P, d, dn, nic, (int)nic_all, (int)(i0 / kt::KC), ksplit, G);
+    CUDA_TRY(cudaGetLastError()); ++g_launches;
+  }
+  k2::finish_kernel<<<std::min(blocks, (int)((size_t)m * P / 256 + 1)), 256, 0, s>>>(G, thetas, m, P, h->vm.prior2[0], out);
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
+  return SGMCMC_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -352,6 +437,9 @@ int sgmcmc_destroy(sgmcmc_handle* h) {
   if (h->cv_grad) cudaFree(h->cv_grad);
   if (h->partial) cudaFree(h->partial);
   if (h->noise) cudaFree(h->noise);
+  if (h->k2_xs) cudaFree(h->k2_xs);
+  if (h->k2_xt) cudaFree(h->k2_xt);
+  if (h->k2_scratch) cudaFree(h->k2_scratch);
   delete h;
   return SGMCMC_OK;
 }
@@ -389,6 +477,8 @@ int sgmcmc_set_data(sgmcmc_handle* h, const void* xv, const void* y, void* strea
   CUDA_TRY(cudaGetLastError()); ++g_launches;
   h->vm.rows = h->rows;
   h->has_data = true;
+  if (h->k2_xs) { cudaFree(h->k2_xs); h->k2_xs = nullptr; }      // operand copies of the previous table
+  if (h->k2_xt) { cudaFree(h->k2_xt); h->k2_xt = nullptr; }
   return SGMCMC_OK;
 }
 
@@ -402,6 +492,9 @@ int sgmcmc_fullbatch_grad(sgmcmc_handle* h, const float* thetas, int32_t m, floa
     return dispatch_big(h, run, m, s);
   }
   if (h->cfg.family == SGMCMC_FAMILY_GAUSSIAN_MEAN) return fullgrad_impl<SGMCMC_FAMILY_GAUSSIAN_MEAN>(h, thetas, m, out, s);
+  // many parameter vectors: two tensor-core contractions instead of m passes over the table (SGMCMC_K2_TC=0/1 overrides)
+  const int tc = env_int("SGMCMC_K2_TC", -1);
+  if ((tc == 1 || (tc < 0 && m >= 64)) && h->cfg.data_dim <= sg::k2::DN_MAX) return fullgrad_tc(h, thetas, m, out, s);
   return fullgrad_impl<SGMCMC_FAMILY_LOGREG>(h, thetas, m, out, s);
 }
 

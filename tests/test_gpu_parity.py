@@ -423,6 +423,31 @@ def test_fullbatch_grad_matches_oracle_and_reference_test(cuda):
             close(got[m], ref, rtol=2e-5, what="fullbatch grad")
 
 
+@pytest.mark.parametrize("n,d,m", [(3000, 100, 130), (777, 10, 64), (5000, 37, 300), (128, 100, 128), (20000, 100, 1000)])
+def test_fullbatch_grad_tensor_core_path(cuda, n, d, m):
+    """K2 at many parameter vectors (csrc/k2_gemm.cuh: two tcgen05 3xTF32 contractions, the imq_KSD `grads` producer)
+    against the oracle's grad_log_post and against the row-streaming SIMT path, ragged shapes included."""
+    import torch
+
+    from sgmcmcjax_b200 import kernels as NK
+
+    fam, fns, data, th0 = logreg_case(n=n, d=d, seed=n + d)
+    init_fn, _, _ = NK.build_sgld_kernel(1e-5, fns[0], fns[1], data, 10)
+    eng = init_fn.engine
+    rng = np.random.default_rng(m)
+    thetas = (th0[0][None, :] + 0.05 * rng.normal(size=(m, d))).astype(np.float32)
+    got = eng.fullbatch_grad(torch.from_numpy(thetas).cuda()).cpu().numpy()        # m >= 64 -> tensor cores
+    os.environ["SGMCMC_K2_TC"] = "0"
+    try:
+        simt = eng.fullbatch_grad(torch.from_numpy(thetas[:5].copy()).cuda()).cpu().numpy()
+    finally:
+        del os.environ["SGMCMC_K2_TC"]
+    for j in (0, 1, 4, m // 2, m - 1):
+        ref = fam.grad_log_post([thetas[j]], data, n, np.float64)[0]
+        close(got[j], ref, rtol=2e-5, what=f"K2 tensor-core row {j}")
+    close(got[:5], simt, rtol=2e-5, what="K2 tensor-core vs SIMT")
+
+
 def test_error_behaviour_matches_reference(cuda):
     from sgmcmcjax_b200 import samplers as NS
     from sgmcmcjax_b200.models import gaussian_mean as G
