@@ -245,7 +245,21 @@ def extra_workloads(args, torch, lib, hbm_peak, X, y, theta_true):
     s = samplers.build_sgldCV_sampler(1e-4, L.loglikelihood, L.logprior, (X, y), BATCH, th, pbar=False)
     ms, nl = _time_engine(torch, s.engine, lib, keys, th0, 10, 5, 3)
     report("C2 logreg SGLD-CV batch=10000", ms, C, 10, 1, algorithmic_bytes_per_chain_step(BATCH) + 8 * DIM, nl)
-    del s
+    # ---- C5 front half: the `grads` argument of imq_KSD = full-batch grad_log_post at the sample points (K2 on tensor cores)
+    Mk = args.ksd_n
+    pts = (theta_true[None, :] + 0.01 * random.normal(random.PRNGKey(7), (Mk, DIM))).contiguous()
+    s.engine.fullbatch_grad(pts)                                                     # operand prep (once per table), scratch, warm-up
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.sgmcmc_launch_count()
+    a.record(); gk = s.engine.fullbatch_grad(pts); b.record(); torch.cuda.synchronize()
+    msk = a.elapsed_time(b)
+    assert torch.isfinite(gk).all()
+    out.append({"config": f"C5 grads: full-batch grad_log_post at {Mk} sample points, logreg N={N_DATA} D={DIM} (tcgen05 3xTF32)",
+                "value": Mk * float(N_DATA) / (msk * 1e-3), "unit": "(theta,row) pairs/s", "ms": msk,
+                "algorithmic_tflops": 4.0 * Mk * N_DATA * DIM / (msk * 1e-3) / 1e12,
+                "gpu_launches": int(lib.sgmcmc_launch_count() - l0)})
+    del s, pts, gk
     # ---- C1 README Gaussian: one chain, latency-bound (4 MB table lives in L2)
     Xg = random.normal(random.PRNGKey(0), (10000, 100))
     s = samplers.build_sgld_sampler(1e-5, G.loglikelihood, G.logprior, (Xg,), 1000, pbar=False)

@@ -131,7 +131,9 @@ int sgmcmc_set_data(sgmcmc_handle* h, const void* x, const void* y, void* stream
 int sgmcmc_set_centering(sgmcmc_handle* h, const float* theta_hat, void* stream);
 
 /* Full-batch grad_log_post (util.py:43-49 with all rows) at M parameter vectors:
- * thetas device f32 [M, P] -> out device f32 [M, P]. */
+ * thetas device f32 [M, P] -> out device f32 [M, P].  This is also the `grads` producer of imq_KSD (ksd.py:43).
+ * Logistic regression with m >= 64 runs as two tcgen05 contractions (operand copies of the table are built on the
+ * first such call and owned by the handle); otherwise one streaming pass over the rows per parameter vector. */
 int sgmcmc_fullbatch_grad(sgmcmc_handle* h, const float* thetas, int32_t m, float* out, void* stream);
 
 /* init_fn(key, params) of kernels.py:48-51 for every chain: state->theta must hold params.
