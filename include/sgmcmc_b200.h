@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SGMCMC_ABI_VERSION 2
+#define SGMCMC_ABI_VERSION 3
 
 enum { SGMCMC_OK = 0, SGMCMC_E_INVALID = -1, SGMCMC_E_UNSUPPORTED = -2, SGMCMC_E_CUDA = -3,
        SGMCMC_E_STATE = -4 };
@@ -155,6 +155,28 @@ int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k,
  * (device u32 [C, 2]); state->key is not touched. */
 int sgmcmc_kernel_step(sgmcmc_handle* h, sgmcmc_state* st, int32_t i, const uint32_t* keys,
                        const sgmcmc_step_coef* coef, void* stream);
+
+/* ---- optional data-sharded mode (vector families, standard / CV estimators, no SGHMC) ----------
+ * The ROWS of the table are split over ranks (for tables that do not fit one GPU); every rank runs every chain with the
+ * same keys, draws the same minibatch indices (gradient_estimation.py:32 over ALL n_data rows), processes the ones it
+ * holds, and the host all-reduces the [C, DS] minibatch sums once per step (DS = data_dim rounded up to 4).
+ *   sgmcmc_create(cfg with n_data = TOTAL rows); sgmcmc_set_row_shard(h, row0, n_rows); sgmcmc_set_data(h, x, y) with
+ *   n_rows rows; [CV: all-reduce sgmcmc_fullbatch_grad, then sgmcmc_set_centering_grad];
+ *   sgmcmc_shard_init -> all-reduce sum -> { sgmcmc_shard_step(flags = STEP [| UPDATE2]) -> all-reduce sum } x K
+ *   -> sgmcmc_shard_step(flags = [UPDATE2]) to finish the last gradient. */
+#define SGMCMC_SHARD_UPDATE2 1   /* run the palindrome's update2 (baoab / badodab, coef_prev) after finishing the gradient */
+#define SGMCMC_SHARD_STEP 2      /* then do one transition (samplers.py:47-51) up to this rank's partial sums */
+int sgmcmc_set_row_shard(sgmcmc_handle* h, int64_t row0, int64_t n_rows);
+/* CV centre with an externally reduced full-batch gradient (gradient_estimation.py:70): device f32 [P] each. */
+int sgmcmc_set_centering_grad(sgmcmc_handle* h, const float* theta_hat, const float* grad, void* stream);
+/* init_fn (kernels.py:48-51) up to this rank's partial minibatch sums: sum_out device f32 [C, DS]. */
+int sgmcmc_shard_init(sgmcmc_handle* h, sgmcmc_state* st, const uint32_t* keys, int32_t sampler_mode, float* sum_out,
+                      void* stream);
+/* Finish the gradient of the previous estimate from the all-reduced sums sum_in [C, DS]; then, per `flags`, update2 and
+ * one transition i whose sample goes to sample_out [C, P] (may be NULL) and whose partial sums go to sum_out. */
+int sgmcmc_shard_step(sgmcmc_handle* h, sgmcmc_state* st, int32_t i, const sgmcmc_step_coef* coef,
+                      const sgmcmc_step_coef* coef_prev, int32_t flags, const float* sum_in, float* sum_out, float* sample_out,
+                      void* stream);
 
 /* random.choice(key, arange(n), (batch,)) (gradient_estimation.py:32): key is a HOST
  * pointer to 2 words, out a device int32 [batch].  Test hook for bit-exactness. */

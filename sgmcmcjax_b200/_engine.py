@@ -63,7 +63,9 @@ class Engine:
 
     def __init__(self, diffusion: str, dt, loglikelihood: Callable, logprior: Callable, data, batch_size: int,
                  estimator: str = "standard", centering_value=None, update_rate: Optional[int] = None,
-                 leapfrog: int = 0, hyper: Optional[dict] = None, flags: int = 0):
+                 leapfrog: int = 0, hyper: Optional[dict] = None, flags: int = 0, row_shard=None, group=None):
+        """row_shard = (row0, n_total): `data` holds only rows [row0, row0 + len) of a table of n_total rows that is
+        split over the ranks of `group` (optional data-sharded mode, include/sgmcmc_b200.h)."""
         torch = _native.require_cuda()
         self.lib = _native.load()
         if type(data) != tuple:                                   # gradient_estimation.py:25
@@ -83,9 +85,13 @@ class Engine:
         x = self._data[0]
         if x.dim() != 2:
             raise ValueError("data[0] must be [N, D]")
-        self.n_data, self.data_dim = int(x.shape[0]), int(x.shape[1])
-        if len(self._data) == 2 and self._data[1].shape[0] != self.n_data:
+        self.n_local, self.data_dim = int(x.shape[0]), int(x.shape[1])
+        if len(self._data) == 2 and self._data[1].shape[0] != self.n_local:
             raise ValueError("data arrays must share their leading dimension")
+        self.row_shard, self.group = row_shard, group
+        self.n_data = int(row_shard[1]) if row_shard is not None else self.n_local
+        if row_shard is not None and not self.spec.vector:
+            raise NotImplementedError("the data-sharded mode covers the vector families (gaussian_mean, logistic_regression)")
         self.batch = self.n_data if batch_size is None else int(batch_size)
         self._handle = C.c_void_p(0)
         self._coef_cache = {}
@@ -127,6 +133,8 @@ class Engine:
         for k, name in enumerate(order):
             cfg.hyper[k] = float(self.hp[name])
         _native.check(self.lib.sgmcmc_create(C.byref(cfg), C.byref(self._handle)))
+        if self.row_shard is not None:
+            _native.check(self.lib.sgmcmc_set_row_shard(self._handle, int(self.row_shard[0]), self.n_local))
         y = self._data[1] if len(self._data) == 2 else None
         _native.check(self.lib.sgmcmc_set_data(self._handle, _vp(self._data[0]), _vp(y), self._stream()))
         if self.spec.vector:
@@ -135,7 +143,15 @@ class Engine:
             center = self.flatten_params(self._centering_value, broadcast_chains=None)[0]
             if center.shape[0] != 1:
                 raise ValueError("centering_value must be a single parameter pytree")
-            _native.check(self.lib.sgmcmc_set_centering(self._handle, _vp(center), self._stream()))
+            if self.row_shard is None:
+                _native.check(self.lib.sgmcmc_set_centering(self._handle, _vp(center), self._stream()))
+            else:       # gradient_estimation.py:70 over ALL rows: local rows here, one all-reduce across the ranks
+                from . import parallel
+
+                g = self.fullbatch_grad(center)
+                if self.group is not False:
+                    g = parallel.sharded_fullbatch_grad(g, parallel.prior_grad(self.spec, self.leaf_size, center), self.group)
+                _native.check(self.lib.sgmcmc_set_centering_grad(self._handle, _vp(center), _vp(g), self._stream()))
 
     def __del__(self):
         try:
@@ -242,6 +258,35 @@ class Engine:
         _native.check(self.lib.sgmcmc_kernel_step(self._handle, C.byref(cs), int(i), _vp(keys), _vp(coef),
                                                   self._stream()))
         return coef
+
+    # ---- data-sharded mode --------------------------------------------------------------------
+    @property
+    def sum_width(self) -> int:
+        return (self.data_dim + 3) & ~3
+
+    def shard_init(self, st, keys, sampler_mode: bool):
+        """init_fn up to this shard's partial minibatch sums -> CUDA f32 [C, DS]."""
+        torch = _native.require_cuda()
+        part = torch.empty((st["theta"].shape[0], self.sum_width), dtype=torch.float32, device="cuda")
+        cs = self._cstate(st)
+        _native.check(self.lib.sgmcmc_shard_init(self._handle, C.byref(cs), _vp(keys), 1 if sampler_mode else 0, _vp(part),
+                                                 self._stream()))
+        return part
+
+    def shard_step(self, st, i: int, flags: int, sum_in, sample_out=None):
+        """Finish the previous gradient from the complete sums `sum_in`; per flags run update2 / one transition.
+        Returns this shard's partial sums of the new estimate (None without SHARD_STEP)."""
+        torch = _native.require_cuda()
+        coef, _ = self._coefs(i, 1)
+        coef_prev, _ = self._coefs(max(i - 1, 0), 1)
+        part = None
+        if flags & _native.SHARD_STEP:
+            part = torch.empty((st["theta"].shape[0], self.sum_width), dtype=torch.float32, device="cuda")
+        cs = self._cstate(st)
+        _native.check(self.lib.sgmcmc_shard_step(self._handle, C.byref(cs), int(i), _vp(coef), _vp(coef_prev), int(flags),
+                                                 _vp(sum_in), _vp(part), _vp(sample_out), self._stream()))
+        self._keep = (coef, coef_prev)
+        return part
 
     def fullbatch_grad(self, thetas):
         torch = _native.require_cuda()

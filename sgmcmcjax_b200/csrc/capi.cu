@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(1024 / NCH) fullgrad_partial_kernel(const VecM
   for (int e = threadIdx.x; e < m.DS; e += blockDim.x) s_theta[e] = e < m.P ? thetas[(size_t)mi * m.P + e] : 0.f;
   __syncthreads();
   const unsigned lo = split * rows_per_split;
-  const unsigned hi = min(m.n_data, lo + rows_per_split);
+  const unsigned hi = min(m.own_n, lo + rows_per_split);
   RandintPlan dummy{};
   row_pass<FAMILY, false, NCH>(m, true, dummy, lo, hi > lo ? hi - lo : 0u, s_theta, s_theta, s_part);
   __syncthreads();
@@ -114,7 +114,7 @@ __global__ void fullgrad_finish_kernel(const VecModel m, const float* __restrict
     const int leaf = e / m.leaf_dim, d = e - leaf * m.leaf_dim;
     float S = 0.f;
     for (int sp = 0; sp < splits; ++sp) S += partial[((size_t)mi * splits + sp) * m.DS + d];
-    out[(size_t)mi * m.P + e] = grad_from_sum<FAMILY>(m, leaf, d, S, thetas[(size_t)mi * m.P + e], 1.0f, (float)m.n_data);
+    out[(size_t)mi * m.P + e] = grad_from_sum<FAMILY>(m, leaf, d, S, thetas[(size_t)mi * m.P + e], 1.0f, (float)m.own_n);
   }
 }
 
@@ -227,10 +227,10 @@ int fullgrad_impl(sgmcmc_handle* h, const float* thetas, int m, float* out, cuda
   const int warps = 8 / (h->nch > 2 ? 2 : 1);
   int splits = (h->num_sms * 4 + m - 1) / m;
   const unsigned min_rows = 512;
-  const unsigned max_splits = (h->vm.n_data + min_rows - 1) / min_rows;
+  const unsigned max_splits = (h->vm.own_n + min_rows - 1) / min_rows;
   if ((unsigned)splits > max_splits) splits = (int)max_splits;
   if (splits < 1) splits = 1;
-  const unsigned rows_per_split = (h->vm.n_data + splits - 1) / splits;
+  const unsigned rows_per_split = (h->vm.own_n + splits - 1) / splits;
   const size_t need = (size_t)m * splits * h->DS;
   if (need > h->partial_elems) {
     if (h->partial) CUDA_TRY(cudaFree(h->partial));
@@ -416,6 +416,7 @@ int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
   vm.family = cfg->family; vm.estimator = cfg->estimator; vm.diffusion = cfg->diffusion; vm.flags = cfg->flags;
   vm.n_leaves = cfg->n_leaves; vm.leaf_dim = cfg->data_dim; vm.P = h->P; vm.DS = h->DS;
   vm.n_data = (unsigned)cfg->n_data; vm.batch = (unsigned)cfg->batch;
+  vm.own_lo = 0u; vm.own_n = vm.n_data;
   vm.full_batch = (cfg->estimator == SGMCMC_EST_STANDARD && (int64_t)cfg->batch == cfg->n_data) ? 1 : 0;
   vm.leapfrog = cfg->leapfrog; vm.update_rate = cfg->update_rate;
   vm.scale = (float)cfg->n_data / (float)cfg->batch;
@@ -470,10 +471,11 @@ int sgmcmc_set_data(sgmcmc_handle* h, const void* xv, const void* y, void* strea
     return SGMCMC_OK;
   }
   const float* x = (const float*)xv;
-  if (!h->rows) CUDA_TRY(cudaMalloc(&h->rows, n * h->DS * sizeof(float)));
-  const size_t total = n * h->DS;
+  const size_t nrows = (size_t)h->vm.own_n;                      // == n unless sgmcmc_set_row_shard was called
+  if (!h->rows) CUDA_TRY(cudaMalloc(&h->rows, nrows * h->DS * sizeof(float)));
+  const size_t total = nrows * h->DS;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 16);
-  sg::pack_rows_kernel<<<blocks, 256, 0, s>>>(x, (const int*)y, h->rows, n, h->cfg.data_dim, h->DS, h->cfg.family);
+  sg::pack_rows_kernel<<<blocks, 256, 0, s>>>(x, (const int*)y, h->rows, nrows, h->cfg.data_dim, h->DS, h->cfg.family);
   CUDA_TRY(cudaGetLastError()); ++g_launches;
   h->vm.rows = h->rows;
   h->has_data = true;
@@ -494,7 +496,8 @@ int sgmcmc_fullbatch_grad(sgmcmc_handle* h, const float* thetas, int32_t m, floa
   if (h->cfg.family == SGMCMC_FAMILY_GAUSSIAN_MEAN) return fullgrad_impl<SGMCMC_FAMILY_GAUSSIAN_MEAN>(h, thetas, m, out, s);
   // many parameter vectors: two tensor-core contractions instead of m passes over the table (SGMCMC_K2_TC=0/1 overrides)
   const int tc = env_int("SGMCMC_K2_TC", -1);
-  if ((tc == 1 || (tc < 0 && m >= 64)) && h->cfg.data_dim <= sg::k2::DN_MAX) return fullgrad_tc(h, thetas, m, out, s);
+  if ((tc == 1 || (tc < 0 && m >= 64)) && h->cfg.data_dim <= sg::k2::DN_MAX && h->vm.own_n == h->vm.n_data)
+    return fullgrad_tc(h, thetas, m, out, s);
   return fullgrad_impl<SGMCMC_FAMILY_LOGREG>(h, thetas, m, out, s);
 }
 
@@ -572,6 +575,58 @@ int sgmcmc_kernel_step(sgmcmc_handle* h, sgmcmc_state* st, int32_t i, const uint
   }
   sg::VecRun run{};
   run.st = *st; run.i0 = i; run.K = 1; run.coef = coef; run.coef_stride = 0; run.step_keys = keys;
+  return dispatch_vec(h, run, (cudaStream_t)stream);
+}
+
+int sgmcmc_set_row_shard(sgmcmc_handle* h, int64_t row0, int64_t n_rows) {
+  if (!h) return fail(SGMCMC_E_INVALID, "null handle");
+  if (h->big) return fail(SGMCMC_E_UNSUPPORTED, "the data-sharded mode covers the vector families (gaussian_mean, logreg)");
+  if (h->has_data) return fail(SGMCMC_E_STATE, "sgmcmc_set_row_shard must precede sgmcmc_set_data");
+  if (row0 < 0 || n_rows < 1 || row0 + n_rows > h->cfg.n_data) return fail(SGMCMC_E_INVALID, "row shard out of range");
+  if (h->cfg.estimator == SGMCMC_EST_SVRG || h->cfg.diffusion == SGMCMC_DIFF_SGHMC || h->vm.full_batch)
+    return fail(SGMCMC_E_UNSUPPORTED, "data-sharded mode: SVRG, SGHMC and the full-batch bypass are not supported");
+  h->vm.own_lo = (unsigned)row0; h->vm.own_n = (unsigned)n_rows;
+  return SGMCMC_OK;
+}
+
+int sgmcmc_set_centering_grad(sgmcmc_handle* h, const float* theta_hat, const float* grad, void* stream) {
+  if (!h || !theta_hat || !grad) return fail(SGMCMC_E_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->cv_center) CUDA_TRY(cudaMalloc(&h->cv_center, h->P * sizeof(float)));
+  if (!h->cv_grad) CUDA_TRY(cudaMalloc(&h->cv_grad, h->P * sizeof(float)));
+  CUDA_TRY(cudaMemcpyAsync(h->cv_center, theta_hat, h->P * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->cv_grad, grad, h->P * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  h->vm.cv_center = h->cv_center; h->vm.cv_grad = h->cv_grad;
+  h->bm.cv_center = h->cv_center; h->bm.cv_grad = h->cv_grad;
+  h->has_center = true;
+  return SGMCMC_OK;
+}
+
+int sgmcmc_shard_init(sgmcmc_handle* h, sgmcmc_state* st, const uint32_t* keys, int32_t sampler_mode, float* sum_out,
+                      void* stream) {
+  int rc = check_state(h, st);
+  if (rc != SGMCMC_OK) return rc;
+  if (h->big) return fail(SGMCMC_E_UNSUPPORTED, "data-sharded mode covers the vector families");
+  if (!keys || !sum_out) return fail(SGMCMC_E_INVALID, "keys and sum_out must not be null");
+  if (sampler_mode && !st->key) return fail(SGMCMC_E_INVALID, "state.key is required in sampler mode");
+  sg::VecRun run{};
+  run.st = *st; run.mode = sampler_mode ? 2 : 1; run.init_keys = keys; run.sum_out = sum_out;
+  return dispatch_vec(h, run, (cudaStream_t)stream);
+}
+
+int sgmcmc_shard_step(sgmcmc_handle* h, sgmcmc_state* st, int32_t i, const sgmcmc_step_coef* coef,
+                      const sgmcmc_step_coef* coef_prev, int32_t flags, const float* sum_in, float* sum_out, float* sample_out,
+                      void* stream) {
+  int rc = check_state(h, st);
+  if (rc != SGMCMC_OK) return rc;
+  if (h->big) return fail(SGMCMC_E_UNSUPPORTED, "data-sharded mode covers the vector families");
+  if (!sum_in || i < 0 || !st->key) return fail(SGMCMC_E_INVALID, "bad argument");
+  if ((flags & sg::SHARD_STEP) && (!coef || !sum_out)) return fail(SGMCMC_E_INVALID, "a step needs coef and sum_out");
+  if ((flags & sg::SHARD_UPDATE2) && !coef_prev) return fail(SGMCMC_E_INVALID, "update2 needs coef_prev");
+  sg::VecRun run{};
+  run.st = *st; run.i0 = i; run.K = 1; run.coef = coef; run.coef_stride = 0; run.coef_prev = coef_prev;
+  run.shard_flags = flags; run.sum_in = sum_in; run.sum_out = (flags & sg::SHARD_STEP) ? sum_out : nullptr;
+  run.samples = sample_out; run.sample_chain_stride = (size_t)h->P;
   return dispatch_vec(h, run, (cudaStream_t)stream);
 }
 

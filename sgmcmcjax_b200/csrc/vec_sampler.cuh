@@ -33,7 +33,8 @@ struct VecModel {
   float lik2[MAXL];        // gaussian_mean: 2 a_l
   float prior2[MAXL];      // gaussian_mean: 2 c_l ; logreg: [0] = prior precision
   float hyper[4];
-  const float* rows;       // [n_data][DS]
+  const float* rows;       // [own_n][DS]: rows own_lo .. own_lo + own_n - 1 of the table (data-sharded mode: a slice)
+  unsigned own_lo, own_n;  // own_lo = 0, own_n = n_data unless the rows are sharded over ranks
   const float* cv_center;  // [P]  (CV only)
   const float* cv_grad;    // [P]  full-batch gradient at cv_center
 };
@@ -48,7 +49,13 @@ struct VecRun {
   const uint32_t* step_keys; // [C][2]: kernel(i, key, state) mode (K == 1), else nullptr
   int mode;                  // 0 = run, 1 = init_fn with keys as given, 2 = init with sampler split
   const uint32_t* init_keys; // [C][2] for mode 1/2
+  // data-sharded mode (rows split over ranks, one all-reduce of the [C, DS] minibatch sums per step, done by the host):
+  const float* sum_in;       // [C][DS] all-reduced sums of the previous estimate: the gradient is finished from them first
+  float* sum_out;            // [C][DS] this rank's partial sums of the new estimate (the gradient is NOT finished)
+  int shard_flags;           // SHARD_UPDATE2: run the palindrome's update2 (coef_prev) after finishing the gradient;
+  const sgmcmc_step_coef* coef_prev;   //   SHARD_STEP: then do one transition and leave its partial sums in sum_out
 };
+constexpr int SHARD_UPDATE2 = 1, SHARD_STEP = 2;
 
 // ---------------------------------------------------------------------------------------
 // shared-memory carve-up (dynamic): all arrays padded to DSP = max(P, DS) rounded to 4
@@ -133,6 +140,7 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const unsigned h = (count + 1u) >> 1;
   const int DS = m.DS;
+  const bool sharded = m.own_n != m.n_data;
   const float4* __restrict__ rows = reinterpret_cast<const float4*>(m.rows);
   const int row_f4 = DS >> 2;
 
@@ -161,14 +169,33 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
       if (sequential) { iA = seq_base + b; iB = seq_base + b + h; } else { randint_block(plan, b, iA, iB); }
       jA = (int)iA;
       if (b + h < count) jB = (int)iB;
+      if (sharded && !sequential) {                      // keep only the rows this rank holds, as local row numbers
+        jA = (iA - m.own_lo < m.own_n) ? (int)(iA - m.own_lo) : -1;
+        if (jB >= 0) jB = (iB - m.own_lo < m.own_n) ? (int)(iB - m.own_lo) : -1;
+      }
     }
+    // sharded: owned rows are scattered over the lanes - compact them so that every group of 8 is full
+    const unsigned maskA = sharded ? __ballot_sync(FULL, jA >= 0) : 0u, maskB = sharded ? __ballot_sync(FULL, jB >= 0) : 0u;
+    const int cntA = __popc(maskA), cntB = __popc(maskB);
 #pragma unroll 1
     for (int grp = 0; grp < 8; ++grp) {
       const int src = (grp < 4) ? jA : jB;
       const int base = (grp & 3) * 8;
       int r[8];
+      if (sharded) {
+        const unsigned mask = (grp < 4) ? maskA : maskB;
+        const int cnt = (grp < 4) ? cntA : cntB;
+        if (base >= cnt) continue;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) r[u] = __shfl_sync(FULL, src, base + u);
+        for (int u = 0; u < 8; ++u) {
+          const int from = __fns(mask, 0, base + u + 1);       // lane of the (base + u)-th owned row, or -1
+          const int v = __shfl_sync(FULL, src, from & 31);
+          r[u] = base + u < cnt ? v : -1;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u] = __shfl_sync(FULL, src, base + u);
+      }
       // validity is monotone in the stream position, so an invalid first row ends the group
       if (r[0] < 0) continue;
       float4 x[8][NCH];
@@ -265,9 +292,9 @@ struct ChainCtx {
   // full-batch gradient at s.theta into dst[] (sequential pass over every row)
   __device__ void full_grad(float* dst) {
     RandintPlan dummy{};
-    row_pass<FAMILY, false, NCH>(m, true, dummy, 0u, m.n_data, s.theta, s.center, s.part);
+    row_pass<FAMILY, false, NCH>(m, true, dummy, 0u, m.own_n, s.theta, s.center, s.part);
     fold_parts(s, m.DS);
-    const float rows = (float)m.n_data;
+    const float rows = (float)m.own_n;
     for (int e = threadIdx.x; e < m.P; e += blockDim.x) {
       const int leaf = e / m.leaf_dim, d = e - leaf * m.leaf_dim;
       dst[e] = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.theta[e], 1.0f, rows);
@@ -293,9 +320,19 @@ struct ChainCtx {
       full_grad(s.grad);                               // gradient_estimation.py:41-42
       return;
     }
+    partial_sums(k2);
+    finish_from_sums();
+  }
+
+  // minibatch sums over the rows of this rank: s.S[d] = sum_i x_i (gaussian) / sum_i (w_i [- w_c,i]) x~_i (logreg)
+  __device__ void partial_sums(Key k2) {
     const RandintPlan plan = randint_plan(k2, m.n_data, m.batch);
     row_pass<FAMILY, CV, NCH>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part);
     fold_parts(s, m.DS);
+  }
+
+  // s.grad from the (complete) minibatch sums in s.S, evaluated at s.theta
+  __device__ void finish_from_sums() {
     const float rows = (float)m.batch;
     for (int e = threadIdx.x; e < m.P; e += blockDim.x) {
       const int leaf = e / m.leaf_dim, d = e - leaf * m.leaf_dim;
@@ -501,11 +538,32 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
   ChainCtx<FAMILY, CV, NCH> ctx(m, s);
   Key carry{0u, 0u};
 
+  if (run.sum_in) {                                   // finish the previous estimate from the all-reduced sums
+    for (int d = threadIdx.x; d < m.DS; d += blockDim.x) s.S[d] = run.sum_in[(size_t)c * m.DS + d];
+    __syncthreads();
+    ctx.finish_from_sums();
+    if (run.shard_flags & SHARD_UPDATE2) ctx.diffuse(2, run.i0, *run.coef_prev, 4);
+  }
   if (run.mode != 0) {
     // init_fn (kernels.py:48-51), optionally preceded by samplers.py:53
     Key k; k.a = run.init_keys[2 * c]; k.b = run.init_keys[2 * c + 1];
     if (run.mode == 2) { Key sub; split2(k, carry, sub); k = sub; }
-    ctx.estimate(0, k, true);
+    if (run.sum_out) ctx.partial_sums(k); else ctx.estimate(0, k, true);
+  } else if (run.sum_out || run.sum_in) {
+    // data-sharded step: one transition whose estimate stops at this rank's partial sums
+    carry.a = st.key[2 * c]; carry.b = st.key[2 * c + 1];
+    if (run.shard_flags & SHARD_STEP) {
+      const sgmcmc_step_coef cf = run.coef[0];
+      Key nk, sub; split2(carry, nk, sub); carry = nk;           // samplers.py:49
+      ctx.expand_step_keys(sub);
+      Key k2; k2.a = s.keys[2]; k2.b = s.keys[3];
+      ctx.diffuse(1, run.i0, cf, 4);
+      if (run.samples) {
+        float* dst = run.samples + (size_t)c * run.sample_chain_stride;
+        for (int e = threadIdx.x; e < P; e += blockDim.x) dst[e] = s.theta[e];
+      }
+      ctx.partial_sums(k2);
+    }
   } else {
     if (run.step_keys == nullptr) { carry.a = st.key[2 * c]; carry.b = st.key[2 * c + 1]; }
     for (int sidx = 0; sidx < run.K; ++sidx) {
@@ -535,6 +593,8 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
   if (threadIdx.x == 0 && st.key && (run.mode == 2 || (run.mode == 0 && run.step_keys == nullptr))) {
     st.key[2 * c] = carry.a; st.key[2 * c + 1] = carry.b;
   }
+  if (run.sum_out)
+    for (int d = threadIdx.x; d < m.DS; d += blockDim.x) run.sum_out[(size_t)c * m.DS + d] = s.S[d];
 }
 
 }  // namespace sg

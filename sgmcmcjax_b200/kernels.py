@@ -41,7 +41,12 @@ def _like(t, like):
     return t
 
 
+_row_shard = None      # set by parallel.build_data_sharded_sampler while it calls a build_*_kernel factory
+
+
 def _build(diffusion, dt, loglikelihood, logprior, data, batch_size, **kw) -> Tuple[Callable, Callable, Callable]:
+    if _row_shard is not None:
+        kw.update(row_shard=_row_shard[0], group=_row_shard[1])
     eng = Engine(diffusion, dt, loglikelihood, logprior, data, batch_size, **kw)
 
     def _wrap(st, treedef, batched, like) -> SamplerState:

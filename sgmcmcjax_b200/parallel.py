@@ -3,6 +3,9 @@
 * Sampling: chains are independent units.  Chain c of the job always uses ``split(key, C_total)[c]``, rank r
   owns the contiguous block ``chain_shard(C_total, r, world)``; data is replicated per GPU and there is NO
   collective inside the sampling loop.  ``gather_chains`` is the optional all-gather of the samples at the end.
+* Optional data-sharded mode (tables that do not fit one GPU): the ROWS are split over ranks, every rank runs every
+  chain with the same keys and processes the minibatch rows it holds; one all-reduce of the [C, D] minibatch sums
+  per step (``build_data_sharded_sampler``).
 * KSD: the symmetric Gram tile list is dealt round-robin to ranks (``ksd_tile_partition`` mirrors
   csrc/ksd_tc.cuh), each rank produces one fp64 partial, ONE all-reduce of a double (``allreduce_scalar``).
 
@@ -94,3 +97,78 @@ def sharded_fullbatch_grad(local_grad, prior, group=None):
     total = local_grad.clone()
     dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     return total - (world - 1) * prior
+
+
+def build_data_sharded_sampler(build_kernel_fn, *args, shards, n_total, group=None, distributed=None, **kwargs):
+    """Sampler for a table whose ROWS are split into shards (north_star "optional data-sharded mode").
+
+    ``build_kernel_fn(*args, **kwargs)`` is one of the ``kernels.build_*_kernel`` factories (vector families; standard or
+    CV estimator; not SGHMC) whose ``data`` argument is replaced, shard by shard, with the entries of
+    ``shards = [(row_offset, data_tuple), ...]`` - normally ONE entry: this rank's rows.  With ``torch.distributed``
+    initialised (``distributed`` defaults to that) the [C, D] minibatch sums are all-reduced across ranks once per step
+    (NCCL over NVLink); several local shards are summed on the device first.  The chains are identical on every rank
+    and equal, up to fp32 summation order, to the unsharded sampler with the same keys."""
+    import torch
+
+    from . import _native, _tree, kernels
+    from ._engine import keys_to_device
+
+    if distributed is None:
+        import torch.distributed as dist
+        distributed = dist.is_available() and dist.is_initialized()
+    args = list(args)
+    data_pos = next(k for k, a in enumerate(args) if type(a) is tuple)      # the `data` tuple of the reference signature
+    engines = []
+    for row0, data in shards:
+        a = list(args)
+        a[data_pos] = data
+        kernels._row_shard = ((int(row0), int(n_total)), group if distributed else False)
+        try:
+            init_fn, _, _ = build_kernel_fn(*a, **kwargs)
+        finally:
+            kernels._row_shard = None
+        engines.append(init_fn.engine)
+    if len(engines) > 1 and engines[0].estimator == "cv" and not distributed:
+        # several local shards and no process group: combine the centre's full-batch gradient here
+        total = sum(e.fullbatch_grad(e.flatten_params(e._centering_value, None)[0]) for e in engines)
+        center = engines[0].flatten_params(engines[0]._centering_value, None)[0]
+        total = total - (len(engines) - 1) * prior_grad(engines[0].spec, engines[0].leaf_size, center)
+        import ctypes as C
+        for e in engines:
+            _native.check(e.lib.sgmcmc_set_centering_grad(e._handle, C.c_void_p(center.data_ptr()), C.c_void_p(total.data_ptr()),
+                                                          e._stream()))
+        torch.cuda.current_stream().synchronize()
+    palindrome = engines[0].diffusion in ("baoab", "badodab")
+
+    def reduce_parts(parts):
+        total = parts[0] if len(parts) == 1 else torch.stack(parts).sum(0)
+        if distributed:
+            import torch.distributed as dist
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        return total
+
+    def sampler(key, Nsamples: int, params):
+        e0 = engines[0]
+        keys, kb = keys_to_device(key)
+        flat, treedef, pb = e0.flatten_params(params, broadcast_chains=keys.shape[0])
+        batched, nsamp, n_chains = kb or pb, int(Nsamples), flat.shape[0]
+        states = [e.new_state(flat) for e in engines]
+        total = reduce_parts([e.shard_init(st, keys, True) for e, st in zip(engines, states)])
+        samples = torch.empty((nsamp, n_chains, e0.P), dtype=torch.float32, device="cuda")
+        for i in range(nsamp):
+            flags = _native.SHARD_STEP | (_native.SHARD_UPDATE2 if (palindrome and i > 0) else 0)
+            parts = [e.shard_step(st, i, flags, total, samples[i] if k == 0 else None)
+                     for k, (e, st) in enumerate(zip(engines, states))]
+            total = reduce_parts(parts)
+        for e, st in zip(engines, states):                                    # finish the last gradient (and update2)
+            e.shard_step(st, nsamp, _native.SHARD_UPDATE2 if (palindrome and nsamp > 0) else 0, total)
+        out = samples.permute(1, 0, 2).contiguous()
+        lead = (n_chains, nsamp) if batched else (nsamp,)
+        tree = e0.unflatten_params(out if batched else out[0], treedef, lead)
+        leaves, td = _tree.flatten(tree)
+        like = _tree.flatten(params)[0][0]
+        sampler.states = states
+        return _tree.unflatten(td, [kernels._like(l, like) for l in leaves])
+
+    sampler.engines = engines
+    return sampler

@@ -448,6 +448,52 @@ def test_fullbatch_grad_tensor_core_path(cuda, n, d, m):
     close(got[:5], simt, rtol=2e-5, what="K2 tensor-core vs SIMT")
 
 
+@pytest.mark.parametrize("name,dt,kw", [KERNELS[0], KERNELS[1], KERNELS[3], KERNELS[5], KERNELS[7], KERNELS[9]],
+                         ids=["sgld", "sgldCV", "psgld", "sgnht", "baoab", "badodabCV"])
+@pytest.mark.parametrize("case", ["gauss2", "logreg"])
+def test_data_sharded_mode_equals_unsharded(cuda, name, dt, kw, case):
+    """Optional data-sharded mode: the rows split into 3 uneven shards (here all on one GPU, their partial sums added on
+    the device - across ranks the same sum is one all-reduce): same chains as the unsharded sampler and the oracle."""
+    from sgmcmcjax_b200 import kernels as NK
+    from sgmcmcjax_b200 import parallel
+
+    if case == "logreg":
+        fam, fns, data, th0 = logreg_case(n=1500, d=10)
+        batch = 200
+    else:
+        fam, fns, data, th0 = gauss_case(True, n=1000)
+        batch = 64
+    center = [np.asarray(t + np.float32(0.01)) for t in th0]
+    n = data[0].shape[0]
+    cuts = [0, n // 5, n // 5 + n // 2, n]
+    shards = [(lo, tuple(a[lo:hi] for a in data)) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    kw = dict(kw)
+    pos = []
+    okw = {}
+    if kw.pop("cv", False):
+        okw["centering_value"] = center
+        pos.append(as_params(center))
+    if "gamma" in kw:
+        okw["gamma"] = kw["gamma"]
+        pos.append(kw.pop("gamma"))
+    builder = getattr(NK, f"build_{name}_kernel")
+    sampler = parallel.build_data_sharded_sampler(builder, dt, fns[0], fns[1], data, batch, *pos, shards=shards, n_total=n,
+                                                  distributed=False)
+    keys = P.split(P.PRNGKey(3), 2)
+    th = [np.stack([t, t + np.float32(0.02)]) for t in th0]
+    got = leaves_of(sampler(keys, 7, as_params(th)))
+    ok = S.build_kernel(name, fam, data, batch, dt, **okw)
+    for c in range(2):
+        ref, _, _ = S.run_sampler(ok, keys[c], 7, [t[c] for t in th])
+        for g, r in zip(got, ref):
+            assert g.shape[:2] == (2, 7)
+            close(g[c], r, rtol=1e-4, what=f"sharded {name}/{case} chain {c}")
+    # the finished gradient in the states of all shards is the complete one
+    g0 = to_np(sampler.states[0]["grad"])
+    for st in sampler.states[1:]:
+        assert np.array_equal(g0, to_np(st["grad"]))
+
+
 def test_error_behaviour_matches_reference(cuda):
     from sgmcmcjax_b200 import samplers as NS
     from sgmcmcjax_b200.models import gaussian_mean as G
