@@ -34,6 +34,64 @@ from .kernels import (
 )
 
 
+_PIPELINE_BYTES = 8 << 20
+_PIPELINE_CHUNKS = 5
+_pinned = {}       # (device, shape) -> two page-locked staging tensors, reused across calls (never handed to the caller)
+
+
+def _host_result(params) -> bool:
+    import numpy as np
+
+    like = _tree.flatten(params)[0][0]
+    return isinstance(like, np.ndarray) or np.isscalar(like) or isinstance(like, (list, tuple))
+
+
+def _run_pipelined(torch, eng, st, samples, nsamp: int, keep):
+    """K steps as a few launches; block j's samples go device -> pinned staging (copy engine, side stream) -> the numpy
+    result (host memcpy) while block j + 1 computes.  Returns float32 [C, nsamp, P] (numpy)."""
+    import numpy as np
+
+    n_chains, P = samples.shape[0], eng.P
+    kc = -(-nsamp // _PIPELINE_CHUNKS)
+    key = (torch.cuda.current_device(), n_chains, kc, P)
+    if key not in _pinned:
+        _pinned[key] = [torch.empty((n_chains, kc, P), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    stage = _pinned[key]
+    out = np.empty((n_chains, nsamp, P), dtype=np.float32)
+    main, side = torch.cuda.current_stream(), _side_stream(torch)
+    pending = None                                                 # (event, slot, i0, k) of the block whose copy is in flight
+    for j, i0 in enumerate(range(0, nsamp, kc)):
+        k = min(kc, nsamp - i0)
+        keep.append(eng.run(st, i0, k, samples[:, i0:], sample_chain_stride=nsamp * P))
+        done = torch.cuda.Event()
+        done.record(main)
+        side.wait_event(done)
+        with torch.cuda.stream(side):
+            stage[j & 1][:, :k].copy_(samples[:, i0:i0 + k], non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(side)
+        if pending is not None:                                     # unpack the previous block while this one runs
+            ev, slot, p0, pk = pending
+            ev.synchronize()
+            out[:, p0:p0 + pk] = stage[slot][:, :pk].numpy()
+        pending = (copied, j & 1, i0, k)
+    ev, slot, p0, pk = pending
+    ev.synchronize()
+    out[:, p0:p0 + pk] = stage[slot][:, :pk].numpy()
+    main.synchronize()
+    return out
+
+
+_side = {}
+
+
+def _side_stream(torch):
+    dev = torch.cuda.current_device()
+    if dev not in _side:
+        _side[dev] = torch.cuda.Stream()
+    return _side[dev]
+
+
 def _build_native_sampler(init_fn: Callable, as_list: bool, pbar: bool) -> Callable:
     eng = init_fn.engine
 
@@ -61,6 +119,12 @@ def _build_native_sampler(init_fn: Callable, as_list: bool, pbar: bool) -> Calla
                 torch.cuda.current_stream().synchronize()
                 bar.update(k)
             bar.close()
+        elif nsamp > 0 and _host_result(params) and not as_list and samples.numel() * 4 >= _PIPELINE_BYTES:
+            # host (numpy) result: a few launches instead of one, the device->host copy of each block of samples and its
+            # unpacking into the result array overlapped with the next launch
+            host = _run_pipelined(torch, eng, st, samples, nsamp, keep)
+            lead = (n_chains, nsamp) if batched else (nsamp,)
+            return eng.unflatten_params(host if batched else host[0], treedef, lead)
         elif nsamp > 0:
             keep.append(eng.run(st, 0, nsamp, samples))           # samplers.py:57
         like = _tree.flatten(params)[0][0]
