@@ -149,8 +149,8 @@ k2_scores_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
           const uint64_t dx = make_desc_sw64(sb + 2 * CHUNK_BYTES);          // [Xh | Xl]: 256 rows
           for (int k = 0; k < slices; ++k) {
             const uint32_t accum = (c | k) ? 1u : 0u;
-            umma_tf32(tmem_base, dth + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc_n(256), accum);          // Th.Xh | Th.Xl
-            umma_tf32(tmem_base + 256, dtl + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc_n(128), accum);    // Tl.Xh
+            umma_tf32(tmem_base, dth + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc_n(256), accum);   // Th.Xh | Th.Xl
+            umma_tf32(tmem_base, dtl + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc_n(128), 1u);      // += Tl.Xh
           }
           tc_commit(&tail->empty[stage]);
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
@@ -172,17 +172,16 @@ k2_scores_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cb = cgrp * 32; cb < cgrp * 32 + 32; cb += 8) {
-        uint32_t p0[8], p1[8], p2[8];
-        tmem_ld8(tl + cb, p0);
-        tmem_ld8(tl + TILE + cb, p1);
-        tmem_ld8(tl + 2 * TILE + cb, p2);
+        uint32_t p0[8], p1[8];
+        tmem_ld8(tl + cb, p0);                                 // Th.Xh + Tl.Xh
+        tmem_ld8(tl + TILE + cb, p1);                          // Th.Xl
         tmem_ld_wait();
         const int ic = (it * TILE + cb) / KC;                  // row chunk of these 8 columns
         if (gm < m && ic < nic) {
           float hi[8], lo[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float sc = (__uint_as_float(p1[e]) + __uint_as_float(p2[e])) + __uint_as_float(p0[e]);
+            const float sc = __uint_as_float(p1[e]) + __uint_as_float(p0[e]);
             const float w = -sigmoid_f(sc);
             hi[e] = tf32_rna(w);
             lo[e] = tf32_rna(w - hi[e]);
