@@ -47,7 +47,9 @@ enum { SGMCMC_EST_STANDARD = 0, SGMCMC_EST_CV = 1, SGMCMC_EST_SVRG = 2 };
 
 /* diffusions.py:47-347 */
 enum { SGMCMC_DIFF_SGLD = 0, SGMCMC_DIFF_PSGLD = 1, SGMCMC_DIFF_SGLDADAM = 2, SGMCMC_DIFF_SGHMC = 3,
-       SGMCMC_DIFF_BAOAB = 4, SGMCMC_DIFF_SGNHT = 5, SGMCMC_DIFF_BADODAB = 6 };
+       SGMCMC_DIFF_BAOAB = 4, SGMCMC_DIFF_SGNHT = 5, SGMCMC_DIFF_BADODAB = 6,
+       SGMCMC_DIFF_ADAM_OPT = 7 };   /* not a sampler: the Adam MAP optimiser of optimizer.py:12-62 (sgmcmc_optimize only);
+                                        hyper = {b1, b2, eps}, step coefficients as for sgldAdam with h = learning rate */
 
 #define SGMCMC_MAX_LEAVES 8
 
@@ -150,6 +152,13 @@ int sgmcmc_init(sgmcmc_handle* h, sgmcmc_state* st, const uint32_t* keys, int32_
 int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k,
                const sgmcmc_step_coef* coef, int32_t coef_stride, float* samples,
                int64_t sample_chain_stride, void* stream);
+
+/* K iterations of the optimiser loop of optimizer.py:41-60 (vector families; the handle is created with
+ * SGMCMC_DIFF_ADAM_OPT and the standard estimator): key, subkey = split(key); value and gradient of log_post on the
+ * minibatch drawn with subkey; optax.adam ascent step.  state: theta (params), aux1 / aux2 (Adam moments, zero at the
+ * start), grad (scratch), key.  lp_out: NULL or device f32 [C, K], the log-posterior values (optimizer.py:47). */
+int sgmcmc_optimize(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const sgmcmc_step_coef* coef, float* lp_out,
+                    void* stream);
 
 /* kernel(i, key, state) of kernels.py:53-64 / :110-122 with caller-supplied per-chain keys
  * (device u32 [C, 2]); state->key is not touched. */

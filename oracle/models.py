@@ -47,6 +47,22 @@ class GaussianMean:
         return out
 
 
+def _gauss_log_post(self, leaves, batch, n_data, dtype=np.float64):
+    """util.py:43-44: logprior + Ndata * mean_i loglik_i (value), evaluated in `dtype`."""
+    (x,) = batch
+    x = np.asarray(x, dtype=dtype)
+    lik = dtype(0.0)
+    pri = dtype(0.0)
+    for th, a, c in zip(leaves, self.a, self.c):
+        th = np.asarray(th, dtype=dtype)
+        lik = lik - dtype(a) * ((x - th[None, :]) ** 2).sum(dtype=dtype)
+        pri = pri - dtype(c) * (th * th).sum(dtype=dtype)
+    return dtype(pri + dtype(n_data) * lik / dtype(x.shape[0]))
+
+
+GaussianMean.log_post = _gauss_log_post
+
+
 def _sigmoid(z):
     out = np.empty_like(z)
     pos = z >= 0
@@ -74,6 +90,20 @@ class LogisticRegression:
         r = (np.asarray(y, dtype=dtype) - _sigmoid(z)).astype(dtype)
         scale = dtype(n_data) / dtype(x.shape[0])
         return [(scale * (r @ x).astype(dtype) - dtype(self.prior_precision) * th).astype(dtype)]
+
+
+def _logreg_log_post(self, leaves, batch, n_data, dtype=np.float64):
+    """logprior + Ndata * mean_i loglik_i with loglik = -logsumexp([0, (1-2y) theta.x]) (logistic_regression.py:65-72)."""
+    x, y = batch
+    (th,) = leaves
+    x = np.asarray(x, dtype=dtype)
+    th = np.asarray(th, dtype=dtype)
+    z = (dtype(1.0) - dtype(2.0) * np.asarray(y, dtype=dtype)) * (x @ th)
+    lik = -(np.maximum(z, 0) + np.log1p(np.exp(-np.abs(z)))).sum(dtype=dtype)
+    return dtype(-dtype(0.5 * self.prior_precision) * (th * th).sum(dtype=dtype) + dtype(n_data) * lik / dtype(x.shape[0]))
+
+
+LogisticRegression.log_post = _logreg_log_post
 
 
 def _softmax(z):

@@ -128,7 +128,8 @@ class Engine:
             cfg.prior_coef[l] = c
         for k, v in enumerate(dims):
             cfg.dims[k] = int(v)
-        order = {"psgld": ("alpha", "eps"), "sgldAdam": ("beta1", "beta2", "eps"), "sghmc": ("alpha",),
+        order = {"psgld": ("alpha", "eps"), "sgldAdam": ("beta1", "beta2", "eps"), "adam_opt": ("beta1", "beta2", "eps"),
+                 "sghmc": ("alpha",),
                  "sgnht": ("a",), "badodab": ("a",)}.get(self.diffusion, ())
         for k, name in enumerate(order):
             cfg.hyper[k] = float(self.hp[name])
@@ -209,7 +210,7 @@ class Engine:
         st = {"theta": theta.clone(), "grad": z(c, self.P), "key": torch.zeros(c, 2, dtype=torch.int32, device="cuda")}
         if self.diffusion != "sgld":
             st["aux1"] = z(c, self.P)
-        if self.diffusion == "sgldAdam":
+        if self.diffusion in ("sgldAdam", "adam_opt"):
             st["aux2"] = z(c, self.P)
         if self.diffusion in ("sgnht", "badodab"):
             st["alpha"] = z(c, self.n_leaves)
@@ -251,6 +252,13 @@ class Engine:
         _native.check(self.lib.sgmcmc_run(self._handle, C.byref(cs), int(i0), int(k), _vp(coef), stride,
                                           _vp(samples), int(sample_chain_stride), self._stream()))
         return coef   # keep alive until the caller synchronises
+
+    def optimize(self, st, i0: int, k: int, lp_out=None):
+        torch = _native.require_cuda()
+        coef = torch.from_numpy(step_coefs(self.diffusion, self.hp, self.schedule, i0, k)).to("cuda")
+        cs = self._cstate(st)
+        _native.check(self.lib.sgmcmc_optimize(self._handle, C.byref(cs), int(i0), int(k), _vp(coef), _vp(lp_out), self._stream()))
+        return coef
 
     def step(self, st, i: int, keys):
         coef, _ = self._coefs(i, 1)

@@ -15,13 +15,13 @@ ABI_VERSION = 3
 
 FAMILY_GAUSSIAN_MEAN, FAMILY_LOGREG, FAMILY_MLP, FAMILY_PMF = 0, 1, 2, 3
 EST_STANDARD, EST_CV, EST_SVRG = 0, 1, 2
-(DIFF_SGLD, DIFF_PSGLD, DIFF_SGLDADAM, DIFF_SGHMC, DIFF_BAOAB, DIFF_SGNHT, DIFF_BADODAB) = range(7)
+(DIFF_SGLD, DIFF_PSGLD, DIFF_SGLDADAM, DIFF_SGHMC, DIFF_BAOAB, DIFF_SGNHT, DIFF_BADODAB, DIFF_ADAM_OPT) = range(8)
 FLAG_BADODABCV_REFERENCE_BUG = 1
 SHARD_UPDATE2, SHARD_STEP = 1, 2
 
 EXPORTS = [
     "sgmcmc_last_error", "sgmcmc_abi_version", "sgmcmc_launch_count", "sgmcmc_create", "sgmcmc_destroy", "sgmcmc_set_data",
-    "sgmcmc_set_centering", "sgmcmc_fullbatch_grad", "sgmcmc_init", "sgmcmc_run", "sgmcmc_kernel_step",
+    "sgmcmc_set_centering", "sgmcmc_fullbatch_grad", "sgmcmc_init", "sgmcmc_run", "sgmcmc_optimize", "sgmcmc_kernel_step",
     "sgmcmc_set_row_shard", "sgmcmc_set_centering_grad", "sgmcmc_shard_init", "sgmcmc_shard_step",
     "sgmcmc_minibatch_indices", "sgmcmc_normal", "sgmcmc_split", "sgmcmc_ksd_imq_partial", "sgmcmc_ksd_workspace_bytes", "sgmcmc_ksd_imq_tc",
 ]
@@ -88,6 +88,7 @@ def load(build_if_missing: bool = True):
         "sgmcmc_init": [vp, C.POINTER(State), vp, i32, vp],
         "sgmcmc_run": [vp, C.POINTER(State), i32, i32, vp, i32, vp, i64, vp],
         "sgmcmc_kernel_step": [vp, C.POINTER(State), i32, vp, vp, vp],
+        "sgmcmc_optimize": [vp, C.POINTER(State), i32, i32, vp, vp, vp],
         "sgmcmc_set_row_shard": [vp, i64, i64],
         "sgmcmc_set_centering_grad": [vp, vp, vp, vp],
         "sgmcmc_shard_init": [vp, C.POINTER(State), vp, i32, vp, vp],

@@ -212,7 +212,8 @@ int check_state(const sgmcmc_handle* h, const sgmcmc_state* st) {
   if (!st->theta || !st->grad) return fail(SGMCMC_E_INVALID, "state.theta and state.grad are required");
   const int d = h->cfg.diffusion;
   if (d != SGMCMC_DIFF_SGLD && !st->aux1) return fail(SGMCMC_E_INVALID, "state.aux1 is required by this diffusion");
-  if (d == SGMCMC_DIFF_SGLDADAM && !st->aux2) return fail(SGMCMC_E_INVALID, "state.aux2 is required by sgldAdam");
+  if ((d == SGMCMC_DIFF_SGLDADAM || d == SGMCMC_DIFF_ADAM_OPT) && !st->aux2)
+    return fail(SGMCMC_E_INVALID, "state.aux2 is required by sgldAdam / the Adam optimiser");
   if ((d == SGMCMC_DIFF_SGNHT || d == SGMCMC_DIFF_BADODAB) && !st->alpha)
     return fail(SGMCMC_E_INVALID, "state.alpha is required by sgnht / badodab");
   if (h->cfg.estimator == SGMCMC_EST_SVRG && (!st->svrg_center || !st->svrg_grad))
@@ -346,7 +347,10 @@ int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
   if (cfg->family < SGMCMC_FAMILY_GAUSSIAN_MEAN || cfg->family > SGMCMC_FAMILY_PMF)
     return fail(SGMCMC_E_UNSUPPORTED, "unknown model family");
   if (cfg->estimator < 0 || cfg->estimator > SGMCMC_EST_SVRG) return fail(SGMCMC_E_INVALID, "bad estimator");
-  if (cfg->diffusion < 0 || cfg->diffusion > SGMCMC_DIFF_BADODAB) return fail(SGMCMC_E_INVALID, "bad diffusion");
+  if (cfg->diffusion < 0 || cfg->diffusion > SGMCMC_DIFF_ADAM_OPT) return fail(SGMCMC_E_INVALID, "bad diffusion");
+  if (cfg->diffusion == SGMCMC_DIFF_ADAM_OPT && (cfg->estimator != SGMCMC_EST_STANDARD || (int64_t)cfg->batch >= cfg->n_data ||
+                                                 cfg->family == SGMCMC_FAMILY_PMF || cfg->family == SGMCMC_FAMILY_MLP))
+    return fail(SGMCMC_E_UNSUPPORTED, "the optimiser covers the vector families with the standard minibatch estimator");
   if (cfg->n_data <= 0 || cfg->n_data > 0x7fffffffLL) return fail(SGMCMC_E_INVALID, "n_data out of range");
   if (cfg->batch <= 0) return fail(SGMCMC_E_INVALID, "batch must be positive");
   if (cfg->n_leaves < 1 || cfg->n_leaves > SGMCMC_MAX_LEAVES) return fail(SGMCMC_E_INVALID, "n_leaves out of range");
@@ -540,6 +544,7 @@ int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const 
   if (k < 0 || i0 < 0) return fail(SGMCMC_E_INVALID, "i0 and k must be non-negative");
   if (!coef || (coef_stride != 0 && coef_stride != 1)) return fail(SGMCMC_E_INVALID, "bad step coefficients");
   if (!st->key) return fail(SGMCMC_E_INVALID, "state.key is required");
+  if (h->cfg.diffusion == SGMCMC_DIFF_ADAM_OPT) return fail(SGMCMC_E_STATE, "this handle is an optimiser: use sgmcmc_optimize");
   if (k == 0) return SGMCMC_OK;
   if (h->big) {
     sg::BigRun run{};
@@ -560,6 +565,18 @@ int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const 
   sg::VecRun run{};
   run.st = *st; run.i0 = i0; run.K = k; run.coef = coef; run.coef_stride = coef_stride; run.samples = samples;
   run.sample_chain_stride = sample_chain_stride > 0 ? (size_t)sample_chain_stride : (size_t)k * h->P;
+  return dispatch_vec(h, run, (cudaStream_t)stream);
+}
+
+int sgmcmc_optimize(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const sgmcmc_step_coef* coef, float* lp_out,
+                    void* stream) {
+  int rc = check_state(h, st);
+  if (rc != SGMCMC_OK) return rc;
+  if (h->cfg.diffusion != SGMCMC_DIFF_ADAM_OPT) return fail(SGMCMC_E_STATE, "the handle was not created with SGMCMC_DIFF_ADAM_OPT");
+  if (k < 0 || i0 < 0 || !coef || !st->key) return fail(SGMCMC_E_INVALID, "bad argument");
+  if (k == 0) return SGMCMC_OK;
+  sg::VecRun run{};
+  run.st = *st; run.i0 = i0; run.K = k; run.coef = coef; run.coef_stride = 1; run.lp_out = lp_out;
   return dispatch_vec(h, run, (cudaStream_t)stream);
 }
 

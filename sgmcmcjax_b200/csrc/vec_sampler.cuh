@@ -52,6 +52,7 @@ struct VecRun {
   // data-sharded mode (rows split over ranks, one all-reduce of the [C, DS] minibatch sums per step, done by the host):
   const float* sum_in;       // [C][DS] all-reduced sums of the previous estimate: the gradient is finished from them first
   float* sum_out;            // [C][DS] this rank's partial sums of the new estimate (the gradient is NOT finished)
+  float* lp_out;             // [C][K] log-posterior values of the optimizer iterations (SGMCMC_DIFF_ADAM_OPT), else nullptr
   int shard_flags;           // SHARD_UPDATE2: run the palindrome's update2 (coef_prev) after finishing the gradient;
   const sgmcmc_step_coef* coef_prev;   //   SHARD_STEP: then do one transition and leave its partial sums in sum_out
 };
@@ -136,7 +137,7 @@ __device__ __forceinline__ float reduce8(const float (&p)[8], int lane) {
 template <int FAMILY, bool CV, int NCH>
 __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, const RandintPlan& plan,
                                          unsigned seq_base, unsigned count, const float* s_theta, const float* s_center,
-                                         float* s_part) {
+                                         float* s_part, float* lp_part = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const unsigned h = (count + 1u) >> 1;
   const int DS = m.DS;
@@ -146,6 +147,7 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
 
   float4 acc[NCH], th[NCH], ct[NCH];
   bool ok[NCH];
+  float lpv = 0.f;     // log-likelihood VALUE terms (optimizer only): gaussian sum |x|^2, logreg sum -softplus(theta.x~)
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int f4 = lane + 32 * c;
@@ -214,6 +216,12 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
           for (int c = 0; c < NCH; ++c) {
             acc[c].x += x[u][c].x; acc[c].y += x[u][c].y; acc[c].z += x[u][c].z; acc[c].w += x[u][c].w;
           }
+        if (lp_part) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) lpv += dot4(x[u][c], x[u][c]);
+        }
       } else {
         float p[8];
 #pragma unroll
@@ -224,6 +232,11 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
         }
         const float z = reduce8(p, lane);
         float wgt = -sigmoid_f(z);
+        if (lp_part) {                                   // lane 4u holds z of row u: loglik = -softplus(z)
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (lane == 4 * u && r[u] >= 0) lpv -= fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
+        }
         if (CV) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -246,6 +259,11 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
 #pragma unroll
   for (int c = 0; c < NCH; ++c)
     if (ok[c]) reinterpret_cast<float4*>(s_part + warp * DS)[lane + 32 * c] = acc[c];
+  if (lp_part) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) lpv += __shfl_xor_sync(FULL, lpv, o);
+    if (lane == 0) lp_part[warp] = lpv;
+  }
 }
 
 // part[W][DS] -> S[DS]  (fixed summation order: deterministic)
@@ -325,10 +343,52 @@ struct ChainCtx {
   }
 
   // minibatch sums over the rows of this rank: s.S[d] = sum_i x_i (gaussian) / sum_i (w_i [- w_c,i]) x~_i (logreg)
-  __device__ void partial_sums(Key k2) {
+  __device__ void partial_sums(Key k2, bool want_lp = false) {
     const RandintPlan plan = randint_plan(k2, m.n_data, m.batch);
-    row_pass<FAMILY, CV, NCH>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part);
+    row_pass<FAMILY, CV, NCH>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part, want_lp ? s.red : nullptr);
     fold_parts(s, m.DS);
+  }
+
+  // log_post VALUE on the minibatch whose sums are in s.S / s.red (util.py:43-44: logprior + Ndata * mean_i loglik_i)
+  __device__ float log_post_value() {
+    const int W = blockDim.x >> 5;
+    float lps = 0.f;
+    for (int w = 0; w < W; ++w) lps += s.red[w];
+    __syncthreads();
+    const float B = (float)m.batch;
+    float lik = 0.f, pri = 0.f;
+    if (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN) {
+      for (int leaf = 0; leaf < m.n_leaves; ++leaf) {      // sum_i |x_i - th|^2 = sum |x|^2 - 2 th.S + B |th|^2
+        float a = 0.f, b = 0.f;
+        for (int d = threadIdx.x; d < m.leaf_dim; d += blockDim.x) {
+          const float t = s.theta[leaf * m.leaf_dim + d];
+          a = fmaf(t, s.S[d], a); b = fmaf(t, t, b);
+        }
+        const float tS = block_sum(a, s.red);
+        const float tt = block_sum(b, s.red);
+        lik -= 0.5f * m.lik2[leaf] * (lps - 2.0f * tS + B * tt);
+        pri -= 0.5f * m.prior2[leaf] * tt;
+      }
+    } else {
+      float b = 0.f;
+      for (int d = threadIdx.x; d < m.leaf_dim; d += blockDim.x) b = fmaf(s.theta[d], s.theta[d], b);
+      pri = -0.5f * m.prior2[0] * block_sum(b, s.red);
+      lik = lps;
+    }
+    return pri + m.scale * lik;
+  }
+
+  // optax.adam ascent step on the gradient in s.grad (oracle/optimizer.py; cf.ca = 1 - b1^t, cf.cb = 1 - b2^t, cf.h = lr)
+  __device__ void adam_step(const sgmcmc_step_coef& cf) {
+    const float b1 = m.hyper[0], b2 = m.hyper[1], eps = m.hyper[2];
+    for (int e = threadIdx.x; e < m.P; e += blockDim.x) {
+      const float g = s.grad[e];
+      const float mm = b1 * s.aux1[e] + (1.0f - b1) * g;
+      const float vv = b2 * s.aux2[e] + (1.0f - b2) * (g * g);
+      s.aux1[e] = mm; s.aux2[e] = vv;
+      s.theta[e] = s.theta[e] + cf.h * (mm / cf.ca) / (sqrtf(vv / cf.cb) + eps);
+    }
+    __syncthreads();
   }
 
   // s.grad from the (complete) minibatch sums in s.S, evaluated at s.theta
@@ -571,7 +631,18 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
       const sgmcmc_step_coef cf = run.coef[(size_t)sidx * run.coef_stride];
       Key sub;
       if (run.step_keys) { sub.a = run.step_keys[2 * c]; sub.b = run.step_keys[2 * c + 1]; }
-      else { Key nk; split2(carry, nk, sub); carry = nk; }      // samplers.py:49
+      else { Key nk; split2(carry, nk, sub); carry = nk; }      // samplers.py:49 / optimizer.py:46
+      if (m.diffusion == SGMCMC_DIFF_ADAM_OPT) {
+        // optimizer.py:45-51: value and gradient on the minibatch drawn with `sub` itself, then the Adam step
+        ctx.partial_sums(sub, run.lp_out != nullptr);
+        ctx.finish_from_sums();
+        if (run.lp_out) {
+          const float lp = ctx.log_post_value();
+          if (threadIdx.x == 0) run.lp_out[(size_t)c * run.K + sidx] = lp;
+        }
+        ctx.adam_step(cf);
+        continue;
+      }
       ctx.transition(i, sub, cf);
       if (run.samples) {
         float* dst = run.samples + (size_t)c * run.sample_chain_stride + (size_t)sidx * P;

@@ -55,12 +55,12 @@ def make_schedule(scalar_or_schedule: Union[float, Callable]) -> Callable:
 DIFFUSION_IDS = {
     "sgld": _native.DIFF_SGLD, "psgld": _native.DIFF_PSGLD, "sgldAdam": _native.DIFF_SGLDADAM,
     "sghmc": _native.DIFF_SGHMC, "baoab": _native.DIFF_BAOAB, "sgnht": _native.DIFF_SGNHT,
-    "badodab": _native.DIFF_BADODAB,
+    "badodab": _native.DIFF_BADODAB, "adam_opt": _native.DIFF_ADAM_OPT,
 }
 
 
 def coef_is_constant(diffusion: str, schedule: Callable) -> bool:
-    return bool(getattr(schedule, "_sgmcmc_constant", False)) and diffusion != "sgldAdam"
+    return bool(getattr(schedule, "_sgmcmc_constant", False)) and diffusion not in ("sgldAdam", "adam_opt")
 
 
 def step_coefs(diffusion: str, hp: dict, schedule: Callable, i0: int, k: int) -> np.ndarray:
@@ -75,7 +75,7 @@ def step_coefs(diffusion: str, hp: dict, schedule: Callable, i0: int, k: int) ->
         ca = cb = f32(0.0)
         if diffusion == "sgld":                                   # diffusions.py:65-68
             ca = np.sqrt(f32(2 * dt))
-        elif diffusion == "sgldAdam":                             # diffusions.py:139-140
+        elif diffusion in ("sgldAdam", "adam_opt"):                # diffusions.py:139-140 / optax bias correction
             ca = f32(1) - np.power(f32(hp["beta1"]), f32(i + 1))
             cb = f32(1) - np.power(f32(hp["beta2"]), f32(i + 1))
         elif diffusion == "sghmc":                                # diffusions.py:181-199

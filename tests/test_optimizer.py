@@ -1,0 +1,78 @@
+"""MAP optimiser (sgmcmcjax/optimizer.py:12-62 with optax.adam): oracle on the CPU, fused CUDA path on the GPU."""
+import numpy as np
+import pytest
+
+from oracle import jax_prng as P
+from oracle import models as M
+from oracle import optimizer as O
+
+
+def reference_test_problem():
+    """tests/test_optimizers.py:8-20."""
+    key = P.PRNGKey(0)
+    mu_true = P.normal(key, (100,))
+    X = (P.normal(key, (10_000, 100)) + mu_true).astype(np.float32)
+    return key, mu_true, X
+
+
+def test_oracle_adam_reaches_the_posterior_mode():
+    """The reference's own (statistical) bar, tests/test_optimizers.py:23-36, on a shorter run."""
+    key, mu_true, X = reference_test_problem()
+    leaves, lps = O.run_adam(M.GaussianMean((0.5,), (0.005,)), (X,), 1000, 1e-2, key, 1500, [np.zeros(100, np.float32)])
+    assert np.allclose(leaves[0], mu_true, atol=1e-1)
+    assert lps.shape == (1500,) and lps[-1] > lps[0]
+
+
+def test_optimizer_api_errors():
+    from sgmcmcjax_b200 import optimizer as NO
+    from sgmcmcjax_b200.models import gaussian_mean as G
+
+    with pytest.raises(TypeError):
+        NO.build_optax_optimizer("adam", G.loglikelihood, G.logprior, (np.zeros((10, 3), np.float32),), 2)
+
+    class FakeOptax:
+        def init(self, p): ...
+        def update(self, g, s): ...
+
+    with pytest.raises(NotImplementedError):
+        NO.build_optax_optimizer(FakeOptax(), G.loglikelihood, G.logprior, (np.zeros((10, 3), np.float32),), 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["gauss", "gauss2", "logreg"])
+def test_adam_iterations_match_oracle(cuda, case):
+    from sgmcmcjax_b200 import optimizer as NO
+    from test_gpu_parity import as_params, close, gauss_case, leaves_of, logreg_case
+
+    if case == "logreg":
+        fam, fns, data, th0 = logreg_case(n=3000, d=20)
+        batch, lr = 300, 1e-2
+    else:
+        fam, fns, data, th0 = gauss_case(case == "gauss2", n=2000, d=7)
+        batch, lr = 100, 1e-2
+    opt = NO.build_optax_optimizer(NO.adam(lr), fns[0], fns[1], data, batch)
+    key = P.PRNGKey(4)
+    params, lps = opt(key, 12, as_params(th0))
+    ref, ref_lps = O.run_adam(fam, data, batch, lr, key, 12, th0)
+    for got, r in zip(leaves_of(params), ref):
+        close(got, r, rtol=2e-5, what=f"adam params {case}")
+    np.testing.assert_allclose(lps, ref_lps, rtol=2e-5)
+    assert lps.shape == (12,)
+
+
+@pytest.mark.gpu
+def test_reference_optimizer_test(cuda):
+    """tests/test_optimizers.py:23-36 verbatim: Adam, lr 1e-2, batch 10 % of N = 10k, 10k iterations."""
+    from sgmcmcjax_b200 import optimizer as NO
+    from sgmcmcjax_b200.models import gaussian_mean as G
+
+    key, mu_true, X = reference_test_problem()
+    optimizer = NO.build_optax_optimizer(NO.adam(1e-2), G.loglikelihood, G.logprior, (X,), int(0.1 * 10_000))
+    params, log_post_list = optimizer(key, 10_000, np.zeros(100, np.float32))
+    assert log_post_list.shape == (10_000,) and params.shape == (100,)
+    assert np.allclose(params, mu_true, atol=1e-1)
+    # multi-chain: independent optimisations, chain c == the single run with keys[c]
+    keys = P.split(key, 3)
+    p3, lp3 = optimizer(keys, 50, np.zeros((3, 100), np.float32))
+    p1, lp1 = optimizer(keys[1], 50, np.zeros(100, np.float32))
+    assert np.array_equal(p3[1], p1) and np.array_equal(lp3[1], lp1)
