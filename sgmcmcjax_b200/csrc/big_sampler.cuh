@@ -110,13 +110,19 @@ __device__ __forceinline__ void leaf_pass(unsigned n, Key key, LD ld, ST st) {
     Elt e0[U], e1[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) { e0[u] = ld(m0 + u * bd); e1[u] = ld(m0 + u * bd + h); }
+    // all U threefry blocks first, as independent chains side by side (ILP for the 20 dependent rounds of each), and
+    // before the first use of a loaded value: the RNG work hides the memory latency of the loads above
+    uint32_t w0[U], w1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) stream_block(key, m0 + u * bd, n, w0[u], w1[u]);
+    float z0[U], z1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { z0[u] = bits_to_normal(w0[u]); z1[u] = bits_to_normal(w1[u]); }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const unsigned m = m0 + u * bd;
-      uint32_t w0, w1;
-      stream_block(key, m, n, w0, w1);
-      st(m, e0[u], bits_to_normal(w0));
-      st(m + h, e1[u], bits_to_normal(w1));
+      st(m, e0[u], z0[u]);
+      st(m + h, e1[u], z1[u]);
     }
   }
 #pragma unroll 1

@@ -98,3 +98,16 @@ def imq_KSD(samples, grads, distributed: bool = False, method: str = "tc"):
         parallel.allreduce_scalar(part)
     val = (torch.sqrt(part[0]) / n).to(torch.float32)
     return _like(val, samples)
+
+
+def posterior_KSD(engine, samples, distributed: bool = False):
+    """imq_KSD of posterior samples [N, P] with their gradients computed here: ``grads = grad_log_post(samples)`` over ALL
+    rows of the engine's data (K2; tensor cores for the logistic-regression family), then the Gram contractions.
+    ``engine`` is ``sampler.engine`` / ``init_fn.engine`` of any builder of this package."""
+    torch = _native.require_cuda()
+    x = to_device(samples, torch.float32)
+    if x.dim() != 2:
+        raise ValueError("samples must be [N, P]")
+    grads = engine.fullbatch_grad(x.contiguous())
+    val = imq_KSD(x, grads, distributed=distributed)
+    return _like(val, samples)

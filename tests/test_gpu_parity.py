@@ -592,6 +592,21 @@ def test_ksd_matches_fp64_literal(cuda, n, d, kind, method):
     assert abs(got - ref) <= 1e-4 * abs(ref), (got, ref)
 
 
+def test_posterior_ksd_pipeline(cuda):
+    """samples -> K2 gradients over all rows (tensor cores at M >= 64) -> imq_KSD, against the oracle end to end."""
+    from sgmcmcjax_b200 import kernels as NK
+    from sgmcmcjax_b200 import ksd as NKSD
+
+    fam, fns, data, th0 = logreg_case(n=4000, d=12, seed=21)
+    init_fn, _, _ = NK.build_sgld_kernel(1e-5, fns[0], fns[1], data, 10)
+    rng = np.random.default_rng(5)
+    pts = (th0[0][None, :] + 0.05 * rng.normal(size=(150, 12))).astype(np.float32)
+    got = float(NKSD.posterior_KSD(init_fn.engine, pts))
+    grads = np.stack([fam.grad_log_post([p], data, 4000, np.float64)[0] for p in pts])
+    ref = OK.imq_ksd_literal(pts, grads)
+    assert abs(got - ref) <= 1e-4 * abs(ref), (got, ref)
+
+
 def test_ksd_tc_tile_partitions_sum_to_whole(cuda):
     from sgmcmcjax_b200 import ksd as NKSD
 
