@@ -550,7 +550,8 @@ int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const 
     sg::BigRun run{};
     run.st = *st; run.i0 = i0; run.K = k; run.coef = coef; run.coef_stride = coef_stride; run.samples = samples;
     run.sample_chain_stride = sample_chain_stride > 0 ? (size_t)sample_chain_stride : (size_t)k * h->P;
-    if (h->cfg.family == SGMCMC_FAMILY_MLP && k > 1 && !env_int("SGMCMC_NO_LOOKAHEAD", 0)) {       // look-ahead noise scratch (stream-ordered reuse: one stream per handle)
+    if (SG_MLP_PRODUCER_WARPS > 0 && h->cfg.family == SGMCMC_FAMILY_MLP && k > 1 && !env_int("SGMCMC_NO_LOOKAHEAD", 0)) {
+      // look-ahead noise scratch of the optional producer warps (stream-ordered reuse: one stream per handle)
       const size_t need = (size_t)st->n_chains * h->P;
       if (need > h->noise_elems) {
         if (h->noise) CUDA_TRY(cudaFree(h->noise));
