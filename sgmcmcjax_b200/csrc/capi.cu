@@ -142,15 +142,23 @@ __global__ void split_kernel(Key key, unsigned num, uint32_t* out) {
 
 namespace {
 
-template <int FAMILY, bool CV, int NCH>
-int launch_vec(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
-  auto kern = sg::vec_sampler_kernel<FAMILY, CV, NCH>;
+template <int FAMILY, bool CV, int NCH, bool EXT>
+int launch_vec_kernel(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
+  auto kern = sg::vec_sampler_kernel<FAMILY, CV, NCH, EXT>;
   const int PP = ((h->P > h->DS ? h->P : h->DS) + 3) & ~3;
   const size_t smem = sg::vec_smem_bytes(PP, h->DS, warps);
   if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<run.st.n_chains, warps * 32, smem, stream>>>(h->vm, run);
   CUDA_TRY(cudaGetLastError()); ++g_launches;
   return SGMCMC_OK;
+}
+
+template <int FAMILY, bool CV, int NCH>
+int launch_vec(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
+  // the extended instantiation carries the row-sharded mode and the optimiser; the plain samplers run the lean one
+  const bool ext = h->vm.own_n != h->vm.n_data || h->cfg.diffusion == SGMCMC_DIFF_ADAM_OPT || run.sum_in || run.sum_out;
+  return ext ? launch_vec_kernel<FAMILY, CV, NCH, true>(h, run, warps, stream)
+             : launch_vec_kernel<FAMILY, CV, NCH, false>(h, run, warps, stream);
 }
 
 template <int FAMILY, bool CV>

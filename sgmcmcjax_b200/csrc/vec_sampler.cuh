@@ -134,14 +134,18 @@ __device__ __forceinline__ float reduce8(const float (&p)[8], int lane) {
 // Row pass: every warp walks its share of the index stream, 64 rows per threefry batch,
 // 8 rows in flight per lane.  Result: part[warp][0..DS) = sum over the warp's rows of
 //   gaussian_mean: x            logreg: w x~  with  w = -sigmoid(theta.x~) [ + sigmoid(center.x~) if CV ]
-template <int FAMILY, bool CV, int NCH>
+// EXT = false is the lean instantiation of the plain samplers (the bench kernel); the row-sharded mode and the
+// optimiser's log-posterior values live in the EXT = true instantiation only (they cost registers in the hot loop:
+// measured +6 % on the C2 step when they shared one kernel).
+template <int FAMILY, bool CV, int NCH, bool EXT = false>
 __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, const RandintPlan& plan,
                                          unsigned seq_base, unsigned count, const float* s_theta, const float* s_center,
-                                         float* s_part, float* lp_part = nullptr) {
+                                         float* s_part, float* lp_part_in = nullptr) {
+  float* lp_part = EXT ? lp_part_in : nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const unsigned h = (count + 1u) >> 1;
   const int DS = m.DS;
-  const bool sharded = m.own_n != m.n_data;
+  const bool sharded = EXT && m.own_n != m.n_data;
   const float4* __restrict__ rows = reinterpret_cast<const float4*>(m.rows);
   const int row_f4 = DS >> 2;
 
@@ -301,7 +305,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // ---------------------------------------------------------------------------------------
-template <int FAMILY, bool CV, int NCH>
+template <int FAMILY, bool CV, int NCH, bool EXT = false>
 struct ChainCtx {
   const VecModel& m;
   Smem s;
@@ -310,7 +314,7 @@ struct ChainCtx {
   // full-batch gradient at s.theta into dst[] (sequential pass over every row)
   __device__ void full_grad(float* dst) {
     RandintPlan dummy{};
-    row_pass<FAMILY, false, NCH>(m, true, dummy, 0u, m.own_n, s.theta, s.center, s.part);
+    row_pass<FAMILY, false, NCH, EXT>(m, true, dummy, 0u, m.own_n, s.theta, s.center, s.part);
     fold_parts(s, m.DS);
     const float rows = (float)m.own_n;
     for (int e = threadIdx.x; e < m.P; e += blockDim.x) {
@@ -345,7 +349,7 @@ struct ChainCtx {
   // minibatch sums over the rows of this rank: s.S[d] = sum_i x_i (gaussian) / sum_i (w_i [- w_c,i]) x~_i (logreg)
   __device__ void partial_sums(Key k2, bool want_lp = false) {
     const RandintPlan plan = randint_plan(k2, m.n_data, m.batch);
-    row_pass<FAMILY, CV, NCH>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part, want_lp ? s.red : nullptr);
+    row_pass<FAMILY, CV, NCH, EXT>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part, want_lp ? s.red : nullptr);
     fold_parts(s, m.DS);
   }
 
@@ -564,7 +568,7 @@ struct ChainCtx {
   }
 };
 
-template <int FAMILY, bool CV, int NCH>
+template <int FAMILY, bool CV, int NCH, bool EXT = false>
 __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel m, const VecRun run) {
   extern __shared__ __align__(16) float smem_raw[];
   const int W = blockDim.x >> 5;
@@ -595,10 +599,10 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
   }
   __syncthreads();
 
-  ChainCtx<FAMILY, CV, NCH> ctx(m, s);
+  ChainCtx<FAMILY, CV, NCH, EXT> ctx(m, s);
   Key carry{0u, 0u};
 
-  if (run.sum_in) {                                   // finish the previous estimate from the all-reduced sums
+  if (EXT && run.sum_in) {                            // finish the previous estimate from the all-reduced sums
     for (int d = threadIdx.x; d < m.DS; d += blockDim.x) s.S[d] = run.sum_in[(size_t)c * m.DS + d];
     __syncthreads();
     ctx.finish_from_sums();
@@ -608,8 +612,8 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
     // init_fn (kernels.py:48-51), optionally preceded by samplers.py:53
     Key k; k.a = run.init_keys[2 * c]; k.b = run.init_keys[2 * c + 1];
     if (run.mode == 2) { Key sub; split2(k, carry, sub); k = sub; }
-    if (run.sum_out) ctx.partial_sums(k); else ctx.estimate(0, k, true);
-  } else if (run.sum_out || run.sum_in) {
+    if (EXT && run.sum_out) ctx.partial_sums(k); else ctx.estimate(0, k, true);
+  } else if (EXT && (run.sum_out || run.sum_in)) {
     // data-sharded step: one transition whose estimate stops at this rank's partial sums
     carry.a = st.key[2 * c]; carry.b = st.key[2 * c + 1];
     if (run.shard_flags & SHARD_STEP) {
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
       Key sub;
       if (run.step_keys) { sub.a = run.step_keys[2 * c]; sub.b = run.step_keys[2 * c + 1]; }
       else { Key nk; split2(carry, nk, sub); carry = nk; }      // samplers.py:49 / optimizer.py:46
-      if (m.diffusion == SGMCMC_DIFF_ADAM_OPT) {
+      if (EXT && m.diffusion == SGMCMC_DIFF_ADAM_OPT) {
         // optimizer.py:45-51: value and gradient on the minibatch drawn with `sub` itself, then the Adam step
         ctx.partial_sums(sub, run.lp_out != nullptr);
         ctx.finish_from_sums();
@@ -664,7 +668,7 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
   if (threadIdx.x == 0 && st.key && (run.mode == 2 || (run.mode == 0 && run.step_keys == nullptr))) {
     st.key[2 * c] = carry.a; st.key[2 * c + 1] = carry.b;
   }
-  if (run.sum_out)
+  if (EXT && run.sum_out)
     for (int d = threadIdx.x; d < m.DS; d += blockDim.x) run.sum_out[(size_t)c * m.DS + d] = s.S[d];
 }
 
