@@ -70,6 +70,20 @@ struct BigRun {
 // for every leaf into dst[P] - the noise of the langevin step that will run with `key`.
 struct NoiseJob { Key key; float* dst; bool valid; };
 
+// Optional phase timers (-DSG_PHASE_TIMING): cycles of block 0 / thread 0 per phase, read back with sgmcmc_debug_phase_cycles.
+#ifdef SG_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define SG_T0() const long long sg_t0__ = clock64()
+#define SG_T1(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_phase_cycles[slot], (unsigned long long)(clock64() - sg_t0__)); } while (0)
+#define SG_TA(var) long long var = clock64()
+#define SG_TB(slot, var) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long n__ = clock64(); atomicAdd(&g_phase_cycles[slot], (unsigned long long)(n__ - var)); var = n__; } } while (0)
+#else
+#define SG_T0() do {} while (0)
+#define SG_T1(slot) do {} while (0)
+#define SG_TA(var) do {} while (0)
+#define SG_TB(slot, var) do {} while (0)
+#endif
+
 struct BigSmem {
   uint32_t keys[2 * (4 + 2 * MAXL)];
   float alpha[MAXL];
@@ -423,9 +437,11 @@ struct BigCtx {
   // phase 1 = `update` (consumes the carried gradient, leaves the buffer zeroed for the next estimate and
   // emits the sample if `sample` is set); phase 2 = `update2` of the palindromes (gradient stays in the buffer).
   __device__ void diffuse(int phase, int i, const sgmcmc_step_coef& cf, int key_slot, float* sample) {
+    SG_T0();
     if (!grad_raw) diffuse_mode<0>(phase, i, cf, key_slot, sample);
     else if (!is_cv()) diffuse_mode<1>(phase, i, cf, key_slot, sample);
     else diffuse_mode<2>(phase, i, cf, key_slot, sample);
+    SG_T1(0);
   }
 
   template <int MODE>

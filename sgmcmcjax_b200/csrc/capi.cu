@@ -656,6 +656,15 @@ int sgmcmc_shard_step(sgmcmc_handle* h, sgmcmc_state* st, int32_t i, const sgmcm
   return dispatch_vec(h, run, (cudaStream_t)stream);
 }
 
+#ifdef SG_PHASE_TIMING
+extern "C" int sgmcmc_debug_phase_cycles(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, sg::g_phase_cycles, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(sg::g_phase_cycles, z, sizeof(z)); }
+  return 0;
+}
+#endif
+
 int sgmcmc_minibatch_indices(const uint32_t* key, int64_t n, int32_t batch, int32_t* out, void* stream) {
   if (!key || !out || n <= 0 || n > 0x7fffffffLL || batch <= 0) return fail(SGMCMC_E_INVALID, "bad argument");
   sg::Key k{key[0], key[1]};

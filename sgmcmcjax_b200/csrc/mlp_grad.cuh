@@ -262,7 +262,9 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       uint8_t* xlo = sb + MLP_ROWS * 128;
       uint8_t* whi = sb + 2 * MLP_ROWS * 128;
       uint8_t* wlo = whi + (size_t)s1n * 128;
+      SG_TA(tt);
       if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }   // MMAs of chunk c - 2 retired
+      SG_TB(9, tt);
       if (fast) {                                                            // out-of-range rows / columns read as zero
         const bool in = c * MLP_KC + ch * 4 < s0;
         if (!(in && xsrc0)) xv0 = zero4;
@@ -275,9 +277,12 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       split4(xv1, hi, lo); *reinterpret_cast<float4*>(xhi + off1) = hi; *reinterpret_cast<float4*>(xlo + off1) = lo;
       if (w0_in) { split4(wv0, hi, lo); *reinterpret_cast<float4*>(whi + off0) = hi; *reinterpret_cast<float4*>(wlo + off0) = lo; }
       if (w1_in) { split4(wv1, hi, lo); *reinterpret_cast<float4*>(whi + off1) = hi; *reinterpret_cast<float4*>(wlo + off1) = lo; }
-      if (c + 2 < n_chunks) fetch(c + 2, xv0, xv1, wv0, wv1);               // two chunks of loads stay in flight
-      fence_proxy_async();
+      SG_TB(10, tt);
+      fence_proxy_async();                      // BEFORE the next loads are issued: the fence would wait for them too
+      SG_TB(11, tt);
       mlptc::worker_sync();
+      SG_TB(12, tt);
+      if (c + 2 < n_chunks) fetch(c + 2, xv0, xv1, wv0, wv1);               // two chunks of loads stay in flight
       if (tid == 0) {
         tc_fence_after();
         const int slices = min(MLP_KC, s0p8 - c * MLP_KC) / 8;
@@ -291,6 +296,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         }
         tc_commit(&ms.bar[st]);
       }
+      SG_TB(13, tt);
       ++uses[st];
     };
     {
@@ -391,9 +397,9 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         split4(xv, hi, lo);
         *reinterpret_cast<float4*>(sb + soff) = hi;
         *reinterpret_cast<float4*>(sb + 8192 + soff) = lo;
-        if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
-        fence_proxy_async();
+        fence_proxy_async();                                   // before the next load is issued (the fence would wait for it)
         mlptc::worker_sync();
+        if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
         if (tid == 0) {
           tc_fence_after();
           const int g = u / npp, p = u - g * npp;
@@ -482,12 +488,14 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     auto dzbuf = [&](int k) { return fbase + plan.dz_off(k); };
     auto dzstr = [&](int k) { return mlp_stride(plan.dz_w(k)); };
 
-    layer1_forward(m, ms, region, th, nb, R, act(1), astr(1));
+    { SG_T0(); layer1_forward(m, ms, region, th, nb, R, act(1), astr(1)); SG_T1(1); }
+    SG_T0();
 
     // =================================================================== softmax + small layers forward
     for (int l = 1; l < L; ++l) {
       float* A = act(l);
       const int as = astr(l), w = sz[l];
+      SG_T0();
       if (tid < R) {                                    // a_l = softmax(z_l), one thread per row
         float mx = -INFINITY;
         for (int c = 0; c < w; ++c) mx = fmaxf(mx, A[tid * as + c]);
@@ -497,6 +505,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         for (int c = 0; c < w; ++c) A[tid * as + c] *= inv;
       }
       mlptc::worker_sync();
+      SG_T1(4);
       float* Zn = act(l + 1);
       const int zs = astr(l + 1), wn = sz[l + 1];
       const float* Wn = th + m.leaf_off[2 * l];
@@ -509,12 +518,14 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         Zn[b * zs + n] = accv + bn[n];
       }
       mlptc::worker_sync();
+      SG_T1(5);
     }
 
     // =================================================================== output layer: dZ_L = y - sum(y) softmax(z_L)
     float* dz = dzbuf(0);
     int dzs = dzstr(0);
     {
+      SG_T0();
       const int w = sz[L], zs = astr(L);
       const float* Z = act(L);
       if (tid < R) {
@@ -531,6 +542,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         }
       }
       mlptc::worker_sync();
+      SG_T1(6);
     }
 
     uint8_t* bhi = region;
@@ -548,6 +560,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       const float* Wl = th + m.leaf_off[2 * (l - 1)];
       float* gW = g + m.leaf_off[2 * (l - 1)];
       float* gb = g + m.leaf_off[2 * (l - 1) + 1];
+      SG_T0();
       for (int o = tid; o < w * wp; o += MLP_THREADS) {             // dW_l[n][k] = sum_b dz[b][n] a_{l-1}[b][k]
         const int k = o % wp, n = o / wp;
         float accv = 0.f;
@@ -559,6 +572,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         for (int b = 0; b < nb; ++b) accv += dz[b * dzs + n];
         gb[n] += sign * accv;
       }
+      SG_T1(7);
       if (l > 2) {
         // dA_{l-1} = dz W_l ; dZ_{l-1} = a (dA - sum_k a dA)   (softmax Jacobian)
         float* dn = dzbuf(cur ^ 1);
@@ -621,6 +635,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           for (int w16 = 0; w16 < 16; ++w16) accv += red[w16 * 128 + n];
           gb1[n] += sign * accv;
         }
+        SG_T1(8);
       }
     }
     if (L == 1) {                                                   // the output layer is layer 1: convert its fp32 dZ
@@ -637,7 +652,8 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     mlptc::fence_proxy_async();
     mlptc::worker_sync();
 
-    layer1_backward(m, ms, region, xs, sign, nb, R, g + m.leaf_off[0], overwrite);
+    SG_T1(2);
+    { SG_T0(); layer1_backward(m, ms, region, xs, sign, nb, R, g + m.leaf_off[0], overwrite); SG_T1(3); }
   }
 
   __device__ static void lik_pass(const BigModel& m, void* fam_smem, const float* theta, const float* center,
