@@ -168,7 +168,8 @@ int sgmcmc_kernel_step(sgmcmc_handle* h, sgmcmc_state* st, int32_t i, const uint
 /* ---- optional data-sharded mode (vector families, standard / CV estimators, no SGHMC) ----------
  * The ROWS of the table are split over ranks (for tables that do not fit one GPU); every rank runs every chain with the
  * same keys, draws the same minibatch indices (gradient_estimation.py:32 over ALL n_data rows), processes the ones it
- * holds, and the host all-reduces the [C, DS] minibatch sums once per step (DS = data_dim rounded up to 4).
+ * holds, and the host all-reduces the [C, DS] minibatch sums once per step (DS = sgmcmc_sum_width(h): the row stride of
+ * the table in floats - data_dim rounded up to 4, plus 4 for logreg with the CV estimator, whose rows carry center . x~).
  *   sgmcmc_create(cfg with n_data = TOTAL rows); sgmcmc_set_row_shard(h, row0, n_rows); sgmcmc_set_data(h, x, y) with
  *   n_rows rows; [CV: all-reduce sgmcmc_fullbatch_grad, then sgmcmc_set_centering_grad];
  *   sgmcmc_shard_init -> all-reduce sum -> { sgmcmc_shard_step(flags = STEP [| UPDATE2]) -> all-reduce sum } x K
@@ -176,6 +177,8 @@ int sgmcmc_kernel_step(sgmcmc_handle* h, sgmcmc_state* st, int32_t i, const uint
 #define SGMCMC_SHARD_UPDATE2 1   /* run the palindrome's update2 (baoab / badodab, coef_prev) after finishing the gradient */
 #define SGMCMC_SHARD_STEP 2      /* then do one transition (samplers.py:47-51) up to this rank's partial sums */
 int sgmcmc_set_row_shard(sgmcmc_handle* h, int64_t row0, int64_t n_rows);
+/* DS: floats per row of the device table == width of the sum_in / sum_out blocks below. */
+int sgmcmc_sum_width(const sgmcmc_handle* h);
 /* CV centre with an externally reduced full-batch gradient (gradient_estimation.py:70): device f32 [P] each. */
 int sgmcmc_set_centering_grad(sgmcmc_handle* h, const float* theta_hat, const float* grad, void* stream);
 /* init_fn (kernels.py:48-51) up to this rank's partial minibatch sums: sum_out device f32 [C, DS]. */

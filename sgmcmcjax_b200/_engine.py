@@ -270,7 +270,7 @@ class Engine:
     # ---- data-sharded mode --------------------------------------------------------------------
     @property
     def sum_width(self) -> int:
-        return (self.data_dim + 3) & ~3
+        return int(self.lib.sgmcmc_sum_width(self._handle))
 
     def shard_init(self, st, keys, sampler_mode: bool):
         """init_fn up to this shard's partial minibatch sums -> CUDA f32 [C, DS]."""

@@ -22,7 +22,7 @@ SHARD_UPDATE2, SHARD_STEP = 1, 2
 EXPORTS = [
     "sgmcmc_last_error", "sgmcmc_abi_version", "sgmcmc_launch_count", "sgmcmc_create", "sgmcmc_destroy", "sgmcmc_set_data",
     "sgmcmc_set_centering", "sgmcmc_fullbatch_grad", "sgmcmc_init", "sgmcmc_run", "sgmcmc_optimize", "sgmcmc_kernel_step",
-    "sgmcmc_set_row_shard", "sgmcmc_set_centering_grad", "sgmcmc_shard_init", "sgmcmc_shard_step",
+    "sgmcmc_set_row_shard", "sgmcmc_sum_width", "sgmcmc_set_centering_grad", "sgmcmc_shard_init", "sgmcmc_shard_step",
     "sgmcmc_minibatch_indices", "sgmcmc_normal", "sgmcmc_split", "sgmcmc_ksd_imq_partial", "sgmcmc_ksd_workspace_bytes", "sgmcmc_ksd_imq_tc",
 ]
 
@@ -91,6 +91,7 @@ def load(build_if_missing: bool = True):
         "sgmcmc_optimize": [vp, C.POINTER(State), i32, i32, vp, vp, vp],
         "sgmcmc_set_row_shard": [vp, i64, i64],
         "sgmcmc_set_centering_grad": [vp, vp, vp, vp],
+        "sgmcmc_sum_width": [vp],
         "sgmcmc_shard_init": [vp, C.POINTER(State), vp, i32, vp, vp],
         "sgmcmc_shard_step": [vp, C.POINTER(State), i32, vp, vp, i32, vp, vp, vp, vp],
         "sgmcmc_minibatch_indices": [C.POINTER(C.c_uint32), i64, i32, vp, vp],

@@ -142,7 +142,7 @@ __global__ void split_kernel(Key key, unsigned num, uint32_t* out) {
 
 namespace {
 
-template <int FAMILY, bool CV, int NCH, bool EXT>
+template <int FAMILY, int CV, int NCH, bool EXT>
 int launch_vec_kernel(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
   auto kern = sg::vec_sampler_kernel<FAMILY, CV, NCH, EXT>;
   const int PP = ((h->P > h->DS ? h->P : h->DS) + 3) & ~3;
@@ -153,7 +153,7 @@ int launch_vec_kernel(const sgmcmc_handle* h, const sg::VecRun& run, int warps, 
   return SGMCMC_OK;
 }
 
-template <int FAMILY, bool CV, int NCH>
+template <int FAMILY, int CV, int NCH>
 int launch_vec(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
   // the extended instantiation carries the row-sharded mode and the optimiser; the plain samplers run the lean one
   const bool ext = h->vm.own_n != h->vm.n_data || h->cfg.diffusion == SGMCMC_DIFF_ADAM_OPT || run.sum_in || run.sum_out;
@@ -161,7 +161,7 @@ int launch_vec(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStr
              : launch_vec_kernel<FAMILY, CV, NCH, false>(h, run, warps, stream);
 }
 
-template <int FAMILY, bool CV>
+template <int FAMILY, int CV>
 int launch_vec_nch(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
   switch (h->nch) {
     case 1: return launch_vec<FAMILY, CV, 1>(h, run, warps, stream);
@@ -189,11 +189,13 @@ int dispatch_vec(const sgmcmc_handle* h, const sg::VecRun& run, cudaStream_t str
   const int warps = choose_warps(h, run.st.n_chains);
   const bool cv = h->cfg.estimator != SGMCMC_EST_STANDARD;
   if (h->cfg.family == SGMCMC_FAMILY_GAUSSIAN_MEAN)
-    return cv ? launch_vec_nch<SGMCMC_FAMILY_GAUSSIAN_MEAN, true>(h, run, warps, stream)
-              : launch_vec_nch<SGMCMC_FAMILY_GAUSSIAN_MEAN, false>(h, run, warps, stream);
-  if (h->cfg.family == SGMCMC_FAMILY_LOGREG)
-    return cv ? launch_vec_nch<SGMCMC_FAMILY_LOGREG, true>(h, run, warps, stream)
-              : launch_vec_nch<SGMCMC_FAMILY_LOGREG, false>(h, run, warps, stream);
+    return cv ? launch_vec_nch<SGMCMC_FAMILY_GAUSSIAN_MEAN, 1>(h, run, warps, stream)
+              : launch_vec_nch<SGMCMC_FAMILY_GAUSSIAN_MEAN, 0>(h, run, warps, stream);
+  if (h->cfg.family == SGMCMC_FAMILY_LOGREG) {
+    if (h->vm.zc_f4 >= 0) return launch_vec_nch<SGMCMC_FAMILY_LOGREG, 2>(h, run, warps, stream);   // fixed centre: z_c column
+    return cv ? launch_vec_nch<SGMCMC_FAMILY_LOGREG, 1>(h, run, warps, stream)
+              : launch_vec_nch<SGMCMC_FAMILY_LOGREG, 0>(h, run, warps, stream);
+  }
   return fail(SGMCMC_E_UNSUPPORTED, "family not implemented by this build");
 }
 
@@ -414,6 +416,11 @@ int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
   sgmcmc_handle* h = new sgmcmc_handle();
   h->cfg = *cfg;
   h->DS = (cfg->data_dim + 3) & ~3;
+  // logreg with a fixed centre (estimator CV): one more float4 per row, whose .x holds center . x~ (csrc/vec_sampler.cuh,
+  // CV == 2).  A 100-float row already spans 13 sectors of 32 bytes at most offsets, so the wider row costs no traffic.
+  const int zc_f4 = h->DS / 4;
+  const bool zc = cfg->family == SGMCMC_FAMILY_LOGREG && cfg->estimator == SGMCMC_EST_CV && zc_f4 < 128;
+  if (zc) h->DS += 4;
   h->P = cfg->n_leaves * cfg->data_dim;
   const int f4 = h->DS / 4;
   h->nch = f4 <= 32 ? 1 : f4 <= 64 ? 2 : f4 <= 128 ? 4 : 8;
@@ -429,6 +436,7 @@ int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
   vm.n_leaves = cfg->n_leaves; vm.leaf_dim = cfg->data_dim; vm.P = h->P; vm.DS = h->DS;
   vm.n_data = (unsigned)cfg->n_data; vm.batch = (unsigned)cfg->batch;
   vm.own_lo = 0u; vm.own_n = vm.n_data;
+  vm.zc_f4 = zc ? zc_f4 : -1;
   vm.full_batch = (cfg->estimator == SGMCMC_EST_STANDARD && (int64_t)cfg->batch == cfg->n_data) ? 1 : 0;
   vm.leapfrog = cfg->leapfrog; vm.update_rate = cfg->update_rate;
   vm.scale = (float)cfg->n_data / (float)cfg->batch;
@@ -456,6 +464,8 @@ int sgmcmc_destroy(sgmcmc_handle* h) {
   delete h;
   return SGMCMC_OK;
 }
+
+static int write_zc_column(sgmcmc_handle* h, cudaStream_t s);
 
 int sgmcmc_set_data(sgmcmc_handle* h, const void* xv, const void* y, void* stream) {
   if (!h || !xv) return fail(SGMCMC_E_INVALID, "null argument");
@@ -493,7 +503,7 @@ int sgmcmc_set_data(sgmcmc_handle* h, const void* xv, const void* y, void* strea
   h->has_data = true;
   if (h->k2_xs) { cudaFree(h->k2_xs); h->k2_xs = nullptr; }      // operand copies of the previous table
   if (h->k2_xt) { cudaFree(h->k2_xt); h->k2_xt = nullptr; }
-  return SGMCMC_OK;
+  return write_zc_column(h, s);                                  // a new table under an existing centre
 }
 
 int sgmcmc_fullbatch_grad(sgmcmc_handle* h, const float* thetas, int32_t m, float* out, void* stream) {
@@ -513,6 +523,18 @@ int sgmcmc_fullbatch_grad(sgmcmc_handle* h, const float* thetas, int32_t m, floa
   return fullgrad_impl<SGMCMC_FAMILY_LOGREG>(h, thetas, m, out, s);
 }
 
+static int write_zc_column(sgmcmc_handle* h, cudaStream_t s) {
+  if (h->vm.zc_f4 < 0 || !h->has_center) return SGMCMC_OK;
+  const int blocks = h->num_sms * 8;
+  switch (h->nch) {
+    case 1: sg::zc_column_kernel<1><<<blocks, 256, 0, s>>>(h->rows, h->vm.own_n, h->DS, h->P, h->vm.zc_f4, h->cv_center); break;
+    case 2: sg::zc_column_kernel<2><<<blocks, 256, 0, s>>>(h->rows, h->vm.own_n, h->DS, h->P, h->vm.zc_f4, h->cv_center); break;
+    default: sg::zc_column_kernel<4><<<blocks, 256, 0, s>>>(h->rows, h->vm.own_n, h->DS, h->P, h->vm.zc_f4, h->cv_center); break;
+  }
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
+  return SGMCMC_OK;
+}
+
 int sgmcmc_set_centering(sgmcmc_handle* h, const float* theta_hat, void* stream) {
   if (!h || !theta_hat) return fail(SGMCMC_E_INVALID, "null argument");
   if (!h->has_data) return fail(SGMCMC_E_STATE, "sgmcmc_set_data has not been called");
@@ -527,7 +549,7 @@ int sgmcmc_set_centering(sgmcmc_handle* h, const float* theta_hat, void* stream)
   h->bm.cv_center = h->cv_center;
   h->bm.cv_grad = h->cv_grad;
   h->has_center = true;
-  return SGMCMC_OK;
+  return write_zc_column(h, s);
 }
 
 int sgmcmc_init(sgmcmc_handle* h, sgmcmc_state* st, const uint32_t* keys, int32_t sampler_mode, void* stream) {
@@ -625,8 +647,11 @@ int sgmcmc_set_centering_grad(sgmcmc_handle* h, const float* theta_hat, const fl
   h->vm.cv_center = h->cv_center; h->vm.cv_grad = h->cv_grad;
   h->bm.cv_center = h->cv_center; h->bm.cv_grad = h->cv_grad;
   h->has_center = true;
+  if (h->has_data) return write_zc_column(h, s);
   return SGMCMC_OK;
 }
+
+int sgmcmc_sum_width(const sgmcmc_handle* h) { return h ? h->DS : 0; }
 
 int sgmcmc_shard_init(sgmcmc_handle* h, sgmcmc_state* st, const uint32_t* keys, int32_t sampler_mode, float* sum_out,
                       void* stream) {

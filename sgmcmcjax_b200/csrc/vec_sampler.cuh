@@ -37,7 +37,12 @@ struct VecModel {
   unsigned own_lo, own_n;  // own_lo = 0, own_n = n_data unless the rows are sharded over ranks
   const float* cv_center;  // [P]  (CV only)
   const float* cv_grad;    // [P]  full-batch gradient at cv_center
+  int zc_f4;               // logreg SGLD-CV & co: float4 index of the row column holding center . x~ (CV == 2), else -1
 };
+// CV template parameter of the kernels: 0 = standard estimator; 1 = the centre's term is evaluated next to theta's from
+// the centre in shared memory (SVRG: the centre moves, per chain; gaussian_mean: free); 2 = logreg with a FIXED centre
+// (estimator CV): center . x~ is a per-row constant, written once into a spare column of the row table by
+// sgmcmc_set_centering (zc_column_kernel) and simply read with the row - no second dot product per row.
 
 struct VecRun {
   sgmcmc_state st;
@@ -137,7 +142,7 @@ __device__ __forceinline__ float reduce8(const float (&p)[8], int lane) {
 // EXT = false is the lean instantiation of the plain samplers (the bench kernel); the row-sharded mode and the
 // optimiser's log-posterior values live in the EXT = true instantiation only (they cost registers in the hot loop:
 // measured +6 % on the C2 step when they shared one kernel).
-template <int FAMILY, bool CV, int NCH, bool EXT = false>
+template <int FAMILY, int CV, int NCH, bool EXT = false>
 __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, const RandintPlan& plan,
                                          unsigned seq_base, unsigned count, const float* s_theta, const float* s_center,
                                          float* s_part, float* lp_part_in = nullptr) {
@@ -160,7 +165,7 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
     th[c] = ct[c] = acc[c];
     if (FAMILY == SGMCMC_FAMILY_LOGREG && ok[c]) {
       th[c] = reinterpret_cast<const float4*>(s_theta)[f4];
-      if (CV) ct[c] = reinterpret_cast<const float4*>(s_center)[f4];
+      if (CV == 1) ct[c] = reinterpret_cast<const float4*>(s_center)[f4];
     }
   }
 
@@ -213,6 +218,20 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
           if (ok[c] && r[u] >= 0) x[u][c] = __ldg(rows + (size_t)r[u] * row_f4 + lane + 32 * c);
         }
       }
+      // CV == 2: the lanes of quad u (where reduce8 leaves theta . x~ of row u) read that row's center . x~ themselves;
+      // the word shares a sector with the row's last float4, so this is one more request, not more traffic
+      float zc = 0.f;
+      if (CV == 2) {
+        int ru;
+        if (sharded) {
+          ru = r[0];
+#pragma unroll
+          for (int u = 1; u < 8; ++u) ru = (lane >> 2) == u ? r[u] : ru;
+        } else {
+          ru = __shfl_sync(FULL, src, base + (lane >> 2));
+        }
+        if (ru >= 0) zc = __ldg(m.rows + (size_t)ru * DS + 4 * m.zc_f4);
+      }
       if (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
@@ -241,7 +260,9 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
           for (int u = 0; u < 8; ++u)
             if (lane == 4 * u && r[u] >= 0) lpv -= fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
         }
-        if (CV) {
+        if (CV == 2) {
+          wgt += sigmoid_f(zc);
+        } else if (CV) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             p[u] = dot4(x[u][0], ct[0]);
@@ -267,6 +288,35 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
 #pragma unroll
     for (int o = 16; o; o >>= 1) lpv += __shfl_xor_sync(FULL, lpv, o);
     if (lane == 0) lp_part[warp] = lpv;
+  }
+}
+
+// rows[i][4 zc_f4] = center . x~_i for every row of the table, with exactly the arithmetic row_pass uses for theta . x~
+// (dot4 per lane and chunk, xor butterfly 16..1 = reduce8's tree), so that at theta == center the CV weights cancel
+// bit for bit like they do when both dots are taken in the kernel.
+template <int NCH>
+__global__ void zc_column_kernel(float* __restrict__ rows, unsigned n_rows, int DS, int P, int zc_f4, const float* __restrict__ center) {
+  const int lane = threadIdx.x & 31;
+  const int row_f4 = DS >> 2;
+  float4 ct[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int e = 4 * (lane + 32 * c);
+    ct[c] = make_float4(e < P ? center[e] : 0.f, e + 1 < P ? center[e + 1] : 0.f, e + 2 < P ? center[e + 2] : 0.f,
+                        e + 3 < P ? center[e + 3] : 0.f);
+  }
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+    const float4* row = reinterpret_cast<const float4*>(rows) + (size_t)r * row_f4;
+    float4 x[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) x[c] = (lane + 32 * c < row_f4) ? row[lane + 32 * c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float p = dot4(x[0], ct[0]);
+#pragma unroll
+    for (int c = 1; c < NCH; ++c) p += dot4(x[c], ct[c]);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) p += __shfl_xor_sync(FULL, p, o);
+    if (lane == 0) rows[(size_t)r * DS + 4 * zc_f4] = p;
   }
 }
 
@@ -305,7 +355,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // ---------------------------------------------------------------------------------------
-template <int FAMILY, bool CV, int NCH, bool EXT = false>
+template <int FAMILY, int CV, int NCH, bool EXT = false>
 struct ChainCtx {
   const VecModel& m;
   Smem s;
@@ -568,7 +618,7 @@ struct ChainCtx {
   }
 };
 
-template <int FAMILY, bool CV, int NCH, bool EXT = false>
+template <int FAMILY, int CV, int NCH, bool EXT = false>
 __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel m, const VecRun run) {
   extern __shared__ __align__(16) float smem_raw[];
   const int W = blockDim.x >> 5;
