@@ -24,7 +24,16 @@
 
 namespace sg {
 
-template <int FAMILY> struct BigThreads { static constexpr int value = 1024; };
+// PMF: CTA shape of one chain.  Measured on C4 (512 chains, SGNHT, ms per 4 steps): 1024 threads x 64 registers 1.37 (the
+// elementwise passes spill the values they load, so every load is waited for at once), 512 x 128 regs 1.15,
+// 2 CTAs x 256 threads x 128 regs with 4 threefry blocks staged per thread 1.08 (default), 4 CTAs x 128 threads 1.11.
+#ifndef SG_BIG_THREADS_PMF
+#define SG_BIG_THREADS_PMF 256
+#endif
+#ifndef SG_BIG_MINBLOCKS_PMF
+#define SG_BIG_MINBLOCKS_PMF 2
+#endif
+template <int FAMILY> struct BigThreads { static constexpr int value = SG_BIG_THREADS_PMF; static constexpr int min_blocks = SG_BIG_MINBLOCKS_PMF; };
 // MLP: warps 0..15 run the gradient (4 per TMEM lane quarter).  SG_MLP_PRODUCER_WARPS > 0 adds warps that generate
 // the NEXT update's Gaussian noise in the shadow of the GEMM phase (all warps run the elementwise passes); measured
 // in round 1 with 8 producer warps: the 85-register cap of a 768-thread CTA costs the GEMM phase more than the
@@ -32,7 +41,7 @@ template <int FAMILY> struct BigThreads { static constexpr int value = 1024; };
 #ifndef SG_MLP_PRODUCER_WARPS
 #define SG_MLP_PRODUCER_WARPS 0
 #endif
-template <> struct BigThreads<SGMCMC_FAMILY_MLP> { static constexpr int value = 512 + 32 * SG_MLP_PRODUCER_WARPS; };
+template <> struct BigThreads<SGMCMC_FAMILY_MLP> { static constexpr int value = 512 + 32 * SG_MLP_PRODUCER_WARPS; static constexpr int min_blocks = 1; };
 
 struct BigModel {
   int family, estimator, diffusion, flags;
@@ -122,8 +131,10 @@ __device__ __forceinline__ void leaf_pass(unsigned n, Key key, LD ld, ST st) {
 #pragma unroll 1
   for (; m0 + (U - 1) * bd < hf; m0 += U * bd) {
     Elt e0[U], e1[U];
+#ifndef SG_LEAF_RNG_FIRST
 #pragma unroll
     for (int u = 0; u < U; ++u) { e0[u] = ld(m0 + u * bd); e1[u] = ld(m0 + u * bd + h); }
+#endif
     // all U threefry blocks first, as independent chains side by side (ILP for the 20 dependent rounds of each), and
     // before the first use of a loaded value: the RNG work hides the memory latency of the loads above
     uint32_t w0[U], w1[U];
@@ -132,6 +143,10 @@ __device__ __forceinline__ void leaf_pass(unsigned n, Key key, LD ld, ST st) {
     float z0[U], z1[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) { z0[u] = bits_to_normal(w0[u]); z1[u] = bits_to_normal(w1[u]); }
+#ifdef SG_LEAF_RNG_FIRST
+#pragma unroll
+    for (int u = 0; u < U; ++u) { e0[u] = ld(m0 + u * bd); e1[u] = ld(m0 + u * bd + h); }
+#endif
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const unsigned m = m0 + u * bd;
@@ -197,7 +212,10 @@ __device__ __forceinline__ void produce_leaf_noise(unsigned n, Key key, float* d
   }
 }
 
-template <int FAMILY> struct BigUnroll { static constexpr int value = 2; };                  // 1024 threads: 64 registers
+#ifndef SG_BIG_UNROLL_PMF
+#define SG_BIG_UNROLL_PMF 4
+#endif
+template <int FAMILY> struct BigUnroll { static constexpr int value = SG_BIG_UNROLL_PMF; };  // 256 threads, 2 CTAs per SM: 128 registers
 #ifndef SG_BIG_UNROLL_MLP
 #define SG_BIG_UNROLL_MLP 4
 #endif
@@ -619,7 +637,7 @@ struct BigCtx {
 };
 
 template <int FAMILY>
-__global__ void __launch_bounds__(BigThreads<FAMILY>::value, 1) big_sampler_kernel(const __grid_constant__ BigModel m, const __grid_constant__ BigRun run) {
+__global__ void __launch_bounds__(BigThreads<FAMILY>::value, BigThreads<FAMILY>::min_blocks) big_sampler_kernel(const __grid_constant__ BigModel m, const __grid_constant__ BigRun run) {
   extern __shared__ __align__(16) uint8_t big_smem_raw[];
   BigSmem& s = *reinterpret_cast<BigSmem*>(big_smem_raw);
   void* fam_smem = big_smem_raw + ((sizeof(BigSmem) + 127) & ~(size_t)127);

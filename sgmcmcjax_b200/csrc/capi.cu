@@ -186,6 +186,9 @@ int choose_warps(const sgmcmc_handle* h, int n_chains) {
 }
 
 int dispatch_vec(const sgmcmc_handle* h, const sg::VecRun& run, cudaStream_t stream) {
+#ifdef SG_NO_VEC   // experiment builds of the big-state sampler only (tools/variant.py): skip the 36 vector instantiations
+  return fail(SGMCMC_E_UNSUPPORTED, "built with SG_NO_VEC");
+#else
   const int warps = choose_warps(h, run.st.n_chains);
   const bool cv = h->cfg.estimator != SGMCMC_EST_STANDARD;
   if (h->cfg.family == SGMCMC_FAMILY_GAUSSIAN_MEAN)
@@ -197,6 +200,7 @@ int dispatch_vec(const sgmcmc_handle* h, const sg::VecRun& run, cudaStream_t str
               : launch_vec_nch<SGMCMC_FAMILY_LOGREG, 0>(h, run, warps, stream);
   }
   return fail(SGMCMC_E_UNSUPPORTED, "family not implemented by this build");
+#endif
 }
 
 template <int FAMILY>
@@ -210,8 +214,12 @@ int launch_big(const sgmcmc_handle* h, const sg::BigRun& run, int blocks, cudaSt
 }
 
 int dispatch_big(const sgmcmc_handle* h, const sg::BigRun& run, int blocks, cudaStream_t stream) {
+#ifndef SG_NO_PMF
   if (h->cfg.family == SGMCMC_FAMILY_PMF) return launch_big<SGMCMC_FAMILY_PMF>(h, run, blocks, stream);
+#endif
+#ifndef SG_NO_MLP
   if (h->cfg.family == SGMCMC_FAMILY_MLP) return launch_big<SGMCMC_FAMILY_MLP>(h, run, blocks, stream);
+#endif
   return fail(SGMCMC_E_UNSUPPORTED, "family not implemented by this build");
 }
 

@@ -1,5 +1,5 @@
 """Profiling driver for the big-state sampler: a few launches of one configuration (used under ncu).
-usage: prof_big.py mlp_psgld|mlp_sghmc|pmf_sgnht [chains] [steps_per_launch] [launches]"""
+usage: prof_big.py mlp_psgld|mlp_sghmc|pmf_sgnht|pmf_badodabcv [chains] [steps_per_launch] [launches]"""
 import sys, numpy as np, torch
 sys.path.insert(0, "/root/repo")
 from sgmcmcjax_b200 import _native, random, samplers
@@ -25,7 +25,10 @@ else:
     ij = torch.stack([torch.randint(0, nu, (Np,), device="cuda"), torch.randint(0, ni, (Np,), device="cuda")], 1).int()
     rt = torch.randint(1, 6, (Np,), device="cuda").float()
     U = 0.1 * random.normal(random.PRNGKey(3), (nu, r)); V = 0.1 * random.normal(random.PRNGKey(4), (ni, r))
-    s = samplers.build_sgnht_sampler(1e-5, F.loglikelihood, F.logprior, (ij, rt), 1000, pbar=False)
+    if which == "pmf_badodabcv":
+        s = samplers.build_badodabCV_sampler(1e-5, F.loglikelihood, F.logprior, (ij, rt), 1000, (U, V), pbar=False)
+    else:
+        s = samplers.build_sgnht_sampler(1e-5, F.loglikelihood, F.logprior, (ij, rt), 1000, pbar=False)
     s.engine.flatten_params((U, V), None)
     flat = torch.cat([U.reshape(-1), V.reshape(-1)])
 eng = s.engine
