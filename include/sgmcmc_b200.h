@@ -153,6 +153,18 @@ int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k,
                const sgmcmc_step_coef* coef, int32_t coef_stride, float* samples,
                int64_t sample_chain_stride, void* stream);
 
+/* sgmcmc_run with thinning and on-device posterior summaries (the reference keeps every state,
+ * samplers.py:57).  Iteration s = 0 .. k-1 of the launch is KEPT when (s + 1) % thin == 0 (thin >= 1; keep launches
+ * aligned: i0 % thin == 0 and k % thin == 0 make chunked runs equal one long run).  A kept state goes to sample slot
+ * (s + 1) / thin - 1 of `samples` (NULL: nothing is stored; sample_chain_stride == 0 means the dense [C, k / thin, P])
+ * and, when `moments` is not NULL, is accumulated around a caller-chosen reference point r (device f32 [C, 3, P]:
+ * plane 2 holds r, e.g. the initial parameters; planes 0 and 1 are zeroed by the caller before the first launch):
+ * moments[c][0][e] += theta_e - r_e, moments[c][1][e] += (theta_e - r_e)^2.  Mean = r + S0 / n and marginal variance
+ * = S1 / n - (S0 / n)^2 follow on the host; the shift keeps the fp32 sums free of cancellation. */
+int sgmcmc_run_thinned(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k,
+                       const sgmcmc_step_coef* coef, int32_t coef_stride, int32_t thin, float* samples,
+                       int64_t sample_chain_stride, float* moments, void* stream);
+
 /* K iterations of the optimiser loop of optimizer.py:41-60 (vector families; the handle is created with
  * SGMCMC_DIFF_ADAM_OPT and the standard estimator): key, subkey = split(key); value and gradient of log_post on the
  * minibatch drawn with subkey; optax.adam ascent step.  state: theta (params), aux1 / aux2 (Adam moments, zero at the

@@ -246,11 +246,18 @@ class Engine:
         _native.check(self.lib.sgmcmc_init(self._handle, C.byref(cs), _vp(keys), 1 if sampler_mode else 0,
                                            self._stream()))
 
-    def run(self, st, i0: int, k: int, samples=None, sample_chain_stride: int = 0):
+    def run(self, st, i0: int, k: int, samples=None, sample_chain_stride: int = 0, thin: int = 1, moments=None):
+        """k iterations from i0.  thin > 1 keeps every thin-th state (slot (s + 1) // thin - 1 of `samples`); `moments`
+        (CUDA f32 [C, 3, P]: planes 0, 1 zeroed, plane 2 = a reference point) accumulates the sum and sum of squares of
+        (kept state - reference)."""
         coef, stride = self._coefs(i0, k)
         cs = self._cstate(st)
-        _native.check(self.lib.sgmcmc_run(self._handle, C.byref(cs), int(i0), int(k), _vp(coef), stride,
-                                          _vp(samples), int(sample_chain_stride), self._stream()))
+        if thin == 1 and moments is None:
+            _native.check(self.lib.sgmcmc_run(self._handle, C.byref(cs), int(i0), int(k), _vp(coef), stride,
+                                              _vp(samples), int(sample_chain_stride), self._stream()))
+        else:
+            _native.check(self.lib.sgmcmc_run_thinned(self._handle, C.byref(cs), int(i0), int(k), _vp(coef), stride, int(thin),
+                                                      _vp(samples), int(sample_chain_stride), _vp(moments), self._stream()))
         return coef   # keep alive until the caller synchronises
 
     def optimize(self, st, i0: int, k: int, lp_out=None):

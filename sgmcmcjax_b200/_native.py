@@ -21,7 +21,7 @@ SHARD_UPDATE2, SHARD_STEP = 1, 2
 
 EXPORTS = [
     "sgmcmc_last_error", "sgmcmc_abi_version", "sgmcmc_launch_count", "sgmcmc_create", "sgmcmc_destroy", "sgmcmc_set_data",
-    "sgmcmc_set_centering", "sgmcmc_fullbatch_grad", "sgmcmc_init", "sgmcmc_run", "sgmcmc_optimize", "sgmcmc_kernel_step",
+    "sgmcmc_set_centering", "sgmcmc_fullbatch_grad", "sgmcmc_init", "sgmcmc_run", "sgmcmc_run_thinned", "sgmcmc_optimize", "sgmcmc_kernel_step",
     "sgmcmc_set_row_shard", "sgmcmc_sum_width", "sgmcmc_set_centering_grad", "sgmcmc_shard_init", "sgmcmc_shard_step",
     "sgmcmc_minibatch_indices", "sgmcmc_normal", "sgmcmc_split", "sgmcmc_ksd_imq_partial", "sgmcmc_ksd_workspace_bytes", "sgmcmc_ksd_imq_tc",
 ]
@@ -87,6 +87,7 @@ def load(build_if_missing: bool = True):
         "sgmcmc_fullbatch_grad": [vp, vp, i32, vp, vp],
         "sgmcmc_init": [vp, C.POINTER(State), vp, i32, vp],
         "sgmcmc_run": [vp, C.POINTER(State), i32, i32, vp, i32, vp, i64, vp],
+        "sgmcmc_run_thinned": [vp, C.POINTER(State), i32, i32, vp, i32, i32, vp, i64, vp, vp],
         "sgmcmc_kernel_step": [vp, C.POINTER(State), i32, vp, vp, vp],
         "sgmcmc_optimize": [vp, C.POINTER(State), i32, i32, vp, vp, vp],
         "sgmcmc_set_row_shard": [vp, i64, i64],

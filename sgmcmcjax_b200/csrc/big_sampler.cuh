@@ -67,6 +67,8 @@ struct BigRun {
   int coef_stride;
   float* samples;
   size_t sample_chain_stride;
+  int thin;                  // keep every thin-th state of the launch (0 / 1: all), sgmcmc_run_thinned
+  float* moments;            // [C][3][P]: sum and sum of squares of (kept state - plane 2), or nullptr
   const uint32_t* step_keys;
   int mode;                  // 0 run, 1 init_fn, 2 init + sampler split, 3 full-batch gradient at fg_thetas
   const uint32_t* init_keys;
@@ -695,8 +697,17 @@ __global__ void __launch_bounds__(BigThreads<FAMILY>::value, BigThreads<FAMILY>:
         if (sidx + 1 < run.K) { Key nk2; split2(carry, nk2, next_sub); has_next = true; }   // peek at the next iteration's key
       }
       // get_params after the transition: the sample is written by the diffusion pass that produces it
-      ctx.transition(i, sub, cf, run.samples ? run.samples + (size_t)c * run.sample_chain_stride + (size_t)sidx * P : nullptr,
+      const bool thinned = run.thin > 1;
+      const bool kept = !thinned || (sidx + 1) % run.thin == 0;
+      const int slot = thinned ? (sidx + 1) / run.thin - 1 : sidx;
+      ctx.transition(i, sub, cf, (run.samples && kept) ? run.samples + (size_t)c * run.sample_chain_stride + (size_t)slot * P : nullptr,
                      next_sub, has_next);
+      if (run.moments && kept) {                                // posterior summaries: one more pass over the kept state
+        __syncthreads();
+        float* mo = run.moments + (size_t)c * 3 * P;
+        for (size_t e = threadIdx.x; e < P; e += blockDim.x) { const float x = ctx.theta[e] - mo[2 * P + e]; mo[e] += x; mo[P + e] = fmaf(x, x, mo[P + e]); }
+        __syncthreads();
+      }
     }
     ctx.finalize();                                             // the state's param_grad is the finalised gradient
   }

@@ -156,7 +156,7 @@ int launch_vec_kernel(const sgmcmc_handle* h, const sg::VecRun& run, int warps, 
 template <int FAMILY, int CV, int NCH>
 int launch_vec(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
   // the extended instantiation carries the row-sharded mode and the optimiser; the plain samplers run the lean one
-  const bool ext = h->vm.own_n != h->vm.n_data || h->cfg.diffusion == SGMCMC_DIFF_ADAM_OPT || run.sum_in || run.sum_out;
+  const bool ext = h->vm.own_n != h->vm.n_data || h->cfg.diffusion == SGMCMC_DIFF_ADAM_OPT || run.sum_in || run.sum_out || run.moments;
   return ext ? launch_vec_kernel<FAMILY, CV, NCH, true>(h, run, warps, stream)
              : launch_vec_kernel<FAMILY, CV, NCH, false>(h, run, warps, stream);
 }
@@ -577,9 +577,16 @@ int sgmcmc_init(sgmcmc_handle* h, sgmcmc_state* st, const uint32_t* keys, int32_
 
 int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const sgmcmc_step_coef* coef,
                int32_t coef_stride, float* samples, int64_t sample_chain_stride, void* stream) {
+  return sgmcmc_run_thinned(h, st, i0, k, coef, coef_stride, 1, samples, sample_chain_stride, nullptr, stream);
+}
+
+int sgmcmc_run_thinned(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const sgmcmc_step_coef* coef,
+                       int32_t coef_stride, int32_t thin, float* samples, int64_t sample_chain_stride, float* moments,
+                       void* stream) {
   int rc = check_state(h, st);
   if (rc != SGMCMC_OK) return rc;
   if (k < 0 || i0 < 0) return fail(SGMCMC_E_INVALID, "i0 and k must be non-negative");
+  if (thin < 1) return fail(SGMCMC_E_INVALID, "thin must be >= 1");
   if (!coef || (coef_stride != 0 && coef_stride != 1)) return fail(SGMCMC_E_INVALID, "bad step coefficients");
   if (!st->key) return fail(SGMCMC_E_INVALID, "state.key is required");
   if (h->cfg.diffusion == SGMCMC_DIFF_ADAM_OPT) return fail(SGMCMC_E_STATE, "this handle is an optimiser: use sgmcmc_optimize");
@@ -587,7 +594,8 @@ int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const 
   if (h->big) {
     sg::BigRun run{};
     run.st = *st; run.i0 = i0; run.K = k; run.coef = coef; run.coef_stride = coef_stride; run.samples = samples;
-    run.sample_chain_stride = sample_chain_stride > 0 ? (size_t)sample_chain_stride : (size_t)k * h->P;
+    run.sample_chain_stride = sample_chain_stride > 0 ? (size_t)sample_chain_stride : (size_t)(k / thin) * h->P;
+    run.thin = thin; run.moments = moments;
     if (SG_MLP_PRODUCER_WARPS > 0 && h->cfg.family == SGMCMC_FAMILY_MLP && k > 1 && !env_int("SGMCMC_NO_LOOKAHEAD", 0)) {
       // look-ahead noise scratch of the optional producer warps (stream-ordered reuse: one stream per handle)
       const size_t need = (size_t)st->n_chains * h->P;
@@ -603,7 +611,8 @@ int sgmcmc_run(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, const 
   }
   sg::VecRun run{};
   run.st = *st; run.i0 = i0; run.K = k; run.coef = coef; run.coef_stride = coef_stride; run.samples = samples;
-  run.sample_chain_stride = sample_chain_stride > 0 ? (size_t)sample_chain_stride : (size_t)k * h->P;
+  run.sample_chain_stride = sample_chain_stride > 0 ? (size_t)sample_chain_stride : (size_t)(k / thin) * h->P;
+  run.thin = thin; run.moments = moments;
   return dispatch_vec(h, run, (cudaStream_t)stream);
 }
 

@@ -58,6 +58,8 @@ struct VecRun {
   const float* sum_in;       // [C][DS] all-reduced sums of the previous estimate: the gradient is finished from them first
   float* sum_out;            // [C][DS] this rank's partial sums of the new estimate (the gradient is NOT finished)
   float* lp_out;             // [C][K] log-posterior values of the optimizer iterations (SGMCMC_DIFF_ADAM_OPT), else nullptr
+  int thin;                  // keep every thin-th state of the launch (0 / 1: all), sgmcmc_run_thinned
+  float* moments;            // [C][3][P]: sum and sum of squares of (kept state - plane 2), or nullptr (EXT kernel)
   int shard_flags;           // SHARD_UPDATE2: run the palindrome's update2 (coef_prev) after finishing the gradient;
   const sgmcmc_step_coef* coef_prev;   //   SHARD_STEP: then do one transition and leave its partial sums in sum_out
 };
@@ -698,9 +700,16 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
         continue;
       }
       ctx.transition(i, sub, cf);
+      const bool thinned = run.thin > 1;
+      if (thinned && (sidx + 1) % run.thin != 0) continue;
       if (run.samples) {
-        float* dst = run.samples + (size_t)c * run.sample_chain_stride + (size_t)sidx * P;
+        const int slot = thinned ? (sidx + 1) / run.thin - 1 : sidx;
+        float* dst = run.samples + (size_t)c * run.sample_chain_stride + (size_t)slot * P;
         for (int e = threadIdx.x; e < P; e += blockDim.x) dst[e] = s.theta[e];
+      }
+      if (EXT && run.moments) {
+        float* mo = run.moments + (size_t)c * 3 * P;
+        for (int e = threadIdx.x; e < P; e += blockDim.x) { const float x = s.theta[e] - mo[2 * P + e]; mo[e] += x; mo[P + e] = fmaf(x, x, mo[P + e]); }
       }
     }
   }

@@ -92,6 +92,79 @@ def _side_stream(torch):
     return _side[dev]
 
 
+def _summaries_sampler(eng, thin: int, summaries: bool, store_samples: bool, pbar: bool) -> Callable:
+    """Sampler with thinning and on-device posterior summaries (not in the reference, whose scan
+    stacks every state, samplers.py:57).  ``sampler(key, Nsamples, params)`` runs Nsamples iterations and keeps the states
+    after iterations thin, 2 thin, ...: returns the Nsamples // thin kept samples (None with ``store_samples=False``), or
+    ``(samples, {"mean": tree, "var": tree, "count": n})`` with ``summaries=True`` - mean and marginal variance of the kept
+    states per chain, accumulated inside the sampling kernel (no [C, K, P] buffer is needed for them)."""
+    if thin < 1:
+        raise ValueError("thin must be >= 1")
+
+    def sampler(key, Nsamples: int, params):
+        torch = _native.require_cuda()
+        keys, kb = keys_to_device(key)
+        flat, treedef, pb = eng.flatten_params(params, broadcast_chains=keys.shape[0])
+        if keys.shape[0] != flat.shape[0]:
+            raise ValueError("need one key per chain")
+        batched = kb or pb
+        n_chains, nsamp = flat.shape[0], int(Nsamples)
+        nkeep = nsamp // thin
+        st = eng.new_state(flat)
+        eng.init(st, keys, sampler_mode=True)
+        samples = torch.empty((n_chains, nkeep, eng.P), dtype=torch.float32, device="cuda") if store_samples else None
+        moments = None
+        if summaries:                                                  # planes: sum (theta - r), sum (theta - r)^2, r = theta_0
+            moments = torch.zeros((n_chains, 3, eng.P), dtype=torch.float32, device="cuda")
+            moments[:, 2] = st["theta"]
+        keep = []
+        # launches are multiples of `thin` so that the kept set does not depend on the chunking
+        chunk = nsamp if not pbar else max(nsamp // 20, 1)
+        chunk = max(-(-chunk // thin) * thin, thin)
+        bar = None
+        if pbar and nsamp > 0:
+            from tqdm.auto import tqdm
+
+            bar = tqdm(total=nsamp)
+        for i0 in range(0, nkeep * thin, chunk):
+            k = min(chunk, nkeep * thin - i0)
+            dst = samples[:, i0 // thin:] if store_samples else None
+            keep.append(eng.run(st, i0, k, dst, sample_chain_stride=nkeep * eng.P if store_samples else 0, thin=thin,
+                                moments=moments))
+            if bar is not None:
+                torch.cuda.current_stream().synchronize()
+                bar.update(k)
+        if nsamp > nkeep * thin:                                       # trailing iterations that keep nothing
+            keep.append(eng.run(st, nkeep * thin, nsamp - nkeep * thin, None))
+        if bar is not None:
+            bar.update(nsamp - nkeep * thin)
+            bar.close()
+        torch.cuda.current_stream().synchronize()
+        like = _tree.flatten(params)[0][0]
+
+        def as_tree(flat_block, lead):
+            tree = eng.unflatten_params(flat_block, treedef, lead)
+            leaves, td = _tree.flatten(tree)
+            return _tree.unflatten(td, [_like(l, like) for l in leaves])
+
+        out = None
+        if store_samples:
+            out = as_tree(samples if batched else samples[0], (n_chains, nkeep) if batched else (nkeep,))
+        if not summaries:
+            return out
+        n = max(nkeep, 1)
+        shift = moments[:, 0].double() / n
+        mean = moments[:, 2].double() + shift
+        var = (moments[:, 1].double() / n - shift * shift).clamp_min(0.0)
+        lead = (n_chains,) if batched else ()
+        summ = {"mean": as_tree((mean if batched else mean[0]).float(), lead),
+                "var": as_tree((var if batched else var[0]).float(), lead), "count": nkeep}
+        return out, summ
+
+    sampler.engine = eng
+    return sampler
+
+
 def _build_native_sampler(init_fn: Callable, as_list: bool, pbar: bool) -> Callable:
     eng = init_fn.engine
 
@@ -152,7 +225,12 @@ def sgmcmc_sampler(build_kernel_fn: Callable) -> Callable:
     def wrapper(*args, **kwargs):
         compiled = kwargs.pop("compiled", True)
         pbar = kwargs.pop("pbar", True)
+        thin = int(kwargs.pop("thin", 1))                    # extensions (keyword-only; defaults = the reference's behaviour)
+        summaries = bool(kwargs.pop("summaries", False))
+        store_samples = bool(kwargs.pop("store_samples", True))
         init_fn, _kernel, _get_params = build_kernel_fn(*args, **kwargs)
+        if thin != 1 or summaries or not store_samples:
+            return _summaries_sampler(init_fn.engine, thin, summaries, store_samples, pbar)
         return _build_native_sampler(init_fn, as_list=not compiled, pbar=pbar)
 
     return wrapper

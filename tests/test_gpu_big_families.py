@@ -217,6 +217,31 @@ def test_sampler_container_and_trajectory(cuda, name, dt, kw, case):
         close(g, r, rtol=1e-4, what=f"{name}/{case} trajectory")
 
 
+@pytest.mark.parametrize("name,dt,kw", [KERNELS[3], KERNELS[5], KERNELS[10]], ids=["psgld", "sgnht", "sghmc"])
+@pytest.mark.parametrize("case", ["mlp", "pmf"])
+def test_thinning_and_on_device_summaries(cuda, name, dt, kw, case):
+    """sgmcmc_run_thinned on the big-state kernel: kept states == every 3rd state of the unthinned run; moments == numpy."""
+    from sgmcmcjax_b200 import samplers as NS
+
+    make, to_params, batch = CASES[case]
+    fam, fns, data, th0 = make()
+    args = ([dt, kw["L"]] if "L" in kw else [dt]) + [fns[0], fns[1], data, batch]
+    build = getattr(NS, f"build_{name}_sampler")
+    full = tree_leaves(build(*args, pbar=False)(P.PRNGKey(4), 14, to_params(th0)))
+    kept, summ = build(*args, pbar=False, thin=3, summaries=True)(P.PRNGKey(4), 14, to_params(th0))
+    assert summ["count"] == 4
+    for f, k, mu, var, t0 in zip(full, tree_leaves(kept), tree_leaves(summ["mean"]), tree_leaves(summ["var"]), th0):
+        assert k.shape == (4,) + f.shape[1:]
+        if case == "pmf":           # float atomics in the gradient: two runs agree to rounding, not bit for bit
+            close(k, f[2::3][:4], rtol=1e-5, what="pmf thinned")
+        else:
+            assert np.array_equal(k, f[2::3][:4])
+        close(mu, k.astype(np.float64).mean(0), rtol=1e-6, what="on-device mean")
+        # one-pass variance around theta_0 in fp32: exact to ~1e-7 of the mean-square displacement from theta_0
+        msd = ((k.astype(np.float64) - t0) ** 2).mean(0)
+        assert (np.abs(var - k.astype(np.float64).var(0)) <= 1e-5 * msd + 1e-14).all()
+
+
 @pytest.mark.parametrize("case", ["mlp", "pmf"])
 def test_multichain_equals_single_chains(cuda, case):
     make, to_params, batch = CASES[case]

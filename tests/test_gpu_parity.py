@@ -355,6 +355,35 @@ def test_pbar_chunked_launches_equal_single_launch(cuda):
     assert np.array_equal(a, b)                                    # resume is bit-reproducible
 
 
+@pytest.mark.parametrize("name,dt,kw", [KERNELS[0], KERNELS[1], KERNELS[10]], ids=["sgld", "sgldCV", "sghmc"])
+def test_thinning_and_on_device_summaries(cuda, name, dt, kw):
+    """SURVEY section 8 f3 (sgmcmc_run_thinned): the kept states are exactly every thin-th state of the unthinned run, for
+    any launch chunking; the on-device mean / variance equal numpy's over the kept states; the oracle agrees."""
+    fam, fns, data, th0 = logreg_case()
+    ok, full_sampler = build_sampler_pair(name, dt, kw, fam, fns, data, 100, th0)
+    _, thin_sampler = build_sampler_pair(name, dt, kw, fam, fns, data, 100, th0, thin=4, summaries=True)
+    full = full_sampler(P.PRNGKey(5), 42, th0[0])
+    kept, summ = thin_sampler(P.PRNGKey(5), 42, th0[0])
+    assert kept.shape == (10, th0[0].shape[0]) and summ["count"] == 10
+    assert np.array_equal(kept, full[3::4][:10])
+    ref, _, _ = S.run_sampler(ok, P.PRNGKey(5), 42, th0)
+    close(kept, ref[0][3::4][:10], rtol=2e-4, what=f"{name} thinned vs oracle")
+    close(summ["mean"], kept.astype(np.float64).mean(0), rtol=1e-6, what="on-device mean")
+    np.testing.assert_allclose(summ["var"], kept.astype(np.float64).var(0), rtol=2e-3, atol=1e-9)
+    # progress-bar chunking (launches rounded to multiples of thin) keeps the same states
+    import sgmcmcjax_b200.samplers as NS
+    args = [dt] + ([kw["L"]] if "L" in kw else []) + [fns[0], fns[1], data, 100] + ([th0[0]] if kw.get("cv") else [])
+    chunked = getattr(NS, f"build_{name}_sampler")(*args, pbar=True, thin=4)(P.PRNGKey(5), 42, th0[0])
+    assert np.array_equal(chunked, kept)
+    # many chains, summaries only: no sample buffer at all
+    keys = P.split(P.PRNGKey(6), 5)
+    only = getattr(NS, f"build_{name}_sampler")(*args, pbar=False, summaries=True, store_samples=False)
+    none, s5 = only(keys, 30, np.tile(th0[0], (5, 1)))
+    assert none is None and s5["mean"].shape == (5, th0[0].shape[0]) and s5["count"] == 30
+    one = full_sampler(keys[2], 30, th0[0])
+    close(s5["mean"][2], one.astype(np.float64).mean(0), rtol=1e-6, what="summaries-only mean")
+
+
 def test_multichain_equals_independent_single_chains(cuda):
     """vmap(sampler, in_axes=(0, None, 0)) semantics: chain c == single-chain run with keys[c]."""
     from sgmcmcjax_b200 import samplers as NS
