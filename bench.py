@@ -87,7 +87,7 @@ def cpu_data():
         rng = np.random.default_rng(42)
         theta = (np.sqrt(10.0) * rng.standard_normal(DIM)).astype(np.float32)
         X = rng.standard_normal((N_DATA, DIM), dtype=np.float32)
-        y = (rng.random(N_DATA) < 1.0 / (1.0 + np.exp(-(X @ theta)))).astype(np.int32)
+        y = (rng.random(N_DATA) < 0.5 * (1.0 + np.tanh(0.5 * (X @ theta)))).astype(np.int32)      # sigmoid without overflow
         _CPU_DATA = (X, y, theta)
     return _CPU_DATA
 
