@@ -452,6 +452,39 @@ def test_fullbatch_grad_matches_oracle_and_reference_test(cuda):
             close(got[m], ref, rtol=2e-5, what="fullbatch grad")
 
 
+@pytest.mark.parametrize("d", [3, 100, 124, 128, 250])
+def test_cv_row_layout_with_center_column(cuda, d):
+    """logreg + CV estimator: the row table carries center . x~ in an extra float4 (csrc/vec_sampler.cuh CV == 2).  The
+    full-batch gradient paths (SIMT and tensor-core) must ignore that column, a step must match the oracle at widths
+    where the extra float4 starts a new 32-lane chunk, and re-centring must refresh the column."""
+    import torch
+
+    from sgmcmcjax_b200 import kernels as NK
+
+    fam, fns, data, th0 = logreg_case(n=1500, d=d, seed=d)
+    ok, (init_fn, kernel, get_params) = build_pair("sgldCV", 1e-4, {"cv": True}, fam, fns, data, 64, th0)
+    plain, _, _ = NK.build_sgld_kernel(1e-5, fns[0], fns[1], data, 64)
+    rng = np.random.default_rng(d)
+    for m in (2, 70):                                              # SIMT path, tensor-core path
+        thetas = torch.from_numpy((th0[0][None, :] + 0.05 * rng.normal(size=(m, d))).astype(np.float32)).cuda()
+        a, b = init_fn.engine.fullbatch_grad(thetas).cpu().numpy(), plain.engine.fullbatch_grad(thetas).cpu().numpy()
+        close(a, b, rtol=2e-5, what=f"K2 with the centre column, m={m}")     # summation order differs (chunking, atomics)
+    key = P.PRNGKey(d)
+    start = [(th0[0] * np.float32(1.01)).astype(np.float32)]
+    ost, nst = ok.init_fn(key, start), init_fn(key, start[0])
+    compare_state(ost, nst, get_params, f"cv init d={d}")
+    for i in range(3):
+        k = P.split(P.PRNGKey(100 + i))[1]
+        nst = kernel(i, k, inject(ost, nst))
+        ost = ok.kernel(i, k, ost)
+        g_ref, g_got = compare_state(ost, nst, get_params, f"cv step {i} d={d}")
+        assert np.abs(g_got - g_ref).max() / max(np.abs(g_ref).max(), 1.0) <= grad_tol("sgldCV")
+    # at theta == centre the two weights cancel bit for bit: the gradient estimate IS the full-batch gradient
+    _, g0 = compare_state(ok.init_fn(key, th0), init_fn(key, th0[0]), get_params, "cv at centre")
+    fb = init_fn.engine.fullbatch_grad(torch.from_numpy(th0[0][None, :]).cuda()).cpu().numpy()[0]
+    assert np.array_equal(g0, fb)
+
+
 @pytest.mark.parametrize("n,d,m", [(3000, 100, 130), (777, 10, 64), (5000, 37, 300), (128, 100, 128), (20000, 100, 1000)])
 def test_fullbatch_grad_tensor_core_path(cuda, n, d, m):
     """K2 at many parameter vectors (csrc/k2_gemm.cuh: two tcgen05 3xTF32 contractions, the imq_KSD `grads` producer)
