@@ -384,6 +384,20 @@ def test_thinning_and_on_device_summaries(cuda, name, dt, kw):
     close(s5["mean"][2], one.astype(np.float64).mean(0), rtol=1e-6, what="summaries-only mean")
 
 
+def test_rhat_from_on_device_summaries(cuda):
+    """diagnostics.rhat on the kernel's per-chain moments == R-hat of the stored draws (README Gaussian, 8 chains)."""
+    from sgmcmcjax_b200 import diagnostics as D
+    from sgmcmcjax_b200 import samplers as NS
+
+    fam, fns, data, th0 = gauss_case(n=2000, d=5)
+    keys = P.split(P.PRNGKey(11), 8)
+    start = np.tile(th0[0], (8, 1)) + np.float32(0.3) * P.normal(P.PRNGKey(12), (8, 5))
+    kept, summ = NS.build_sgld_sampler(1e-4, fns[0], fns[1], data, 100, pbar=False, summaries=True)(keys, 400, start)
+    want = D.rhat_from_samples(kept)
+    np.testing.assert_allclose(D.rhat(summ), want, rtol=1e-4)
+    assert (want < 1.2).all()                                     # dt = 1e-4, 400 steps: the chains have mixed
+
+
 def test_multichain_equals_independent_single_chains(cuda):
     """vmap(sampler, in_axes=(0, None, 0)) semantics: chain c == single-chain run with keys[c]."""
     from sgmcmcjax_b200 import samplers as NS

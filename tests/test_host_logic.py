@@ -70,3 +70,24 @@ def test_no_cpu_fallback():
 
         build_sgld_sampler(1e-5, models.gaussian_mean.loglikelihood, models.gaussian_mean.logprior,
                            (np.zeros((10, 4), np.float32),), 2)
+
+
+def test_rhat_from_moments_matches_textbook_formula():
+    """sgmcmcjax_b200/diagnostics.py: Gelman-Rubin R-hat from per-chain moments == the formula on the stored draws."""
+    from sgmcmcjax_b200 import diagnostics as D
+
+    rng = np.random.default_rng(0)
+    draws = rng.normal(size=(6, 200, 3)) + np.array([0.0, 0.0, 1.0])[None, None, :] * np.arange(6)[:, None, None]
+    n = draws.shape[1]
+    w = draws.var(axis=1, ddof=1).mean(axis=0)
+    b = n * draws.mean(axis=1).var(axis=0, ddof=1)
+    want = np.sqrt(((n - 1) / n * w + b / n) / w)
+    got = D.rhat_from_moments(draws.mean(axis=1), draws.var(axis=1), n)
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    np.testing.assert_allclose(D.rhat_from_samples(draws), want, rtol=1e-12)
+    assert got[0] < 1.05 and got[2] > 2.0                     # mixed / separated chains
+    summ = {"mean": [draws.mean(axis=1), draws.mean(axis=1)[:, :1]], "var": [draws.var(axis=1), draws.var(axis=1)[:, :1]], "count": n}
+    out = D.rhat(summ)
+    assert isinstance(out, list) and out[0].shape == (3,) and out[1].shape == (1,)
+    with pytest.raises(ValueError):
+        D.rhat_from_moments(draws.mean(axis=1)[:1], draws.var(axis=1)[:1], n)
