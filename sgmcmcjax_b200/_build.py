@@ -10,12 +10,17 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libsgmcmc_b200.so")
-SOURCES = ["capi.cu"]
-HEADERS = ["prng.cuh", "vec_sampler.cuh", "ksd.cuh", "ksd_tc.cuh", "big_sampler.cuh", "mlp_grad.cuh", "k2_gemm.cuh"]
+# capi.cu: the C ABI, KSD and K2 kernels; the sampler kernels' template instantiations are spread over the other
+# translation units so that they compile in parallel (one nvcc -c each), then one link.
+SOURCES = ["capi.cu", "vec_inst_gauss.cu", "vec_inst_logreg.cu", "vec_inst_logreg_svrg.cu", "vec_inst_logreg_cv.cu",
+           "big_inst_mlp.cu", "big_inst_pmf.cu"]
+HEADERS = ["prng.cuh", "vec_sampler.cuh", "vec_launch.cuh", "ksd.cuh", "ksd_tc.cuh", "big_sampler.cuh", "big_launch.cuh",
+           "mlp_grad.cuh", "k2_gemm.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC",
 ]
+OBJ_DIR = os.path.join(REPO_DIR, "build", "obj")
 
 
 def _nvcc() -> str:
@@ -38,18 +43,34 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the C-ABI library if it is missing or older than its sources."""
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defs=(), out: str = LIB_PATH, sources=None) -> str:
+    """Compile the C-ABI library if it is missing or older than its sources: every translation unit with its own
+    `nvcc -c` (in parallel), then `nvcc -shared`.  `defs` / `out` / `sources`: experiment builds (tools/variant.py)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    if out == LIB_PATH and not defs and not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO_DIR, "include"), "-o", LIB_PATH,
-           *[os.path.join(CSRC, s) for s in SOURCES]]
+    sources = list(sources or SOURCES)
+    tag = "default" if out == LIB_PATH else os.path.splitext(os.path.basename(out))[0]
+    obj_dir = os.path.join(OBJ_DIR, tag)
+    os.makedirs(obj_dir, exist_ok=True)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
-    return LIB_PATH
+        flags += ["-Xptxas", "-v"]
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc(), *flags, *defs, "-I", os.path.join(REPO_DIR, "include"), "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(sources), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, sources))
+    subprocess.run([_nvcc(), "-shared", "-o", out, *objs], check=True)
+    return out
 
 
 if __name__ == "__main__":

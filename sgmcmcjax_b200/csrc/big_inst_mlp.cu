@@ -1,0 +1,17 @@
+// big_sampler_kernel<MLP> (csrc/mlp_grad.cuh).
+#define SG_BIG_LAUNCH_IMPL
+#include "big_launch.cuh"
+#include "mlp_grad.cuh"
+namespace sg {
+template cudaError_t launch_big_inst<SGMCMC_FAMILY_MLP>(const BigModel&, const BigRun&, int, size_t, cudaStream_t);
+}  // namespace sg
+
+// phase timers of this translation unit's kernel (tools/phase_timing.py)
+#ifdef SG_PHASE_TIMING
+extern "C" int sgmcmc_debug_phase_cycles(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, sg::g_phase_cycles, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(sg::g_phase_cycles, z, sizeof(z)); }
+  return 0;
+}
+#endif

@@ -83,7 +83,7 @@ struct NoiseJob { Key key; float* dst; bool valid; };
 
 // Optional phase timers (-DSG_PHASE_TIMING): cycles of block 0 / thread 0 per phase, read back with sgmcmc_debug_phase_cycles.
 #ifdef SG_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[16];
+static __device__ unsigned long long g_phase_cycles[16];   // per translation unit: read where the kernel is instantiated
 #define SG_T0() const long long sg_t0__ = clock64()
 #define SG_T1(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_phase_cycles[slot], (unsigned long long)(clock64() - sg_t0__)); } while (0)
 #define SG_TA(var) long long var = clock64()
@@ -133,10 +133,8 @@ __device__ __forceinline__ void leaf_pass(unsigned n, Key key, LD ld, ST st) {
 #pragma unroll 1
   for (; m0 + (U - 1) * bd < hf; m0 += U * bd) {
     Elt e0[U], e1[U];
-#ifndef SG_LEAF_RNG_FIRST
 #pragma unroll
     for (int u = 0; u < U; ++u) { e0[u] = ld(m0 + u * bd); e1[u] = ld(m0 + u * bd + h); }
-#endif
     // all U threefry blocks first, as independent chains side by side (ILP for the 20 dependent rounds of each), and
     // before the first use of a loaded value: the RNG work hides the memory latency of the loads above
     uint32_t w0[U], w1[U];
@@ -145,10 +143,6 @@ __device__ __forceinline__ void leaf_pass(unsigned n, Key key, LD ld, ST st) {
     float z0[U], z1[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) { z0[u] = bits_to_normal(w0[u]); z1[u] = bits_to_normal(w1[u]); }
-#ifdef SG_LEAF_RNG_FIRST
-#pragma unroll
-    for (int u = 0; u < U; ++u) { e0[u] = ld(m0 + u * bd); e1[u] = ld(m0 + u * bd + h); }
-#endif
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const unsigned m = m0 + u * bd;

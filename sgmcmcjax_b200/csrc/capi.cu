@@ -6,12 +6,12 @@
 #include <string>
 #include <vector>
 
-#include "big_sampler.cuh"
+#include "big_launch.cuh"
 #include "k2_gemm.cuh"
 #include "ksd.cuh"
 #include "ksd_tc.cuh"
 #include "mlp_grad.cuh"
-#include "vec_sampler.cuh"
+#include "vec_launch.cuh"
 
 namespace {
 
@@ -144,12 +144,10 @@ namespace {
 
 template <int FAMILY, int CV, int NCH, bool EXT>
 int launch_vec_kernel(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
-  auto kern = sg::vec_sampler_kernel<FAMILY, CV, NCH, EXT>;
   const int PP = ((h->P > h->DS ? h->P : h->DS) + 3) & ~3;
   const size_t smem = sg::vec_smem_bytes(PP, h->DS, warps);
-  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<run.st.n_chains, warps * 32, smem, stream>>>(h->vm, run);
-  CUDA_TRY(cudaGetLastError()); ++g_launches;
+  CUDA_TRY((sg::launch_vec_inst<FAMILY, CV, NCH, EXT>(h->vm, run, warps * 32, smem, stream)));   // csrc/vec_inst_*.cu
+  ++g_launches;
   return SGMCMC_OK;
 }
 
@@ -205,11 +203,9 @@ int dispatch_vec(const sgmcmc_handle* h, const sg::VecRun& run, cudaStream_t str
 
 template <int FAMILY>
 int launch_big(const sgmcmc_handle* h, const sg::BigRun& run, int blocks, cudaStream_t stream) {
-  auto kern = sg::big_sampler_kernel<FAMILY>;
   const size_t smem = ((sizeof(sg::BigSmem) + 127) & ~(size_t)127) + sg::FamilyGrad<FAMILY>::smem_bytes(h->bm);
-  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<blocks, sg::BigThreads<FAMILY>::value, smem, stream>>>(h->bm, run);
-  CUDA_TRY(cudaGetLastError()); ++g_launches;
+  CUDA_TRY(sg::launch_big_inst<FAMILY>(h->bm, run, blocks, smem, stream));                        // csrc/big_inst_*.cu
+  ++g_launches;
   return SGMCMC_OK;
 }
 
@@ -698,14 +694,6 @@ int sgmcmc_shard_step(sgmcmc_handle* h, sgmcmc_state* st, int32_t i, const sgmcm
   return dispatch_vec(h, run, (cudaStream_t)stream);
 }
 
-#ifdef SG_PHASE_TIMING
-extern "C" int sgmcmc_debug_phase_cycles(unsigned long long* out16, int reset) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out16, sg::g_phase_cycles, sizeof(unsigned long long) * 16);
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(sg::g_phase_cycles, z, sizeof(z)); }
-  return 0;
-}
-#endif
 
 int sgmcmc_minibatch_indices(const uint32_t* key, int64_t n, int32_t batch, int32_t* out, void* stream) {
   if (!key || !out || n <= 0 || n > 0x7fffffffLL || batch <= 0) return fail(SGMCMC_E_INVALID, "bad argument");

@@ -153,7 +153,9 @@ __device__ __forceinline__ float tf32_rna(float x) {
 
 // ------------------------------------------------------------------------------------------ prep
 // Column sums of X and G in double: sums[0][d], sums[1][d].
-__global__ void colsum_kernel(const float* __restrict__ X, const float* __restrict__ G, int n, int d, double* sums) {
+// (the kernels and the product table are `static`: mlp_grad.cuh reuses this header's tcgen05 / mbarrier wrappers from other
+// translation units)
+static __global__ void colsum_kernel(const float* __restrict__ X, const float* __restrict__ G, int n, int d, double* sums) {
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     double sx = 0.0, sgr = 0.0;
     for (int r = blockIdx.x; r < n; r += gridDim.x) {
@@ -166,7 +168,7 @@ __global__ void colsum_kernel(const float* __restrict__ X, const float* __restri
 }
 
 // One warp per row: centre, split into tf32 hi / lo, row terms.
-__global__ void split_kernel(const float* __restrict__ X, const float* __restrict__ G, int n, int d, int dp,
+static __global__ void split_kernel(const float* __restrict__ X, const float* __restrict__ G, int n, int d, int dp,
                              const double* __restrict__ sums, float* __restrict__ Z, float4* __restrict__ rt) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -230,13 +232,13 @@ __device__ __forceinline__ float imq_k0_tc(float dd, float gg, float gd, float d
 // (12 KB of operand traffic per 128 tensor cycles instead of 8 KB per 64, the 128 B/clk shared-memory port).
 //   TMEM columns: [0,128) x_I.x_J   [128,256) x_I.g_J   [256,384) g_I.x_J   [384,512) g_I.g_J
 // table: (TMEM column of the pair, row-side segment 0 xh 1 xl 2 gh 3 gl, column-side pair 0 = [xh|gh], 1 = [xl|gl])
-__constant__ int16_t PROD[6][3] = {
+static __constant__ int16_t PROD[6][3] = {
     {0, 0, 0}, {0, 0, 1}, {0, 1, 0},          // x_I . [x_J | g_J]  (3xTF32: hi.hi, hi.lo, lo.hi)
     {256, 2, 0}, {256, 2, 1}, {256, 3, 0}     // g_I . [x_J | g_J]
 };
 __device__ __forceinline__ int col_slot(int seg) { return ((seg & 1) << 1) | (seg >> 1); }   // xh 0, gh 1, xl 2, gl 3
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+static __global__ void __launch_bounds__(NUM_THREADS, 1)
 ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict__ rt, int n, int d, int dp,
               int part, int nparts, double* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
