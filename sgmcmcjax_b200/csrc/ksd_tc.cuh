@@ -220,7 +220,8 @@ __device__ __forceinline__ void tile_of(long long t, int T, int& I, int& J) {
 
 __device__ __forceinline__ float imq_k0_tc(float dd, float gg, float gd, float dim) {
   const float b = 1.0f + dd;
-  const float r = rsqrtf(b);
+  float r;                                      // b >= 1: the denormal guard of rsqrtf() (3 more instructions) is dead weight
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
   const float r2 = r * r;
   const float r3 = r2 * r;
   return gg * r + (gd + dim) * r3 - 3.0f * dd * r3 * r2;
@@ -340,6 +341,12 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       mbar_wait(&tail->tmem_full, acc_phase);
       tc_fence_after();
       float tsum = 0.f;
+      const uint32_t colterm_s = smem_u32(&tail->colterm[buf][0]);   // read with ld.shared (the generic path is slower)
+      auto colterm = [&](int j) {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(colterm_s + 16u * (uint32_t)j));
+        return v;
+      };
       const bool diag_tile = I == J;
       const int jmax = min(TILE, n - J * TILE);
       const bool interior = !diag_tile && (I + 1) * TILE <= n && jmax == TILE;   // no masks, no exact diagonal
@@ -355,7 +362,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
         if (interior) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float4 cj = tail->colterm[buf][cb + e];
+            const float4 cj = colterm(cb + e);
             const float dd = fmaf(-2.0f, __uint_as_float(p1[e]), ri.x + cj.x);
             const float gg = __uint_as_float(p2[e]) + (ri.z + cj.z);
             const float gd = (ri.y + cj.y) - (__uint_as_float(p3[e]) + __uint_as_float(p4[e]));
@@ -364,7 +371,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float4 cj = tail->colterm[buf][cb + e];
+            const float4 cj = colterm(cb + e);
             float dd = fmaf(-2.0f, __uint_as_float(p1[e]), ri.x + cj.x);
             float gg = __uint_as_float(p2[e]) + (ri.z + cj.z);
             float gd = (ri.y + cj.y) - (__uint_as_float(p3[e]) + __uint_as_float(p4[e]));
