@@ -230,6 +230,8 @@ def sgmcmc_sampler(build_kernel_fn: Callable) -> Callable:
         store_samples = bool(kwargs.pop("store_samples", True))
         init_fn, _kernel, _get_params = build_kernel_fn(*args, **kwargs)
         if thin != 1 or summaries or not store_samples:
+            if not compiled:
+                raise ValueError("thin / summaries / store_samples are options of the compiled sampler (compiled=True)")
             return _summaries_sampler(init_fn.engine, thin, summaries, store_samples, pbar)
         return _build_native_sampler(init_fn, as_list=not compiled, pbar=pbar)
 

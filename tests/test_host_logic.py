@@ -91,3 +91,13 @@ def test_rhat_from_moments_matches_textbook_formula():
     assert isinstance(out, list) and out[0].shape == (3,) and out[1].shape == (1,)
     with pytest.raises(ValueError):
         D.rhat_from_moments(draws.mean(axis=1)[:1], draws.var(axis=1)[:1], n)
+
+
+def test_sampler_extension_keywords_are_validated_on_the_host():
+    """thin / summaries / store_samples (samplers.py): argument errors are raised before any device work."""
+    from sgmcmcjax_b200 import samplers as NS
+
+    with pytest.raises(ValueError, match="thin must be >= 1"):
+        NS._summaries_sampler(object(), 0, False, True, False)
+    s = NS._summaries_sampler(object(), 3, True, False, False)       # construction needs no device
+    assert callable(s)
