@@ -56,3 +56,36 @@ def rhat_from_samples(samples):
     """Reference implementation on stored draws [C, K, ...] (used by the tests to check the moment route)."""
     s = np.asarray(samples, np.float64)
     return rhat_from_moments(s.mean(axis=1), s.var(axis=1), s.shape[1])
+
+
+def ess_from_samples(samples):
+    """Effective sample size per parameter from stored draws [C, K, ...] (all chains pooled): K C / tau with the
+    integrated autocorrelation time tau estimated by Geyer's initial positive sequence on the chain-averaged
+    autocovariances (FFT).  Needs the draws themselves - use ``thin=`` to keep the buffer small."""
+    x = np.asarray(samples, np.float64)
+    c, k = x.shape[0], x.shape[1]
+    if k < 4:
+        raise ValueError("ESS needs at least 4 draws per chain")
+    flat = x.reshape(c, k, -1)
+    xc = flat - flat.mean(axis=1, keepdims=True)
+    nfft = 1 << (2 * k - 1).bit_length()
+    f = np.fft.rfft(xc, n=nfft, axis=1)
+    acov = np.fft.irfft(f * np.conj(f), n=nfft, axis=1)[:, :k] / k          # biased autocovariance per chain
+    acov = acov.mean(axis=0)                                                 # [K, P]
+    w = acov[0]
+    b_over_n = flat.mean(axis=1).var(axis=0, ddof=1) if c > 1 else 0.0
+    var_plus = w * (k - 1) / k + b_over_n                                    # as in R-hat
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rho = 1.0 - (w - acov) / var_plus                                    # [K, P], rho[0] = 1 - (w - w)/var+ ~ 1
+    out = np.empty(flat.shape[2])
+    for p in range(flat.shape[2]):
+        r = rho[:, p]
+        tau, t = -1.0, 0
+        while t + 1 < k:                                                     # pairs rho[2m] + rho[2m+1] while positive
+            pair = r[t] + r[t + 1]
+            if not np.isfinite(pair) or pair < 0.0:
+                break
+            tau += 2.0 * pair
+            t += 2
+        out[p] = c * k / max(tau, 1.0 / np.log10(max(c * k, 10)))
+    return out.reshape(x.shape[2:])

@@ -101,3 +101,21 @@ def test_sampler_extension_keywords_are_validated_on_the_host():
         NS._summaries_sampler(object(), 0, False, True, False)
     s = NS._summaries_sampler(object(), 3, True, False, False)       # construction needs no device
     assert callable(s)
+
+
+def test_ess_of_an_ar1_process():
+    """diagnostics.ess_from_samples: AR(1) with coefficient rho has ESS / n = (1 - rho) / (1 + rho)."""
+    from sgmcmcjax_b200 import diagnostics as D
+
+    rng = np.random.default_rng(3)
+    c, k = 8, 4000
+    for rho in (0.0, 0.5, 0.9):
+        x = np.zeros((c, k, 2))
+        e = rng.normal(size=(c, k, 2))
+        x[:, 0] = e[:, 0]
+        for t in range(1, k):
+            x[:, t] = rho * x[:, t - 1] + np.sqrt(1 - rho * rho) * e[:, t]
+        ess = D.ess_from_samples(x)
+        want = c * k * (1 - rho) / (1 + rho)
+        assert ess.shape == (2,)
+        assert np.all(np.abs(ess / want - 1.0) < 0.2), (rho, ess, want)
