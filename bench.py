@@ -279,13 +279,13 @@ def extra_workloads(args, torch, lib, hbm_peak, X, y, theta_true):
     row_bytes = 100 * (784 * 4 + 40)
     s = samplers.build_sghmc_sampler(1e-6, 4, B.loglikelihood, B.logprior, (Xm, ym), 100, pbar=False)
     s.engine.flatten_params(params, None)
-    ms, nl = _time_engine(torch, s.engine, lib, keys_m, thm, 2, 3, 3)
-    report("C3 bayesian MLP 784-100-10 SGHMC L=4 batch=100", ms, Cm, 2, 4, row_bytes + 16 * Pm + Pm, nl,
+    ms, nl = _time_engine(torch, s.engine, lib, keys_m, thm, 4, 3, 3)
+    report("C3 bayesian MLP 784-100-10 SGHMC L=4 batch=100", ms, Cm, 4, 4, row_bytes + 16 * Pm + Pm, nl,
            note="one sample = 4 chain-steps (gradient evaluations)")
     s = samplers.build_psgld_sampler(1e-3, B.loglikelihood, B.logprior, (Xm, ym), 100, pbar=False)
     s.engine.flatten_params(params, None)
-    ms, nl = _time_engine(torch, s.engine, lib, keys_m, thm, 4, 3, 3)
-    report("C3 bayesian MLP 784-100-10 pSGLD batch=100", ms, Cm, 4, 1, row_bytes + 16 * Pm + 4 * Pm, nl)
+    ms, nl = _time_engine(torch, s.engine, lib, keys_m, thm, 16, 3, 3)
+    report("C3 bayesian MLP 784-100-10 pSGLD batch=100", ms, Cm, 16, 1, row_bytes + 16 * Pm + 4 * Pm, nl)
     del s, Xm, ym, thm
     # ---- C4 PMF 943 x 1682, rank 20, N=1e5, batch=1000, 512 chains
     Cp, nu, ni, r, Np = 512, 943, 1682, 20, 100_000
@@ -298,11 +298,11 @@ def extra_workloads(args, torch, lib, hbm_peak, X, y, theta_true):
     pmf_bytes = 1000 * 12 + 2 * 1000 * 4 * r + 16 * Pp + 4 * Pp
     s = samplers.build_sgnht_sampler(1e-5, F.loglikelihood, F.logprior, (ij, rt), 1000, pbar=False)
     s.engine.flatten_params((U, V), None)
-    ms, nl = _time_engine(torch, s.engine, lib, keys_p, thp, 4, 3, 3)
-    report("C4 PMF 943x1682 rank 20 SGNHT batch=1000", ms, Cp, 4, 1, pmf_bytes, nl)
+    ms, nl = _time_engine(torch, s.engine, lib, keys_p, thp, 16, 3, 3)
+    report("C4 PMF 943x1682 rank 20 SGNHT batch=1000", ms, Cp, 16, 1, pmf_bytes, nl)
     s = samplers.build_badodabCV_sampler(1e-3, F.loglikelihood, F.logprior, (ij, rt), 1000, (U, V), pbar=False)
-    ms, nl = _time_engine(torch, s.engine, lib, keys_p, thp, 4, 3, 3)
-    report("C4 PMF 943x1682 rank 20 BADODAB-CV batch=1000", ms, Cp, 4, 1, pmf_bytes + 8 * Pp, nl)
+    ms, nl = _time_engine(torch, s.engine, lib, keys_p, thp, 16, 3, 3)
+    report("C4 PMF 943x1682 rank 20 BADODAB-CV batch=1000", ms, Cp, 16, 1, pmf_bytes + 8 * Pp, nl)
     return out
 
 # ------------------------------------------------------------------------------------------ GPU arm
