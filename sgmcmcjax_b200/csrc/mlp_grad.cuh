@@ -196,7 +196,17 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
 
   // ---------------------------------------------------------------------------------------------------
   // Z1 = X W1^T + b1 into act1 (fp32, [rows][zs]); rows >= nb come out as b1.
-  __device__ __noinline__ static void layer1_forward(const BigModel& m, MlpSmem& ms, uint8_t* region, const float* th, int nb,
+  __device__ __forceinline__ static void layer1_forward(const BigModel& m, MlpSmem& ms, uint8_t* region, const float* th, int nb,
+                                        int rows, float* Z, int zs) {
+    const int s0 = m.dims[1];
+    const float* W1 = th + m.leaf_off[0];
+    // fast path (s0 % 4 == 0, W1 at least 8-byte aligned) as its own instantiation: merged with the general path, ptxas
+    // if-converts the two and leaves predicated-off spill stores that still wait for the staged loads
+    if ((s0 & 3) == 0 && (reinterpret_cast<uintptr_t>(W1) & 7) == 0) layer1_forward_impl<true>(m, ms, region, th, nb, rows, Z, zs);
+    else layer1_forward_impl<false>(m, ms, region, th, nb, rows, Z, zs);
+  }
+  template <bool FAST>
+  __device__ __noinline__ static void layer1_forward_impl(const BigModel& m, MlpSmem& ms, uint8_t* region, const float* th, int nb,
                                         int rows, float* Z, int zs) {
     using namespace mlptc;
     const int s0 = m.dims[1], s1 = m.dims[2];
@@ -230,7 +240,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     // Fast path (s0 % 4 == 0, W1 at least 8-byte aligned): every 16-byte chunk is wholly inside or outside a row, so
     // the loads are unconditional (clamped address, result masked) and issue back to back; a branch between two
     // loads would serialise them on the memory latency.
-    const bool fast = x16 && w8;
+    constexpr bool fast = FAST;
     const float* xp0 = xsrc0 ? xsrc0 : X;
     const float* xp1 = xsrc1 ? xsrc1 : X;
     const float* wp0 = wsrc0 ? wsrc0 : W1;

@@ -1,4 +1,6 @@
-"""Per-phase cycles of the MLP sampler (library built with -DSG_PHASE_TIMING, loaded through SGMCMC_B200_LIB)."""
+"""Per-phase cycles of the MLP sampler.  Build the instrumented library first:
+   python tools/variant.py timing --only capi.cu,big_inst_mlp.cu -DSG_PHASE_TIMING -DSG_NO_VEC -DSG_NO_PMF
+(it is loaded from build/variants/lib_timing.so through SGMCMC_B200_LIB)."""
 import ctypes as C, os, subprocess, sys
 sys.path.insert(0, "/root/repo")
 os.environ.setdefault("SGMCMC_B200_LIB", "/root/repo/build/variants/lib_timing.so")
