@@ -293,6 +293,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       mlptc::worker_sync();
       SG_TB(12, tt);
       if (c + 2 < n_chunks) fetch(c + 2, xv0, xv1, wv0, wv1);               // two chunks of loads stay in flight
+      SG_TB(14, tt);
       if (tid == 0) {
         tc_fence_after();
         const int slices = min(MLP_KC, s0p8 - c * MLP_KC) / 8;

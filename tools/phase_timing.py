@@ -15,7 +15,7 @@ lib.sgmcmc_debug_phase_cycles(buf, 0)
 names = ["diffuse passes", "layer-1 forward GEMM", "small layers (softmax, layer 2, dZ1)", "layer-1 backward GEMM",
          "  softmax(z1)", "  softmax + z2 forward", "  output layer dz", "  dW2, db2", "  dW2, db2 + quad dZ1 + db1",
          "  fwd: wait stage free (MMA c-2)", "  fwd: mask + split + st.shared (incl. wait for the loads)", "  fwd: issue loads c+2, fence",
-         "  fwd: worker barrier", "  fwd: MMA issue + commit (thread 0)"]
+         "  fwd: worker barrier", "  fwd: MMA issue + commit (thread 0)", "  fwd: issue loads c+2 (thread 0)"]
 steps = 3 * 4
 for n, v in zip(names, buf):
     print(f"{n:40s} {v / steps / 1.965e3:8.1f} us per chain-step (block 0)")
