@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SGMCMC_ABI_VERSION 3
+#define SGMCMC_ABI_VERSION 4
 
 enum { SGMCMC_OK = 0, SGMCMC_E_INVALID = -1, SGMCMC_E_UNSUPPORTED = -2, SGMCMC_E_CUDA = -3,
        SGMCMC_E_STATE = -4 };
@@ -120,6 +120,12 @@ int64_t sgmcmc_launch_count(void);
 
 int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out);
 int sgmcmc_destroy(sgmcmc_handle* h);
+
+/* Launch shape the vector-family sampler uses for n_chains chains (gaussian_mean, logreg): warps per CTA and CTAs per
+ * chain.  cluster > 1 means one thread-block cluster per chain: the minibatch of gradient_estimation.py:32-33 is split
+ * over the CTAs and the partial sums are exchanged over distributed shared memory (few chains per GPU: config 2 on
+ * 8 GPUs, the single chain of samplers.py:45-58).  Environment overrides: SGMCMC_WARPS_PER_CHAIN, SGMCMC_CLUSTER. */
+int sgmcmc_launch_shape(const sgmcmc_handle* h, int32_t n_chains, int32_t* warps_per_cta, int32_t* cluster);
 
 /* Ingest the data tuple (gradient_estimation.py:25-29).  x: device [n_data, data_dim] row-major,
  * f32 (gaussian_mean, logreg, mlp) or int32 (pmf: (user, item) pairs, data_dim = 2).

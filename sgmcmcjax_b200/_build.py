@@ -36,6 +36,11 @@ def _deps():
     return deps
 
 
+def toolchain_missing(exc: BaseException) -> bool:
+    """True if a build failed because there is no nvcc at all (as opposed to nvcc rejecting the sources)."""
+    return isinstance(exc, RuntimeError) and "nvcc not found" in str(exc)
+
+
 def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
@@ -46,10 +51,24 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False, defs=(), out: str = LIB_PATH, sources=None) -> str:
     """Compile the C-ABI library if it is missing or older than its sources: every translation unit with its own
     `nvcc -c` (in parallel), then `nvcc -shared`.  `defs` / `out` / `sources`: experiment builds (tools/variant.py)."""
-    from concurrent.futures import ThreadPoolExecutor
+    import fcntl
 
     if out == LIB_PATH and not defs and not force and not is_stale():
         return LIB_PATH
+    _nvcc()                                       # fail before taking the lock if there is no toolchain
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    # one builder at a time per output (every torchrun rank sees the same stale library at once); the others wait on
+    # the lock and then find the library fresh
+    with open(os.path.join(OBJ_DIR, "." + os.path.basename(out) + ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if out == LIB_PATH and not defs and not force and not is_stale():
+            return LIB_PATH
+        return _build_locked(verbose, defs, out, sources)
+
+
+def _build_locked(verbose, defs, out, sources) -> str:
+    from concurrent.futures import ThreadPoolExecutor
+
     sources = list(sources or SOURCES)
     tag = "default" if out == LIB_PATH else os.path.splitext(os.path.basename(out))[0]
     obj_dir = os.path.join(OBJ_DIR, tag)
@@ -69,7 +88,9 @@ def build(force: bool = False, verbose: bool = False, defs=(), out: str = LIB_PA
 
     with ThreadPoolExecutor(max_workers=min(len(sources), os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, sources))
-    subprocess.run([_nvcc(), "-shared", "-o", out, *objs], check=True)
+    tmp = f"{out}.tmp.{os.getpid()}"              # link beside the target, then rename: no reader sees a half-written .so
+    subprocess.run([_nvcc(), "-shared", "-o", tmp, *objs], check=True)
+    os.replace(tmp, out)
     return out
 
 

@@ -11,7 +11,7 @@ import os
 from . import _build
 
 MAX_LEAVES = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 FAMILY_GAUSSIAN_MEAN, FAMILY_LOGREG, FAMILY_MLP, FAMILY_PMF = 0, 1, 2, 3
 EST_STANDARD, EST_CV, EST_SVRG = 0, 1, 2
@@ -20,7 +20,7 @@ FLAG_BADODABCV_REFERENCE_BUG = 1
 SHARD_UPDATE2, SHARD_STEP = 1, 2
 
 EXPORTS = [
-    "sgmcmc_last_error", "sgmcmc_abi_version", "sgmcmc_launch_count", "sgmcmc_create", "sgmcmc_destroy", "sgmcmc_set_data",
+    "sgmcmc_last_error", "sgmcmc_abi_version", "sgmcmc_launch_count", "sgmcmc_create", "sgmcmc_destroy", "sgmcmc_launch_shape", "sgmcmc_set_data",
     "sgmcmc_set_centering", "sgmcmc_fullbatch_grad", "sgmcmc_init", "sgmcmc_run", "sgmcmc_run_thinned", "sgmcmc_optimize", "sgmcmc_kernel_step",
     "sgmcmc_set_row_shard", "sgmcmc_sum_width", "sgmcmc_set_centering_grad", "sgmcmc_shard_init", "sgmcmc_shard_step",
     "sgmcmc_minibatch_indices", "sgmcmc_normal", "sgmcmc_split", "sgmcmc_ksd_imq_partial", "sgmcmc_ksd_workspace_bytes", "sgmcmc_ksd_imq_tc",
@@ -66,10 +66,15 @@ def load(build_if_missing: bool = True):
     path = lib_path()
     if build_if_missing and path == _build.LIB_PATH and _build.is_stale():
         try:
-            _build.build()
-        except Exception as e:  # stale-but-present library is still usable
+            _build.build()                        # serialised across processes by a file lock (torchrun ranks)
+        except Exception as e:
             if not os.path.exists(path):
                 raise NativeError(f"libsgmcmc_b200.so is missing and could not be built: {e}") from e
+            if not _build.toolchain_missing(e):   # nvcc ran and failed: a stale library would hide the broken sources
+                raise NativeError(f"libsgmcmc_b200.so is older than its sources and the rebuild failed: {e}") from e
+            import warnings
+
+            warnings.warn(f"libsgmcmc_b200.so is older than its sources and cannot be rebuilt here ({e}); using it as is")
     if not os.path.exists(path):
         raise NativeError(f"{path} not found; run `python -m sgmcmcjax_b200._build` (there is no CPU fallback)")
     lib = C.CDLL(path)
@@ -82,6 +87,7 @@ def load(build_if_missing: bool = True):
     sigs = {
         "sgmcmc_create": [C.POINTER(Config), C.POINTER(vp)],
         "sgmcmc_destroy": [vp],
+        "sgmcmc_launch_shape": [vp, i32, C.POINTER(i32), C.POINTER(i32)],
         "sgmcmc_set_data": [vp, vp, vp, vp],
         "sgmcmc_set_centering": [vp, vp, vp],
         "sgmcmc_fullbatch_grad": [vp, vp, i32, vp, vp],

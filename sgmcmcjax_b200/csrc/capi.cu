@@ -3,7 +3,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "big_launch.cuh"
@@ -55,6 +57,8 @@ struct sgmcmc_handle {
   size_t k2_scratch_bytes = 0;
   int num_sms = 148;
   bool has_data = false, has_center = false;
+  // (threads, cluster asked, extended kernel) -> cluster shape the device can co-schedule (vec_launch.cuh)
+  std::map<std::tuple<int, int, int>, int> cluster_ok;
 };
 
 namespace sg {
@@ -142,55 +146,77 @@ __global__ void split_kernel(Key key, unsigned num, uint32_t* out) {
 
 namespace {
 
+struct VecShape { int warps, cluster; };     // warps per CTA, CTAs per chain (a thread-block cluster if > 1)
+
 template <int FAMILY, int CV, int NCH, bool EXT>
-int launch_vec_kernel(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
+int launch_vec_kernel(sgmcmc_handle* h, const sg::VecRun& run, VecShape shape, cudaStream_t stream) {
   const int PP = ((h->P > h->DS ? h->P : h->DS) + 3) & ~3;
-  const size_t smem = sg::vec_smem_bytes(PP, h->DS, warps);
-  CUDA_TRY((sg::launch_vec_inst<FAMILY, CV, NCH, EXT>(h->vm, run, warps * 32, smem, stream)));   // csrc/vec_inst_*.cu
+  const size_t smem = sg::vec_smem_bytes(PP, h->DS, shape.warps);
+  const auto key = std::make_tuple(shape.warps * 32, shape.cluster, EXT ? 1 : 0);
+  const auto hit = h->cluster_ok.find(key);
+  int used = hit != h->cluster_ok.end() ? hit->second : shape.cluster;
+  CUDA_TRY((sg::launch_vec_inst<FAMILY, CV, NCH, EXT>(h->vm, run, shape.warps * 32, used, smem, stream,   // csrc/vec_inst_*.cu
+                                                      hit == h->cluster_ok.end(), &used)));
+  h->cluster_ok[key] = used;
   ++g_launches;
   return SGMCMC_OK;
 }
 
 template <int FAMILY, int CV, int NCH>
-int launch_vec(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
+int launch_vec(sgmcmc_handle* h, const sg::VecRun& run, VecShape shape, cudaStream_t stream) {
   // the extended instantiation carries the row-sharded mode and the optimiser; the plain samplers run the lean one
   const bool ext = h->vm.own_n != h->vm.n_data || h->cfg.diffusion == SGMCMC_DIFF_ADAM_OPT || run.sum_in || run.sum_out || run.moments;
-  return ext ? launch_vec_kernel<FAMILY, CV, NCH, true>(h, run, warps, stream)
-             : launch_vec_kernel<FAMILY, CV, NCH, false>(h, run, warps, stream);
+  return ext ? launch_vec_kernel<FAMILY, CV, NCH, true>(h, run, shape, stream)
+             : launch_vec_kernel<FAMILY, CV, NCH, false>(h, run, shape, stream);
 }
 
 template <int FAMILY, int CV>
-int launch_vec_nch(const sgmcmc_handle* h, const sg::VecRun& run, int warps, cudaStream_t stream) {
+int launch_vec_nch(sgmcmc_handle* h, const sg::VecRun& run, VecShape shape, cudaStream_t stream) {
   switch (h->nch) {
-    case 1: return launch_vec<FAMILY, CV, 1>(h, run, warps, stream);
-    case 2: return launch_vec<FAMILY, CV, 2>(h, run, warps, stream);
-    case 4: return launch_vec<FAMILY, CV, 4>(h, run, warps, stream);
+    case 1: return launch_vec<FAMILY, CV, 1>(h, run, shape, stream);
+    case 2: return launch_vec<FAMILY, CV, 2>(h, run, shape, stream);
+    case 4: return launch_vec<FAMILY, CV, 4>(h, run, shape, stream);
   }
   return fail(SGMCMC_E_UNSUPPORTED, "data_dim > 512 is not supported by the vector-family sampler");
 }
 
-int choose_warps(const sgmcmc_handle* h, int n_chains) {
+// Launch shape of the vector sampler.  The device holds num_sms x 32 resident warps of this kernel (64 registers per
+// thread); a chain gets its share of them.  Up to 32 / nch warps fit one CTA; a chain that can have more (fewer chains
+// than SMs: config 2 split over 8 GPUs, the README's single chain) gets a cluster of 8-warp CTAs whose warps share the
+// minibatch (csrc/vec_sampler.cuh header).  SGMCMC_WARPS_PER_CHAIN (per CTA) / SGMCMC_CLUSTER override.
+VecShape choose_shape(const sgmcmc_handle* h, int n_chains) {
   const int max_warps = 32 / h->nch;
-  int w = env_int("SGMCMC_WARPS_PER_CHAIN", 0);
-  if (w <= 0) {
-    // fill the machine: ~32 resident warps on each of the SMs
-    const long target = (long)h->num_sms * 32 / (n_chains > 0 ? n_chains : 1);
+  const long share = (long)h->num_sms * 32 / (n_chains > 0 ? n_chains : 1);   // warps this chain can have
+  // a warp needs a full 8-row group of the minibatch (16 rows: two threefry half-streams) to be worth its barriers
+  const long useful = std::max<long>(4, (long)h->vm.batch / 16);
+  const long want = std::min(share, useful);
+  int w = env_int("SGMCMC_WARPS_PER_CHAIN", 0), cl = env_int("SGMCMC_CLUSTER", 0);
+  if (w <= 0 && cl <= 0) {
+    if (want <= max_warps) {
+      cl = 1; w = 4;
+      while (w * 2 <= want) w *= 2;
+    } else {
+      w = std::min(8, max_warps);
+      cl = (int)std::min<long>(16, want / w);
+    }
+  } else if (w <= 0) {
     w = 4;
-    while (w * 2 <= target && w * 2 <= max_warps) w *= 2;
-    // few chains and a short minibatch: more warps than 32-row slices of the batch only add to the folds and barriers
-    // (README config, 1 chain, batch 1000: 9.2 us per step with 32 warps, 8.2 us with 16, 11.3 us with 8)
-    while (w > 8 && (long)w * 32 > (long)h->vm.batch) w >>= 1;
+    while (w * 2 <= want / cl && w * 2 <= max_warps) w *= 2;
+  } else if (cl <= 0) {
+    cl = 1;
   }
   if (w > max_warps) w = max_warps;
   if (w < 1) w = 1;
-  return w;
+  if (cl < 1) cl = 1;
+  if (cl > 16) cl = 16;
+  return VecShape{w, cl};
 }
 
-int dispatch_vec(const sgmcmc_handle* h, const sg::VecRun& run, cudaStream_t stream) {
+int dispatch_vec(sgmcmc_handle* h, const sg::VecRun& run, cudaStream_t stream) {
 #ifdef SG_NO_VEC   // experiment builds of the big-state sampler only (tools/variant.py): skip the 36 vector instantiations
   return fail(SGMCMC_E_UNSUPPORTED, "built with SG_NO_VEC");
 #else
-  const int warps = choose_warps(h, run.st.n_chains);
+  const VecShape warps = choose_shape(h, run.st.n_chains);
   const bool cv = h->cfg.estimator != SGMCMC_EST_STANDARD;
   if (h->cfg.family == SGMCMC_FAMILY_GAUSSIAN_MEAN)
     return cv ? launch_vec_nch<SGMCMC_FAMILY_GAUSSIAN_MEAN, 1>(h, run, warps, stream)
@@ -668,6 +694,14 @@ int sgmcmc_set_centering_grad(sgmcmc_handle* h, const float* theta_hat, const fl
 }
 
 int sgmcmc_sum_width(const sgmcmc_handle* h) { return h ? h->DS : 0; }
+
+int sgmcmc_launch_shape(const sgmcmc_handle* h, int32_t n_chains, int32_t* warps_per_cta, int32_t* cluster) {
+  if (!h || !warps_per_cta || !cluster || n_chains < 1) return fail(SGMCMC_E_INVALID, "bad argument");
+  if (h->big) return fail(SGMCMC_E_UNSUPPORTED, "launch shapes are a property of the vector-family sampler");
+  const VecShape s = choose_shape(h, n_chains);
+  *warps_per_cta = s.warps; *cluster = s.cluster;
+  return SGMCMC_OK;
+}
 
 int sgmcmc_shard_init(sgmcmc_handle* h, sgmcmc_state* st, const uint32_t* keys, int32_t sampler_mode, float* sum_out,
                       void* stream) {

@@ -14,7 +14,18 @@
 // x; logreg stores x~ = (1 - 2y) x, i.e. the label is folded into the sign of the row, which
 // is exactly the argument of the reference's loglik  -logsumexp([0, (1-2y) theta.x])
 // (models/logistic_regression.py:65-67): d loglik / d theta = -sigmoid(theta.x~) x~.
+//
+// Few chains (fewer than the GPU has SMs, e.g. 128 chains per GPU when config 2's 1024 chains are split over 8 GPUs,
+// or the README's single chain): a THREAD-BLOCK CLUSTER owns the chain.  The B-row index stream (and a full-batch
+// pass) is split over the warps of all CTAs of the cluster; every CTA holds a full replica of the chain state in its
+// own shared memory and runs the (tiny, D-element) key tree and diffusion update redundantly - same keys, same
+// arithmetic, bit-identical replicas - so the ONLY exchange per gradient estimate is the [DS] partial row sum:
+// every CTA folds its warps into Sloc[buf], one cluster barrier, every CTA adds the Sloc[buf] of all ranks over
+// DSMEM in rank order (same order everywhere -> replicas stay identical).  Sloc is double-buffered, so one barrier
+// per estimate is enough (a CTA can only reach the estimate after next once every peer has passed the next barrier,
+// i.e. has finished reading this one).  Rank 0 alone writes samples and state back.
 #pragma once
+#include <cooperative_groups.h>
 #include "prng.cuh"
 #include "../../include/sgmcmc_b200.h"
 
@@ -69,6 +80,7 @@ constexpr int SHARD_UPDATE2 = 1, SHARD_STEP = 2;
 // shared-memory carve-up (dynamic): all arrays padded to DSP = max(P, DS) rounded to 4
 struct Smem {
   float *theta, *aux1, *aux2, *grad, *center, *fb, *S, *part;
+  float* sloc;        // [2][DS + 4]: this CTA's folded partial sums (+ log-likelihood value term), read by cluster peers
   float* alpha;       // [MAXL]
   float* red;         // [32] block-reduction scratch
   uint32_t* keys;     // [2 * (4 + 2*MAXL)] step keys
@@ -82,8 +94,9 @@ __device__ __forceinline__ Smem carve(float* base, int PP, int DS, int W) {
   s.grad = base;             base += PP;
   s.center = base;           base += PP;
   s.fb = base;               base += PP;
-  s.S = base;                base += DS;
+  s.S = base;                base += DS + 4;     // [DS] sums, [DS] = log-likelihood value term (optimiser)
   s.part = base;             base += W * DS;
+  s.sloc = base;             base += 2 * (DS + 4);
   s.alpha = base;            base += MAXL;
   s.red = base;              base += 32;
   s.keys = reinterpret_cast<uint32_t*>(base);
@@ -91,10 +104,14 @@ __device__ __forceinline__ Smem carve(float* base, int PP, int DS, int W) {
 }
 constexpr int SMEM_KEY_WORDS = 2 * (4 + 2 * MAXL);
 __host__ __device__ inline size_t vec_smem_bytes(int PP, int DS, int W) {
-  return sizeof(float) * (size_t)(6 * PP + DS + W * DS + MAXL + 32) + sizeof(uint32_t) * SMEM_KEY_WORDS;
+  return sizeof(float) * (size_t)(6 * PP + (DS + 4) + W * DS + 2 * (DS + 4) + MAXL + 32) + sizeof(uint32_t) * SMEM_KEY_WORDS;
 }
 
 // ---------------------------------------------------------------------------------------
+// cluster geometry of this CTA (1 / 0 for a launch without a cluster attribute)
+__device__ __forceinline__ unsigned cluster_size() { unsigned r; asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+
 __device__ __forceinline__ float sigmoid_f(float z) {
   // stable logistic; expf (not __expf): per-row relative error must stay ~1e-7
   const float e = expf(-fabsf(z));
@@ -149,7 +166,9 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
                                          unsigned seq_base, unsigned count, const float* s_theta, const float* s_center,
                                          float* s_part, float* lp_part_in = nullptr) {
   float* lp_part = EXT ? lp_part_in : nullptr;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the stream is dealt to the warps of the whole cluster: W = warps of all its CTAs, gwarp = this warp among them
+  const unsigned W = (blockDim.x >> 5) * cluster_size(), gwarp = cluster_rank() * (blockDim.x >> 5) + warp;
   const unsigned h = (count + 1u) >> 1;
   const int DS = m.DS;
   const bool sharded = EXT && m.own_n != m.n_data;
@@ -174,7 +193,7 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
   // short streams (h < 32 W, e.g. one chain with batch 1000): spread the blocks over ALL warps instead of
   // filling 32 lanes of the first few, so the row groups of a step run in parallel rather than back to back
   const unsigned lpw = h < W * 32u ? (h + W - 1u) / W : 32u;
-  for (unsigned b0 = warp * lpw; b0 < h; b0 += W * lpw) {
+  for (unsigned b0 = gwarp * lpw; b0 < h; b0 += W * lpw) {
     const unsigned b = b0 + lane;
     int jA = -1, jB = -1;
     if ((unsigned)lane < lpw && b < h) {
@@ -322,14 +341,30 @@ __global__ void zc_column_kernel(float* __restrict__ rows, unsigned n_rows, int 
   }
 }
 
-// part[W][DS] -> S[DS]  (fixed summation order: deterministic)
-__device__ __forceinline__ void fold_parts(const Smem& s, int DS) {
+// part[W][DS] (+ red[W], the log-likelihood value terms, if with_lp) -> S[DS] (+ S[DS]); fixed summation order.
+// In a cluster: local fold into sloc[buf], ONE cluster barrier, then every CTA adds the sloc[buf] of all ranks over
+// DSMEM in rank order (see the header comment for why the double buffer makes one barrier enough).
+__device__ __forceinline__ void fold_parts(const Smem& s, int DS, int& buf, bool with_lp = false) {
   const int W = blockDim.x >> 5;
+  const unsigned cs = cluster_size();
+  float* dst = cs > 1 ? s.sloc + buf * (DS + 4) : s.S;
+  const int n = DS + (with_lp ? 1 : 0);
   __syncthreads();
-  for (int d = threadIdx.x; d < DS; d += blockDim.x) {
+  for (int d = threadIdx.x; d < n; d += blockDim.x) {
     float t = 0.f;
-    for (int w = 0; w < W; ++w) t += s.part[w * DS + d];
-    s.S[d] = t;
+    if (d < DS) { for (int w = 0; w < W; ++w) t += s.part[w * DS + d]; }
+    else        { for (int w = 0; w < W; ++w) t += s.red[w]; }
+    dst[d] = t;
+  }
+  if (cs > 1) {
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    cl.sync();
+    for (int d = threadIdx.x; d < n; d += blockDim.x) {
+      float t = 0.f;
+      for (unsigned r = 0; r < cs; ++r) t += cl.map_shared_rank(dst, r)[d];
+      s.S[d] = t;
+    }
+    buf ^= 1;
   }
   __syncthreads();
 }
@@ -361,13 +396,14 @@ template <int FAMILY, int CV, int NCH, bool EXT = false>
 struct ChainCtx {
   const VecModel& m;
   Smem s;
+  int buf = 0;        // sloc half of the next cluster fold
   __device__ ChainCtx(const VecModel& mm, const Smem& ss) : m(mm), s(ss) {}
 
   // full-batch gradient at s.theta into dst[] (sequential pass over every row)
   __device__ void full_grad(float* dst) {
     RandintPlan dummy{};
     row_pass<FAMILY, false, NCH, EXT>(m, true, dummy, 0u, m.own_n, s.theta, s.center, s.part);
-    fold_parts(s, m.DS);
+    fold_parts(s, m.DS, buf);
     const float rows = (float)m.own_n;
     for (int e = threadIdx.x; e < m.P; e += blockDim.x) {
       const int leaf = e / m.leaf_dim, d = e - leaf * m.leaf_dim;
@@ -402,15 +438,12 @@ struct ChainCtx {
   __device__ void partial_sums(Key k2, bool want_lp = false) {
     const RandintPlan plan = randint_plan(k2, m.n_data, m.batch);
     row_pass<FAMILY, CV, NCH, EXT>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part, want_lp ? s.red : nullptr);
-    fold_parts(s, m.DS);
+    fold_parts(s, m.DS, buf, EXT && want_lp);
   }
 
-  // log_post VALUE on the minibatch whose sums are in s.S / s.red (util.py:43-44: logprior + Ndata * mean_i loglik_i)
+  // log_post VALUE on the minibatch whose sums are in s.S (value term in s.S[DS]) (util.py:43-44: logprior + Ndata * mean_i loglik_i)
   __device__ float log_post_value() {
-    const int W = blockDim.x >> 5;
-    float lps = 0.f;
-    for (int w = 0; w < W; ++w) lps += s.red[w];
-    __syncthreads();
+    const float lps = s.S[m.DS];
     const float B = (float)m.batch;
     float lik = 0.f, pri = 0.f;
     if (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN) {
@@ -626,7 +659,9 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
   const int W = blockDim.x >> 5;
   const int PP = ((m.P > m.DS ? m.P : m.DS) + 3) & ~3;
   const Smem s = carve(smem_raw, PP, m.DS, W);
-  const int c = blockIdx.x;
+  const unsigned cs = cluster_size();
+  const int c = blockIdx.x / cs;               // one chain per cluster (cs = 1: per CTA)
+  const bool writer = cluster_rank() == 0;     // the replicas are identical; rank 0 writes samples and state back
   const int P = m.P;
   const sgmcmc_state& st = run.st;
 
@@ -674,7 +709,7 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
       ctx.expand_step_keys(sub);
       Key k2; k2.a = s.keys[2]; k2.b = s.keys[3];
       ctx.diffuse(1, run.i0, cf, 4);
-      if (run.samples) {
+      if (run.samples && writer) {
         float* dst = run.samples + (size_t)c * run.sample_chain_stride;
         for (int e = threadIdx.x; e < P; e += blockDim.x) dst[e] = s.theta[e];
       }
@@ -694,7 +729,7 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
         ctx.finish_from_sums();
         if (run.lp_out) {
           const float lp = ctx.log_post_value();
-          if (threadIdx.x == 0) run.lp_out[(size_t)c * run.K + sidx] = lp;
+          if (threadIdx.x == 0 && writer) run.lp_out[(size_t)c * run.K + sidx] = lp;
         }
         ctx.adam_step(cf);
         continue;
@@ -702,12 +737,12 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
       ctx.transition(i, sub, cf);
       const bool thinned = run.thin > 1;
       if (thinned && (sidx + 1) % run.thin != 0) continue;
-      if (run.samples) {
+      if (run.samples && writer) {
         const int slot = thinned ? (sidx + 1) / run.thin - 1 : sidx;
         float* dst = run.samples + (size_t)c * run.sample_chain_stride + (size_t)slot * P;
         for (int e = threadIdx.x; e < P; e += blockDim.x) dst[e] = s.theta[e];
       }
-      if (EXT && run.moments) {
+      if (EXT && run.moments && writer) {
         float* mo = run.moments + (size_t)c * 3 * P;
         for (int e = threadIdx.x; e < P; e += blockDim.x) { const float x = s.theta[e] - mo[2 * P + e]; mo[e] += x; mo[P + e] = fmaf(x, x, mo[P + e]); }
       }
@@ -715,6 +750,8 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
   }
 
   // write the chain state back
+  if (cs > 1) cooperative_groups::this_cluster().sync();   // no CTA may exit while a peer still reads its sloc
+  if (!writer) return;
   for (int e = threadIdx.x; e < P; e += blockDim.x) {
     const size_t o = (size_t)c * P + e;
     if (run.mode == 0) st.theta[o] = s.theta[e];
