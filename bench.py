@@ -3,10 +3,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Workload (BASELINE.json configs[1]): logistic regression N=1e6 rows, D=100, minibatch 1e4, SGLD
-(dt=1e-5), 1024 independent chains PER GPU (chains are the unit that shards; no collective on the data
-path; scaling "weak").  One bench "step" = one launch of the fused sampler kernel advancing every chain
-by --inner SGLD iterations (threefry index draw + random row gather + per-example gradients + reduction
-+ diffusion update with in-register Gaussian noise, samples written to HBM).
+(dt=1e-5), 1024 independent chains IN TOTAL, sharded over the GPUs (chains are the unit that shards:
+rank r owns chain_shard(1024, r, N), 128 chains per GPU at N=8; data replicated; no collective on the
+data path; scaling "strong").  One bench "step" = one launch of the fused sampler kernel advancing every
+chain by --inner SGLD iterations (threefry index draw + random row gather + per-example gradients +
+reduction + diffusion update with in-register Gaussian noise, samples written to HBM).  At N > 1 the
+same run with 1024 chains PER GPU is reported beside it as "weak" (zero-communication weak scaling is
+linear by construction; it is context, not the headline).
 
 value      chain-steps/s over all GPUs, inputs resident in HBM, CUDA-event timed, max over ranks.
 e2e        same metric through the public API `sampler(key, Nsamples, params)` with HOST (numpy) keys and
@@ -16,6 +19,8 @@ roofline   algorithmic bytes (B*(row+label bytes) + 8P + 4
 cpu_baseline  the numpy oracle (restatement of the reference's JAX semantics; JAX itself is not installable
            here) on the host cores, one chain per worker process, bounded sample.
 ksd        imq_KSD on N=50k x D=100 (configs[4]) in pairs/s; row blocks shard over ranks, one all-reduce.
+checks     (N > 1, outside every timed region) one chain of every rank re-run on rank 0 with the same key and launch
+           shape must be bit-identical; the distributed KSD sum must equal the single-rank sum to 1e-9.
 """
 from __future__ import annotations
 
@@ -43,6 +48,16 @@ UNIT = "chain-steps/s"
 def algorithmic_bytes_per_chain_step(batch=BATCH, dim=DIM, n_state=1):
     # B*(row_bytes(X)+row_bytes(y)) + 4P*(2 n_state) + 4P (sample emitted)
     return batch * (4 * dim + 4) + 4 * dim * 2 * n_state + 4 * dim
+
+
+def tf32_peak_tflops(bf16_peak):
+    """Dense TF32 tensor peak for the KSD roofline: the measured tcgen05 kind::tf32 rate committed under profiles/
+    (tools/tf32_peak.py) if present, else half the measured bf16 rate as a proxy."""
+    try:
+        v = json.load(open(os.path.join(ROOT, "profiles", "tf32_peak.json")))
+        return float(v["tf32_tflops"]), f"measured tcgen05 kind::tf32 peak ({v['how']})"
+    except Exception:
+        return 0.5 * bf16_peak, "0.5 x measured bf16 (no TF32 peak was measured)"
 
 
 def peaks():
@@ -131,7 +146,7 @@ def reference_arm(args):
     line = {
         "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(statistics.mean(times)), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "note": "reference arm = numpy oracle on host cores; the "
                    "reference itself needs jax==0.4.13, which is not installable in this image"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
@@ -143,8 +158,8 @@ def reference_arm(args):
 
 
 def workload_name(args):
-    return (f"logreg N={N_DATA} D={DIM} batch={args.batch} SGLD dt={DT}, {args.chains} chains/GPU, "
-            f"{args.inner} chain-steps per launch")
+    return (f"logreg N={N_DATA} D={DIM} batch={args.batch} SGLD dt={DT}, {args.chains} chains in total sharded over the "
+            f"GPUs, {args.inner} chain-steps per launch")
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -306,6 +321,95 @@ def extra_workloads(args, torch, lib, hbm_peak, X, y, theta_true):
     return out
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def _timed_launches(torch, dist, world, eng, lib, keys_host, theta0_host, K, steps, warmup):
+    """Device-resident timing of `steps` launches of K chain-steps for this rank's chains (state in HBM, one launch per
+    bench step), bracketed by barrier + synchronize; returns (max-over-ranks total ms, this rank's per-launch ms list,
+    launches, final samples, state)."""
+    from sgmcmcjax_b200._engine import keys_to_device
+
+    C = keys_host.shape[0]
+    keys_dev, _ = keys_to_device(keys_host)
+    st = eng.new_state(torch.from_numpy(theta0_host).cuda())
+    eng.init(st, keys_dev, sampler_mode=True)
+    samples = torch.empty((C, K, eng.P), dtype=torch.float32, device="cuda")
+    i0 = 0
+    for _ in range(warmup):
+        eng.run(st, i0, K, samples); i0 += K
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = lib.sgmcmc_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    t_wall0 = time.perf_counter()
+    ev[0].record()
+    for s in range(steps):
+        eng.run(st, i0, K, samples); i0 += K
+        ev[s + 1].record()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    launches = lib.sgmcmc_launch_count() - l0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    per_launch_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(steps)]
+    t = torch.tensor([ev[0].elapsed_time(ev[-1])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert torch.isfinite(samples).all(), "non-finite samples"
+    return float(t.item()), per_launch_ms, int(launches), (t_wall0, t_wall1)
+
+
+def _multi_gpu_checks(torch, dist, rank, world, lib, eng, sampler, all_keys, theta_row, shards, K, ksd_inputs):
+    """Outside every timed region.  (1) Chain sharding: the first chain of every rank, run by that rank inside its shard,
+    must equal the same key run on rank 0 - same launch shape, so bit for bit.  (2) KSD: the all-reduced tile sums must
+    equal the single-rank sum to 1e-9 relative."""
+    import ctypes as C
+
+    from sgmcmcjax_b200 import ksd
+
+    checks = {}
+    lo, hi = shards[rank]
+    w, cl = C.c_int32(0), C.c_int32(0)
+    lib.sgmcmc_launch_shape(eng._handle, hi - lo, C.byref(w), C.byref(cl))
+    th = np.tile(theta_row, (hi - lo, 1)).astype(np.float32)
+    mine = sampler(np.ascontiguousarray(all_keys[lo:hi]), K, th)[0]                 # [K, P] of this rank's first chain
+    mine_t = torch.from_numpy(np.ascontiguousarray(mine)).cuda()
+    gathered = [torch.empty_like(mine_t) for _ in range(world)]
+    dist.all_gather(gathered, mine_t)
+    shape_t = torch.tensor([w.value, cl.value], dtype=torch.int32, device="cuda")
+    shapes = [torch.empty_like(shape_t) for _ in range(world)]
+    dist.all_gather(shapes, shape_t)
+    if rank == 0:
+        worst, exact = 0.0, True
+        for r in range(world):
+            rlo, rhi = shards[r]
+            ws, cs = (int(v) for v in shapes[r].cpu())
+            os.environ["SGMCMC_WARPS_PER_CHAIN"], os.environ["SGMCMC_CLUSTER"] = str(ws), str(cs)
+            try:
+                again = sampler(np.ascontiguousarray(all_keys[rlo:rlo + 1]), K, theta_row[None].astype(np.float32))[0]
+            finally:
+                del os.environ["SGMCMC_WARPS_PER_CHAIN"], os.environ["SGMCMC_CLUSTER"]
+            got = gathered[r].cpu().numpy()
+            exact = exact and bool(np.array_equal(got, again))
+            worst = max(worst, float(np.abs(got - again).max() / max(np.abs(again).max(), 1e-30)))
+        checks["chain_of_rank_r_equals_same_key_on_rank_0"] = {"bit_identical": exact, "max_rel_diff": worst,
+                                                               "chains_checked": world, "steps": K}
+        assert exact, f"sharded chains differ from the single-GPU run of the same keys (max rel diff {worst:.3e})"
+    if ksd_inputs is not None:
+        pts, grads = ksd_inputs
+        n = int(pts.shape[0])
+        part = ksd.imq_KSD_tiles(pts, grads, rank, world)
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            whole = ksd.imq_KSD_tiles(pts, grads, 0, 1)
+            rel = float((part - whole).abs().item() / abs(whole.item()))
+            checks["distributed_ksd_equals_single_rank"] = {"rel_diff": rel, "n": n, "bar": 1e-9}
+            assert rel <= 1e-9, f"distributed KSD sum differs from the single-rank sum by {rel:.3e}"
+    dist.barrier()
+    return checks
+
+
 def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -322,7 +426,7 @@ def gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    from sgmcmcjax_b200 import _native, ksd, random, samplers
+    from sgmcmcjax_b200 import _native, ksd, parallel, random, samplers
     from sgmcmcjax_b200.models import logistic_regression as L
 
     torch.cuda.set_device(local)
@@ -335,48 +439,25 @@ def gpu_arm(args):
     theta_true, X, y = L.gen_data(random.PRNGKey(42), DIM, N_DATA)
     sampler = samplers.build_sgld_sampler(DT, L.loglikelihood, L.logprior, (X, y), args.batch, pbar=False)
     eng = sampler.engine
-    C, K, P = args.chains, args.inner, DIM
-    all_keys = random.split(random.PRNGKey(0), C * world)             # chain c of the job == key c, any N
-    keys_host = np.ascontiguousarray(all_keys[rank * C:(rank + 1) * C])
-    theta0_host = np.tile(theta_true.cpu().numpy(), (C, 1)).astype(np.float32)
+    CT, K, P = args.chains, args.inner, DIM
+    shards = [parallel.chain_shard(CT, r, world) for r in range(world)]
+    lo, hi = shards[rank]
+    C = hi - lo                                                         # this rank's chains (128 of 1024 at N = 8)
+    all_keys = random.split(random.PRNGKey(0), CT)                      # chain c of the job == key c, for any N
+    keys_host = np.ascontiguousarray(all_keys[lo:hi])
+    theta_row = theta_true.cpu().numpy().astype(np.float32)
+    theta0_host = np.tile(theta_row, (C, 1)).astype(np.float32)
 
     # ---- device-resident timing: state lives in HBM, one launch per bench step
-    from sgmcmcjax_b200._engine import keys_to_device
-    keys_dev, _ = keys_to_device(keys_host)
-    st = eng.new_state(torch.from_numpy(theta0_host).cuda())
-    eng.init(st, keys_dev, sampler_mode=True)
-    samples = torch.empty((C, K, P), dtype=torch.float32, device="cuda")
     clocks = ClockSampler(local) if rank == 0 else None      # already streaming when the timed region starts
-    i0 = 0
-    for _ in range(args.warmup):
-        eng.run(st, i0, K, samples); i0 += K
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    l0 = lib.sgmcmc_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    t_wall0 = time.perf_counter()
-    ev[0].record()
-    for s in range(args.steps):
-        eng.run(st, i0, K, samples); i0 += K
-        ev[s + 1].record()
-    torch.cuda.synchronize()
-    t_wall1 = time.perf_counter()
-    launches = lib.sgmcmc_launch_count() - l0
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    per_launch_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
-    total_ms = ev[0].elapsed_time(ev[-1])
+    total_ms_max, per_launch_ms, launches, (t_wall0, t_wall1) = _timed_launches(
+        torch, dist, world, eng, lib, keys_host, theta0_host, K, args.steps, args.warmup)
     clk = clocks.stop(t_wall0, t_wall1) if clocks else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = world * C * K * args.steps / (total_ms_max * 1e-3)
-    assert torch.isfinite(samples).all(), "non-finite samples"
+    value = CT * K * args.steps / (total_ms_max * 1e-3)
 
+    import ctypes as ct
+    w_, cl_ = ct.c_int32(0), ct.c_int32(0)
+    lib.sgmcmc_launch_shape(eng._handle, C, ct.byref(w_), ct.byref(cl_))
     kern_ms = float(statistics.mean(per_launch_ms))
     alg_bytes = algorithmic_bytes_per_chain_step(args.batch) * C * K
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
@@ -388,7 +469,17 @@ def gpu_arm(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "kernel": "vec_sampler_kernel<LOGREG>", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms}
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
+                "note": f"rank 0's GPU: {C} chains per launch as {cl_.value} CTA(s) x {w_.value} warps per chain"}
+
+    # ---- weak-scaling context at N > 1: 1024 chains on EVERY GPU (the round-1 headline)
+    weak = None
+    if world > 1 and not args.no_weak:
+        wk = random.split(random.PRNGKey(1), CT * world)
+        wt, _, _, _ = _timed_launches(torch, dist, world, eng, lib, np.ascontiguousarray(wk[rank * CT:(rank + 1) * CT]),
+                                      np.tile(theta_row, (CT, 1)).astype(np.float32), K, args.steps, args.warmup)
+        weak = {"value": world * CT * K * args.steps / (wt * 1e-3), "unit": UNIT, "chains_per_gpu": CT,
+                "ms_per_step": wt / args.steps, "scaling": "weak"}
 
     # ---- end to end through the public API: host keys + host params in, host samples out
     Ke = args.e2e_steps
@@ -406,20 +497,20 @@ def gpu_arm(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     # Ke chain-steps are counted; the init_fn gradient (samplers.py:54) is extra uncounted work
-    e2e = {"value": world * C * Ke / float(te.item()), "unit": UNIT,
+    e2e = {"value": CT * Ke / float(te.item()), "unit": UNIT,
            "h2d_bytes_per_step": int((keys_host.nbytes + theta0_host.nbytes) * K / Ke),
            "d2h_bytes_per_step": int(C * K * P * 4),
-           "note": f"sampler(key, {Ke}, params) with numpy in/out incl. init_fn; bytes scaled to one bench step "
+           "note": f"sampler(key, {Ke}, params) with numpy in/out incl. init_fn; bytes per rank, scaled to one bench step "
                    f"({K} chain-steps per chain)"}
 
     # ---- KSD (configs[4]): 50k x 100 points, row blocks over ranks, one all-reduce of a double
-    ksd_line = None
+    ksd_line, ksd_inputs = None, None
     if not args.no_ksd:
         n = args.ksd_n
         pts = theta_true[None, :] + 0.02 * random.normal(random.PRNGKey(7), (n, DIM))
         grads = -50.0 * (pts - theta_true[None, :]) + random.normal(random.PRNGKey(8), (n, DIM))
         pts, grads = pts.contiguous(), grads.contiguous()
-        r0, r1 = ksd.row_block(n, rank, world)
+        ksd_inputs = (pts, grads)
         for _ in range(2):
             ksd.imq_KSD(pts, grads, distributed=world > 1)
         torch.cuda.synchronize()
@@ -438,32 +529,37 @@ def gpu_arm(args):
         ms = float(tk.item())
         pairs = float(n) * n
         flops = 6.0 * DIM * pairs                                     # 3 Gram contractions, 2 flops per MAC
+        tf32_peak, tf32_src = tf32_peak_tflops(bf16_peak)
+        issued = 1.5 * flops / (ms * 1e-3) / 1e12
         ksd_line = {"metric": "imq_KSD pairs/sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n": n, "d": DIM,
                     "ms": ms, "ksd": float(val), "equiv_tflops": flops / (ms * 1e-3) / 1e12,
                     "method": "tcgen05 3xTF32 Gram tiles (upper triangle, dealt round-robin to ranks)",
-                    "roofline": {"bound": "tensor", "achieved": 1.5 * flops / (ms * 1e-3) / 1e12,
-                                 "peak": 0.5 * bf16_peak, "unit": "TFLOP/s",
-                                 "frac": 1.5 * flops / (ms * 1e-3) / 1e12 / (0.5 * bf16_peak),
-                                 "note": "achieved = ISSUED tf32 flops (3 split products per dot, half the tiles by "
-                                         "symmetry: 1.5 x the algorithmic 6*D*N^2); peak = 0.5 x measured bf16 "
-                                         "(no TF32 peak was measured)"}}
+                    "roofline": {"bound": "tensor", "achieved": issued, "peak": world * tf32_peak, "unit": "TFLOP/s",
+                                 "frac": issued / (world * tf32_peak),
+                                 "note": "achieved = ISSUED tf32 flops over all ranks (3 split products per dot, half the "
+                                         "tiles by symmetry: 1.5 x the algorithmic 6*D*N^2); peak = n_gpus x " + tf32_src}}
+
+    checks = None
+    if world > 1:
+        checks = _multi_gpu_checks(torch, dist, rank, world, lib, eng, sampler, all_keys, theta_row, shards, K, ksd_inputs)
 
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
-        del sampler, eng, st, samples
+        del sampler, eng
         torch.cuda.empty_cache()
         extras = extra_workloads(args, torch, lib, hbm_peak, X, y, theta_true)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "l2": "data table 400 MB > 126 MB L2, rows drawn at random "
-                       "every step (inputs larger than L2; no explicit flush)", "chains_total": world * C,
-                       "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
+                       "every step (inputs larger than L2; no explicit flush)", "chains_total": CT,
+                       "chains_per_gpu": [h_ - l_ for l_, h_ in shards],
+                       "parallelism": f"{CT} chains sharded over {world} GPU(s), no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clk, "ksd": ksd_line, "extras": extras,
+            "clocks": clk, "checks": checks, "weak": weak, "ksd": ksd_line, "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -477,7 +573,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--chains", type=int, default=CHAINS, help="chains per GPU")
+    ap.add_argument("--chains", type=int, default=CHAINS, help="chains IN TOTAL (sharded over the GPUs)")
+    ap.add_argument("--no-weak", action="store_true", help="skip the 1024-chains-per-GPU context run at N > 1")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--inner", type=int, default=10, help="chain-steps per launch (= per bench step)")
     ap.add_argument("--e2e-steps", type=int, default=50)

@@ -215,6 +215,11 @@ int sgmcmc_minibatch_indices(const uint32_t* key, int64_t n, int32_t batch, int3
 /* random.normal(key, (n,)) in fp32 (diffusions.py:67 etc.): key HOST pointer, out device f32 [n]. */
 int sgmcmc_normal(const uint32_t* key, int32_t n, float* out, void* stream);
 
+/* random.uniform(key, (n,)) on [0, 1) in fp32 (jax 0.4.13: 23 mantissa bits per word) -> device out[n]. */
+int sgmcmc_uniform(const uint32_t* key, int32_t n, float* out, void* stream);
+/* vmap(random.bernoulli)(random.split(key, n), p) as models/logistic_regression.py:59-61 draws the labels:
+ * out[i] = uniform(split(key, n)[i], ()) < p[i]; p device f32 [n], out device int32 [n]. */
+int sgmcmc_bernoulli_rows(const uint32_t* key, int32_t n, const float* p, int32_t* out, void* stream);
 /* random.split(key, num): key HOST pointer, out device u32 [num, 2]. */
 int sgmcmc_split(const uint32_t* key, int32_t num, uint32_t* out, void* stream);
 

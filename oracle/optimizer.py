@@ -28,8 +28,11 @@ def run_adam(family, data, batch_size, lr, key, n_iters, leaves, b1=0.9, b2=0.99
     lps = np.empty(n_iters, dtype=f)
     for i in range(n_iters):
         key, sub = prng.split(key)
-        idx = prng.choice_indices(sub, n, batch_size)
-        mb = tuple(a[idx] for a in data)
+        if batch_size == n:                                   # static full-batch bypass, gradient_estimation.py:41-42
+            mb = tuple(data)
+        else:
+            idx = prng.choice_indices(sub, n, batch_size)
+            mb = tuple(a[idx] for a in data)
         lps[i] = family.log_post(leaves, mb, n, np.float64)
         g = family.grad_log_post(leaves, mb, n, f)
         c1 = f(1) - np.power(f(b1), f(i + 1))

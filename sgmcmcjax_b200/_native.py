@@ -23,7 +23,7 @@ EXPORTS = [
     "sgmcmc_last_error", "sgmcmc_abi_version", "sgmcmc_launch_count", "sgmcmc_create", "sgmcmc_destroy", "sgmcmc_launch_shape", "sgmcmc_set_data",
     "sgmcmc_set_centering", "sgmcmc_fullbatch_grad", "sgmcmc_init", "sgmcmc_run", "sgmcmc_run_thinned", "sgmcmc_optimize", "sgmcmc_kernel_step",
     "sgmcmc_set_row_shard", "sgmcmc_sum_width", "sgmcmc_set_centering_grad", "sgmcmc_shard_init", "sgmcmc_shard_step",
-    "sgmcmc_minibatch_indices", "sgmcmc_normal", "sgmcmc_split", "sgmcmc_ksd_imq_partial", "sgmcmc_ksd_workspace_bytes", "sgmcmc_ksd_imq_tc",
+    "sgmcmc_minibatch_indices", "sgmcmc_normal", "sgmcmc_uniform", "sgmcmc_bernoulli_rows", "sgmcmc_split", "sgmcmc_ksd_imq_partial", "sgmcmc_ksd_workspace_bytes", "sgmcmc_ksd_imq_tc",
 ]
 
 
@@ -104,6 +104,8 @@ def load(build_if_missing: bool = True):
         "sgmcmc_minibatch_indices": [C.POINTER(C.c_uint32), i64, i32, vp, vp],
         "sgmcmc_normal": [C.POINTER(C.c_uint32), i32, vp, vp],
         "sgmcmc_split": [C.POINTER(C.c_uint32), i32, vp, vp],
+        "sgmcmc_uniform": [C.POINTER(C.c_uint32), i32, vp, vp],
+        "sgmcmc_bernoulli_rows": [C.POINTER(C.c_uint32), i32, vp, vp, vp],
         "sgmcmc_ksd_imq_partial": [vp, vp, i32, i32, i32, i32, vp, vp],
         "sgmcmc_ksd_imq_tc": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
     }

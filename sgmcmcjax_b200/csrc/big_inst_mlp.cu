@@ -7,7 +7,7 @@ template cudaError_t launch_big_inst<SGMCMC_FAMILY_MLP>(const BigModel&, const B
 }  // namespace sg
 
 // phase timers of this translation unit's kernel (tools/phase_timing.py)
-#ifdef SG_PHASE_TIMING
+#if defined(SG_PHASE_TIMING) && !defined(SG_PHASE_TIMING_VEC)
 extern "C" int sgmcmc_debug_phase_cycles(unsigned long long* out16, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out16, sg::g_phase_cycles, sizeof(unsigned long long) * 16);

@@ -81,20 +81,6 @@ struct BigRun {
 // for every leaf into dst[P] - the noise of the langevin step that will run with `key`.
 struct NoiseJob { Key key; float* dst; bool valid; };
 
-// Optional phase timers (-DSG_PHASE_TIMING): cycles of block 0 / thread 0 per phase, read back with sgmcmc_debug_phase_cycles.
-#ifdef SG_PHASE_TIMING
-static __device__ unsigned long long g_phase_cycles[16];   // per translation unit: read where the kernel is instantiated
-#define SG_T0() const long long sg_t0__ = clock64()
-#define SG_T1(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_phase_cycles[slot], (unsigned long long)(clock64() - sg_t0__)); } while (0)
-#define SG_TA(var) long long var = clock64()
-#define SG_TB(slot, var) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long n__ = clock64(); atomicAdd(&g_phase_cycles[slot], (unsigned long long)(n__ - var)); var = n__; } } while (0)
-#else
-#define SG_T0() do {} while (0)
-#define SG_T1(slot) do {} while (0)
-#define SG_TA(var) do {} while (0)
-#define SG_TB(slot, var) do {} while (0)
-#endif
-
 struct BigSmem {
   uint32_t keys[2 * (4 + 2 * MAXL)];
   float alpha[MAXL];

@@ -57,8 +57,8 @@ struct sgmcmc_handle {
   size_t k2_scratch_bytes = 0;
   int num_sms = 148;
   bool has_data = false, has_center = false;
-  // (threads, cluster asked, extended kernel) -> cluster shape the device can co-schedule (vec_launch.cuh)
-  std::map<std::tuple<int, int, int>, int> cluster_ok;
+  // (threads, cluster asked, extended kernel, chains) -> cluster shape the device can co-schedule (vec_launch.cuh)
+  std::map<std::tuple<int, int, int, int>, int> cluster_ok;
 };
 
 namespace sg {
@@ -83,6 +83,17 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, const int* __restr
 __global__ void pack_ratings_kernel(const int* __restrict__ ij, const float* __restrict__ y, int4* __restrict__ out, size_t n) {
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
     out[t] = make_int4(ij[2 * t], ij[2 * t + 1], __float_as_int(y[t]), 0);
+}
+
+// pmf: count the ratings whose (user, item) ids fall outside [0, n_users) x [0, n_items) - they would index past the
+// factor matrices in FamilyGrad<PMF>::lik_pass (1-based MovieLens ids do exactly that)
+__global__ void pmf_check_ids_kernel(const int* __restrict__ ij, size_t n, int nu, int ni, unsigned* __restrict__ bad) {
+  unsigned mine = 0;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = ij[2 * t], j = ij[2 * t + 1];
+    mine += (i < 0 || i >= nu || j < 0 || j >= ni) ? 1u : 0u;
+  }
+  if (mine) atomicAdd(bad, mine);
 }
 
 // K2 stage 1: CTA (split, m) sums its row range at thetas[m] into partial[m][split][DS].
@@ -137,6 +148,24 @@ __global__ void normal_kernel(Key key, unsigned n, float* out) {
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) out[e] = normal_at(key, e, n);
 }
 
+// random.uniform(key, (n,)) on [0, 1): 23 mantissa bits of each word
+__global__ void uniform_kernel(Key key, unsigned n, float* out) {
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    out[e] = __uint_as_float((stream_word(key, e, n) >> 9) | 0x3F800000u) - 1.0f;
+}
+
+// vmap(random.bernoulli)(split(key, n), p) of models/logistic_regression.py:59-61: row i draws
+// uniform(split(key, n)[i], ()) < p[i]; a shape-() draw is word 0 of the block of counters (0, pad 0)
+__global__ void bernoulli_rows_kernel(Key key, unsigned n, const float* __restrict__ p, int* __restrict__ out) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const Key ki = split_at(key, n, i);
+    uint32_t w0 = 0u, w1 = 0u;
+    threefry(ki, w0, w1);
+    const float u = __uint_as_float((w0 >> 9) | 0x3F800000u) - 1.0f;
+    out[i] = u < p[i] ? 1 : 0;
+  }
+}
+
 __global__ void split_kernel(Key key, unsigned num, uint32_t* out) {
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < 2u * num; e += gridDim.x * blockDim.x)
     out[e] = stream_word(key, e, 2u * num);
@@ -151,8 +180,8 @@ struct VecShape { int warps, cluster; };     // warps per CTA, CTAs per chain (a
 template <int FAMILY, int CV, int NCH, bool EXT>
 int launch_vec_kernel(sgmcmc_handle* h, const sg::VecRun& run, VecShape shape, cudaStream_t stream) {
   const int PP = ((h->P > h->DS ? h->P : h->DS) + 3) & ~3;
-  const size_t smem = sg::vec_smem_bytes(PP, h->DS, shape.warps);
-  const auto key = std::make_tuple(shape.warps * 32, shape.cluster, EXT ? 1 : 0);
+  const size_t smem = sg::vec_smem_bytes(PP, h->DS, shape.warps, shape.cluster);
+  const auto key = std::make_tuple(shape.warps * 32, shape.cluster, EXT ? 1 : 0, run.st.n_chains);
   const auto hit = h->cluster_ok.find(key);
   int used = hit != h->cluster_ok.end() ? hit->second : shape.cluster;
   CUDA_TRY((sg::launch_vec_inst<FAMILY, CV, NCH, EXT>(h->vm, run, shape.warps * 32, used, smem, stream,   // csrc/vec_inst_*.cu
@@ -181,33 +210,31 @@ int launch_vec_nch(sgmcmc_handle* h, const sg::VecRun& run, VecShape shape, cuda
 }
 
 // Launch shape of the vector sampler.  The device holds num_sms x 32 resident warps of this kernel (64 registers per
-// thread); a chain gets its share of them.  Up to 32 / nch warps fit one CTA; a chain that can have more (fewer chains
-// than SMs: config 2 split over 8 GPUs, the README's single chain) gets a cluster of 8-warp CTAs whose warps share the
-// minibatch (csrc/vec_sampler.cuh header).  SGMCMC_WARPS_PER_CHAIN (per CTA) / SGMCMC_CLUSTER override.
+// thread); a chain gets its share of them, but no more warps than the minibatch has groups of 8 rows.  Up to 32 / nch
+// warps fit one CTA, and one such CTA per chain already saturates HBM from 128 SMs (measured: 128 chains of config 2,
+// 1 x 32 warps 0.91-0.96 of the copy peak, clusters of 2 x 16 / 4 x 8 the same or less).  Only when there are fewer
+// chains than HALF the SMs does a chain get a thread-block cluster (csrc/vec_sampler.cuh header): num_sms / n_chains
+// CTAs, at most 16 (README config, one chain: 8.3 us per step in one CTA, 4.3 us as 16 CTAs x 8 warps).
+// SGMCMC_WARPS_PER_CHAIN (per CTA) / SGMCMC_CLUSTER override.
 VecShape choose_shape(const sgmcmc_handle* h, int n_chains) {
   const int max_warps = 32 / h->nch;
-  const long share = (long)h->num_sms * 32 / (n_chains > 0 ? n_chains : 1);   // warps this chain can have
-  // a warp needs a full 8-row group of the minibatch (16 rows: two threefry half-streams) to be worth its barriers
-  const long useful = std::max<long>(4, (long)h->vm.batch / 16);
+  if (n_chains < 1) n_chains = 1;
+  const long share = (long)h->num_sms * 32 / n_chains;                 // warps this chain can have
+  const long useful = std::max<long>(4, (long)h->vm.batch / 8);       // one full 8-row group per warp
   const long want = std::min(share, useful);
   int w = env_int("SGMCMC_WARPS_PER_CHAIN", 0), cl = env_int("SGMCMC_CLUSTER", 0);
-  if (w <= 0 && cl <= 0) {
-    if (want <= max_warps) {
-      cl = 1; w = 4;
-      while (w * 2 <= want) w *= 2;
-    } else {
-      w = std::min(8, max_warps);
-      cl = (int)std::min<long>(16, want / w);
-    }
-  } else if (w <= 0) {
+  if (cl <= 0) {
+    cl = std::min(16, h->num_sms / n_chains);
+    if (cl < 2 || want <= max_warps) cl = 1;
+  }
+  if (w <= 0) {
+    const long per_cta = (want + cl - 1) / cl;
     w = 4;
-    while (w * 2 <= want / cl && w * 2 <= max_warps) w *= 2;
-  } else if (cl <= 0) {
-    cl = 1;
+    if (cl > 1) { while (w < per_cta) w *= 2; }                        // clusters: round up (each CTA sits alone on its SM)
+    else { while (w * 2 <= per_cta) w *= 2; }                          // one CTA per chain: round down (CTAs share SMs)
   }
   if (w > max_warps) w = max_warps;
   if (w < 1) w = 1;
-  if (cl < 1) cl = 1;
   if (cl > 16) cl = 16;
   return VecShape{w, cl};
 }
@@ -391,7 +418,7 @@ int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
     return fail(SGMCMC_E_UNSUPPORTED, "unknown model family");
   if (cfg->estimator < 0 || cfg->estimator > SGMCMC_EST_SVRG) return fail(SGMCMC_E_INVALID, "bad estimator");
   if (cfg->diffusion < 0 || cfg->diffusion > SGMCMC_DIFF_ADAM_OPT) return fail(SGMCMC_E_INVALID, "bad diffusion");
-  if (cfg->diffusion == SGMCMC_DIFF_ADAM_OPT && (cfg->estimator != SGMCMC_EST_STANDARD || (int64_t)cfg->batch >= cfg->n_data ||
+  if (cfg->diffusion == SGMCMC_DIFF_ADAM_OPT && (cfg->estimator != SGMCMC_EST_STANDARD || (int64_t)cfg->batch > cfg->n_data ||
                                                  cfg->family == SGMCMC_FAMILY_PMF || cfg->family == SGMCMC_FAMILY_MLP))
     return fail(SGMCMC_E_UNSUPPORTED, "the optimiser covers the vector families with the standard minibatch estimator");
   if (cfg->n_data <= 0 || cfg->n_data > 0x7fffffffLL) return fail(SGMCMC_E_INVALID, "n_data out of range");
@@ -469,6 +496,7 @@ int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
   vm.n_leaves = cfg->n_leaves; vm.leaf_dim = cfg->data_dim; vm.P = h->P; vm.DS = h->DS;
   vm.n_data = (unsigned)cfg->n_data; vm.batch = (unsigned)cfg->batch;
   vm.own_lo = 0u; vm.own_n = vm.n_data;
+  { const uint32_t mm = 65536u % vm.n_data; vm.randint_mult = (mm * mm) % vm.n_data; }   // uint32 wrap-around as in jax
   vm.zc_f4 = zc ? zc_f4 : -1;
   vm.full_batch = (cfg->estimator == SGMCMC_EST_STANDARD && (int64_t)cfg->batch == cfg->n_data) ? 1 : 0;
   vm.leapfrog = cfg->leapfrog; vm.update_rate = cfg->update_rate;
@@ -506,8 +534,26 @@ int sgmcmc_set_data(sgmcmc_handle* h, const void* xv, const void* y, void* strea
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)h->cfg.n_data;
   if (h->cfg.family == SGMCMC_FAMILY_PMF) {
-    if (!h->data0) CUDA_TRY(cudaMalloc(&h->data0, n * sizeof(int4)));
     const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->num_sms * 16);
+    {   // one-time range check of the ids (synchronises the stream; ingestion is not a hot path)
+      unsigned* bad_dev = nullptr;
+      unsigned bad = 0;
+      CUDA_TRY(cudaMalloc(&bad_dev, sizeof(unsigned)));
+      cudaError_t e = cudaMemsetAsync(bad_dev, 0, sizeof(unsigned), s);
+      if (e == cudaSuccess) {
+        sg::pmf_check_ids_kernel<<<blocks, 256, 0, s>>>((const int*)xv, n, h->cfg.dims[0], h->cfg.dims[1], bad_dev);
+        e = cudaGetLastError(); ++g_launches;
+      }
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, bad_dev, sizeof(unsigned), cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      cudaFree(bad_dev);
+      CUDA_TRY(e);
+      if (bad)
+        return fail(SGMCMC_E_INVALID, std::to_string(bad) + " pmf rating(s) have a (user, item) id outside [0, " +
+                                          std::to_string(h->cfg.dims[0]) + ") x [0, " + std::to_string(h->cfg.dims[1]) +
+                                          "): ids are 0-based row numbers of U and V");
+    }
+    if (!h->data0) CUDA_TRY(cudaMalloc(&h->data0, n * sizeof(int4)));
     sg::pack_ratings_kernel<<<blocks, 256, 0, s>>>((const int*)xv, (const float*)y, (int4*)h->data0, n);
     CUDA_TRY(cudaGetLastError()); ++g_launches;
     h->bm.data0 = h->data0;
@@ -746,6 +792,24 @@ int sgmcmc_normal(const uint32_t* key, int32_t n, float* out, void* stream) {
   sg::Key k{key[0], key[1]};
   const int blocks = std::min((n + 255) / 256, 148 * 8);
   sg::normal_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(k, (unsigned)n, out);
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
+  return SGMCMC_OK;
+}
+
+int sgmcmc_uniform(const uint32_t* key, int32_t n, float* out, void* stream) {
+  if (!key || !out || n <= 0) return fail(SGMCMC_E_INVALID, "bad argument");
+  sg::Key k{key[0], key[1]};
+  const int blocks = std::min((n + 255) / 256, 148 * 8);
+  sg::uniform_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(k, (unsigned)n, out);
+  CUDA_TRY(cudaGetLastError()); ++g_launches;
+  return SGMCMC_OK;
+}
+
+int sgmcmc_bernoulli_rows(const uint32_t* key, int32_t n, const float* p, int32_t* out, void* stream) {
+  if (!key || !p || !out || n <= 0) return fail(SGMCMC_E_INVALID, "bad argument");
+  sg::Key k{key[0], key[1]};
+  const int blocks = std::min((n + 255) / 256, 148 * 8);
+  sg::bernoulli_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(k, (unsigned)n, p, out);
   CUDA_TRY(cudaGetLastError()); ++g_launches;
   return SGMCMC_OK;
 }

@@ -13,6 +13,20 @@
 
 namespace sg {
 
+// Optional phase timers (-DSG_PHASE_TIMING): cycles of block 0 / thread 0 per phase, read back with sgmcmc_debug_phase_cycles.
+#ifdef SG_PHASE_TIMING
+static __device__ unsigned long long g_phase_cycles[32];   // per translation unit: read where the kernel is instantiated
+#define SG_T0() const long long sg_t0__ = clock64()
+#define SG_T1(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_phase_cycles[slot], (unsigned long long)(clock64() - sg_t0__)); } while (0)
+#define SG_TA(var) long long var = clock64()
+#define SG_TB(slot, var) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long n__ = clock64(); atomicAdd(&g_phase_cycles[slot], (unsigned long long)(n__ - var)); var = n__; } } while (0)
+#else
+#define SG_T0() do {} while (0)
+#define SG_T1(slot) do {} while (0)
+#define SG_TA(var) do {} while (0)
+#define SG_TB(slot, var) do {} while (0)
+#endif
+
 struct Key { uint32_t a, b; };
 
 // plain C rotate (ptxas emits SHF.L.W): __funnelshift_l is an `asm volatile` in the CUDA headers, and volatile asms

@@ -7,7 +7,7 @@ namespace sg {
 
 // cudaFuncSetAttribute (if the dynamic shared memory needs it) + launch of vec_sampler_kernel<FAMILY, CV, NCH, EXT>
 // with one cluster of `cluster` CTAs (1, 2, 4, 8 or 16) of `threads` threads per chain.  A cluster shape the device
-// cannot co-schedule is shrunk until it fits (validate = true: asks cudaOccupancyMaxActiveClusters first; the caller
+// cannot co-schedule for all chains at once is shrunk until it can (validate = true: asks cudaOccupancyMaxActiveClusters first; the caller
 // caches the answer, *cluster_used, and passes validate = false from then on).
 template <int FAMILY, int CV, int NCH, bool EXT>
 cudaError_t launch_vec_inst(const VecModel& m, const VecRun& run, int threads, int cluster, size_t smem, cudaStream_t stream,
@@ -41,7 +41,10 @@ cudaError_t launch_vec_inst(const VecModel& m, const VecRun& run, int threads, i
     if (!validate) break;
     int active = 0;
     const cudaError_t e = cudaOccupancyMaxActiveClusters(&active, kern, &cfg);
-    if (e == cudaSuccess && active > 0) break;
+    // every chain's cluster should be resident at once (a second wave doubles the launch time); the device places at
+    // most `active` clusters of this shape (one GPC holds 16 - 20 SMs)
+    if (e == cudaSuccess && active >= run.st.n_chains) break;
+    if (e == cudaSuccess && active > 0 && cluster == 2) break;
     (void)cudaGetLastError();
   }
   if (cluster_used) *cluster_used = cluster;

@@ -20,9 +20,10 @@
 // pass) is split over the warps of all CTAs of the cluster; every CTA holds a full replica of the chain state in its
 // own shared memory and runs the (tiny, D-element) key tree and diffusion update redundantly - same keys, same
 // arithmetic, bit-identical replicas - so the ONLY exchange per gradient estimate is the [DS] partial row sum:
-// every CTA folds its warps into Sloc[buf], one cluster barrier, every CTA adds the Sloc[buf] of all ranks over
-// DSMEM in rank order (same order everywhere -> replicas stay identical).  Sloc is double-buffered, so one barrier
-// per estimate is enough (a CTA can only reach the estimate after next once every peer has passed the next barrier,
+// every CTA folds its warps and PUSHES the result into slot recv[buf][its rank] of every CTA of the cluster (remote
+// shared-memory stores), one cluster barrier, every CTA adds its own recv[buf][0 .. cs) from local shared memory in
+// rank order (same order everywhere -> replicas stay identical).  recv is double-buffered, so one barrier per
+// estimate is enough (a CTA can only reach the estimate after next once every peer has passed the next barrier,
 // i.e. has finished reading this one).  Rank 0 alone writes samples and state back.
 #pragma once
 #include <cooperative_groups.h>
@@ -38,6 +39,7 @@ struct VecModel {
   int family, estimator, diffusion, flags;
   int n_leaves, leaf_dim, P, DS;
   unsigned n_data, batch;
+  unsigned randint_mult;   // ((2^16 % n_data)^2 mod 2^32) % n_data: the multiplier of jax's randint (prng.cuh RandintPlan)
   int full_batch;          // standard estimator with batch == n_data (gradient_estimation.py:41-42)
   int leapfrog, update_rate;
   float scale;             // fp32(n_data) / fp32(batch)   (util.py:44, mean then * Ndata)
@@ -80,13 +82,13 @@ constexpr int SHARD_UPDATE2 = 1, SHARD_STEP = 2;
 // shared-memory carve-up (dynamic): all arrays padded to DSP = max(P, DS) rounded to 4
 struct Smem {
   float *theta, *aux1, *aux2, *grad, *center, *fb, *S, *part;
-  float* sloc;        // [2][DS + 4]: this CTA's folded partial sums (+ log-likelihood value term), read by cluster peers
+  float* recv;        // [2][cs][DS + 4]: folded partial sums (+ log-likelihood value term) PUSHED here by every CTA of the cluster
   float* alpha;       // [MAXL]
   float* red;         // [32] block-reduction scratch
   uint32_t* keys;     // [2 * (4 + 2*MAXL)] step keys
 };
 
-__device__ __forceinline__ Smem carve(float* base, int PP, int DS, int W) {
+__device__ __forceinline__ Smem carve(float* base, int PP, int DS, int W, int cs) {
   Smem s;
   s.theta = base;            base += PP;
   s.aux1 = base;             base += PP;
@@ -96,15 +98,20 @@ __device__ __forceinline__ Smem carve(float* base, int PP, int DS, int W) {
   s.fb = base;               base += PP;
   s.S = base;                base += DS + 4;     // [DS] sums, [DS] = log-likelihood value term (optimiser)
   s.part = base;             base += W * DS;
-  s.sloc = base;             base += 2 * (DS + 4);
+  s.recv = base;             base += cs > 1 ? 2 * cs * (DS + 4) : 0;
   s.alpha = base;            base += MAXL;
   s.red = base;              base += 32;
   s.keys = reinterpret_cast<uint32_t*>(base);
   return s;
 }
+// key words: [0,4) k1 k2 of the step, [4, 4 + 2 MAXL) leaf keys of k1, [20,24) randint plan keys (split(k2)),
+// [24,32) two slots of (next carry, next sub) computed one step ahead (expand_step_keys)
 constexpr int SMEM_KEY_WORDS = 2 * (4 + 2 * MAXL);
-__host__ __device__ inline size_t vec_smem_bytes(int PP, int DS, int W) {
-  return sizeof(float) * (size_t)(6 * PP + (DS + 4) + W * DS + 2 * (DS + 4) + MAXL + 32) + sizeof(uint32_t) * SMEM_KEY_WORDS;
+constexpr int KEY_PLAN = 4 + 2 * MAXL, KEY_NEXT = KEY_PLAN + 4;
+static_assert(KEY_NEXT + 8 <= SMEM_KEY_WORDS, "key slots");
+__host__ __device__ inline size_t vec_smem_bytes(int PP, int DS, int W, int cs) {
+  return sizeof(float) * (size_t)(6 * PP + (DS + 4) + W * DS + (cs > 1 ? 2 * cs * (DS + 4) : 0) + MAXL + 32) +
+         sizeof(uint32_t) * SMEM_KEY_WORDS;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -117,6 +124,23 @@ __device__ __forceinline__ float sigmoid_f(float z) {
   const float e = expf(-fabsf(z));
   const float s = 1.0f / (1.0f + e);
   return z >= 0.0f ? s : e * s;
+}
+
+// one float4 of a data row.  SG_ROW_LOAD selects the cache policy (experiments): 0 = ld.global.nc (__ldg),
+// 1 = ld.global.cg (L2 only), 2 = ld.global.nc.L1::no_allocate
+#ifndef SG_ROW_LOAD
+#define SG_ROW_LOAD 0
+#endif
+__device__ __forceinline__ float4 load_row4(const float4* p) {
+#if SG_ROW_LOAD == 1
+  return __ldcg(p);
+#elif SG_ROW_LOAD == 2
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
@@ -193,6 +217,7 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
   // short streams (h < 32 W, e.g. one chain with batch 1000): spread the blocks over ALL warps instead of
   // filling 32 lanes of the first few, so the row groups of a step run in parallel rather than back to back
   const unsigned lpw = h < W * 32u ? (h + W - 1u) / W : 32u;
+  SG_TA(t_rp);
   for (unsigned b0 = gwarp * lpw; b0 < h; b0 += W * lpw) {
     const unsigned b = b0 + lane;
     int jA = -1, jB = -1;
@@ -209,8 +234,12 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
     // sharded: owned rows are scattered over the lanes - compact them so that every group of 8 is full
     const unsigned maskA = sharded ? __ballot_sync(FULL, jA >= 0) : 0u, maskB = sharded ? __ballot_sync(FULL, jB >= 0) : 0u;
     const int cntA = __popc(maskA), cntB = __popc(maskB);
+    SG_TB(10, t_rp);
+    // the rows of this batch as one list of 2 lpw entries: [0, lpw) = jA of lanes 0 .. lpw-1, [lpw, 2 lpw) = their jB;
+    // short streams (lpw < 32) so fill their groups of 8 from both halves instead of running two half-empty ones
+    const int ngrp = sharded ? 8 : (int)((2u * lpw + 7u) >> 3);
 #pragma unroll 1
-    for (int grp = 0; grp < 8; ++grp) {
+    for (int grp = 0; grp < ngrp; ++grp) {
       const int src = (grp < 4) ? jA : jB;
       const int base = (grp & 3) * 8;
       int r[8];
@@ -224,19 +253,26 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
           const int v = __shfl_sync(FULL, src, from & 31);
           r[u] = base + u < cnt ? v : -1;
         }
-      } else {
+      } else if (lpw == 32u) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) r[u] = __shfl_sync(FULL, src, base + u);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const unsigned e = 8u * grp + u;
+          const int v = __shfl_sync(FULL, e >= lpw ? jB : jA, (e >= lpw ? e - lpw : e) & 31u);
+          r[u] = e < 2u * lpw ? v : -1;
+        }
       }
-      // validity is monotone in the stream position, so an invalid first row ends the group
-      if (r[0] < 0) continue;
+      // rows past the end of the stream are -1 (loaded as zeros); a group without any row is skipped
+      if ((r[0] & r[1] & r[2] & r[3] & r[4] & r[5] & r[6] & r[7]) < 0) continue;
       float4 x[8][NCH];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           x[u][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok[c] && r[u] >= 0) x[u][c] = __ldg(rows + (size_t)r[u] * row_f4 + lane + 32 * c);
+          if (ok[c] && r[u] >= 0) x[u][c] = load_row4(rows + (size_t)r[u] * row_f4 + lane + 32 * c);
         }
       }
       // CV == 2: the lanes of quad u (where reduce8 leaves theta . x~ of row u) read that row's center . x~ themselves;
@@ -244,7 +280,7 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
       float zc = 0.f;
       if (CV == 2) {
         int ru;
-        if (sharded) {
+        if (sharded || lpw != 32u) {
           ru = r[0];
 #pragma unroll
           for (int u = 1; u < 8; ++u) ru = (lane >> 2) == u ? r[u] : ru;
@@ -302,6 +338,7 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
       }
     }
   }
+  SG_TB(11, t_rp);
 #pragma unroll
   for (int c = 0; c < NCH; ++c)
     if (ok[c]) reinterpret_cast<float4*>(s_part + warp * DS)[lane + 32 * c] = acc[c];
@@ -342,31 +379,44 @@ __global__ void zc_column_kernel(float* __restrict__ rows, unsigned n_rows, int 
 }
 
 // part[W][DS] (+ red[W], the log-likelihood value terms, if with_lp) -> S[DS] (+ S[DS]); fixed summation order.
-// In a cluster: local fold into sloc[buf], ONE cluster barrier, then every CTA adds the sloc[buf] of all ranks over
-// DSMEM in rank order (see the header comment for why the double buffer makes one barrier enough).
+// In a cluster: the local fold is pushed to recv[buf][rank] of every CTA, ONE cluster barrier, then every CTA adds
+// its recv[buf][0 .. cs) in rank order (see the header comment for why the double buffer makes one barrier enough).
 __device__ __forceinline__ void fold_parts(const Smem& s, int DS, int& buf, bool with_lp = false) {
   const int W = blockDim.x >> 5;
   const unsigned cs = cluster_size();
-  float* dst = cs > 1 ? s.sloc + buf * (DS + 4) : s.S;
-  const int n = DS + (with_lp ? 1 : 0);
+  const int n = DS + (with_lp ? 1 : 0), stride = DS + 4;
+  SG_TA(t_f);
   __syncthreads();
-  for (int d = threadIdx.x; d < n; d += blockDim.x) {
-    float t = 0.f;
-    if (d < DS) { for (int w = 0; w < W; ++w) t += s.part[w * DS + d]; }
-    else        { for (int w = 0; w < W; ++w) t += s.red[w]; }
-    dst[d] = t;
-  }
-  if (cs > 1) {
-    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
-    cl.sync();
+  SG_TB(12, t_f);
+  if (cs == 1) {
     for (int d = threadIdx.x; d < n; d += blockDim.x) {
       float t = 0.f;
-      for (unsigned r = 0; r < cs; ++r) t += cl.map_shared_rank(dst, r)[d];
+      if (d < DS) { for (int w = 0; w < W; ++w) t += s.part[w * DS + d]; }
+      else        { for (int w = 0; w < W; ++w) t += s.red[w]; }
+      s.S[d] = t;
+    }
+  } else {
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    float* slot = s.recv + ((size_t)buf * cs + cluster_rank()) * stride;
+    for (int d = threadIdx.x; d < n; d += blockDim.x) {
+      float t = 0.f;
+      if (d < DS) { for (int w = 0; w < W; ++w) t += s.part[w * DS + d]; }
+      else        { for (int w = 0; w < W; ++w) t += s.red[w]; }
+      for (unsigned r = 0; r < cs; ++r) cl.map_shared_rank(slot, r)[d] = t;
+    }
+    SG_TB(5, t_f);
+    cl.sync();
+    SG_TB(6, t_f);
+    const float* mine = s.recv + (size_t)buf * cs * stride;
+    for (int d = threadIdx.x; d < n; d += blockDim.x) {
+      float t = 0.f;
+      for (unsigned r = 0; r < cs; ++r) t += mine[r * stride + d];
       s.S[d] = t;
     }
     buf ^= 1;
   }
   __syncthreads();
+  SG_TB(7, t_f);
 }
 
 // grad_log_post at theta from the folded row sum S (util.py:43-44).
@@ -396,7 +446,10 @@ template <int FAMILY, int CV, int NCH, bool EXT = false>
 struct ChainCtx {
   const VecModel& m;
   Smem s;
-  int buf = 0;        // sloc half of the next cluster fold
+  int buf = 0;              // recv half of the next cluster fold
+  bool plan_cached = false; // keys[KEY_PLAN ..] hold split(k2) of the estimate about to run
+  int look_slot = -1;       // >= 0: the next expand_step_keys also splits look_carry into keys[KEY_NEXT + 4 look_slot ..]
+  Key look_carry{0u, 0u};
   __device__ ChainCtx(const VecModel& mm, const Smem& ss) : m(mm), s(ss) {}
 
   // full-batch gradient at s.theta into dst[] (sequential pass over every row)
@@ -431,13 +484,31 @@ struct ChainCtx {
       return;
     }
     partial_sums(k2);
+    SG_TA(t_fs);
     finish_from_sums();
+    SG_TB(8, t_fs);
   }
 
   // minibatch sums over the rows of this rank: s.S[d] = sum_i x_i (gaussian) / sum_i (w_i [- w_c,i]) x~_i (logreg)
-  __device__ void partial_sums(Key k2, bool want_lp = false) {
-    const RandintPlan plan = randint_plan(k2, m.n_data, m.batch);
+  __device__ void partial_sums(Key k2, bool want_lp = false, bool all_rows = false) {
+    SG_TA(t_ps);
+    RandintPlan plan{};
+    if (all_rows) {                                      // static full-batch bypass (gradient_estimation.py:41-42): no RNG
+      row_pass<FAMILY, false, NCH, EXT>(m, true, plan, 0u, m.own_n, s.theta, s.center, s.part, want_lp ? s.red : nullptr);
+      fold_parts(s, m.DS, buf, EXT && want_lp);
+      return;
+    }
+    if (plan_cached) {                                   // split(k2) was taken next to the leaf keys
+      plan.k_hi.a = s.keys[KEY_PLAN]; plan.k_hi.b = s.keys[KEY_PLAN + 1];
+      plan.k_lo.a = s.keys[KEY_PLAN + 2]; plan.k_lo.b = s.keys[KEY_PLAN + 3];
+      plan.span = m.n_data; plan.batch = m.batch; plan.mult = m.randint_mult;
+      plan_cached = false;
+    } else {
+      plan = randint_plan(k2, m.n_data, m.batch);
+    }
+    SG_TB(3, t_ps);
     row_pass<FAMILY, CV, NCH, EXT>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part, want_lp ? s.red : nullptr);
+    SG_TB(4, t_ps);
     fold_parts(s, m.DS, buf, EXT && want_lp);
   }
 
@@ -507,17 +578,32 @@ struct ChainCtx {
     Key k; k.a = s.keys[slot + 2 * leaf]; k.b = s.keys[slot + 2 * leaf + 1]; return k;
   }
 
-  // warp 0 expands `key` into split(key)[0], split(key)[1] and split(split(key)[0], n_leaves):
-  //   keys[0..1] = k1, keys[2..3] = k2, keys[4 + 2j ..] = leaf keys of k1
+  // The key tree of one langevin step, spread over three warps that run side by side (state-independent work,
+  // one barrier):
+  //   warp 0: k1, k2 = split(key) -> keys[0..3];  leaf keys split(k1, n_leaves) -> keys[4 + 2j ..]
+  //   warp 1: k2 again;  the randint plan's keys split(k2) (jax draws hi / lo bits with them) -> keys[KEY_PLAN ..]
+  //   warp 2: if the sampler loop asked for it (look_slot >= 0): split(carry) of the NEXT iteration
+  //           (samplers.py:49) -> keys[KEY_NEXT + 4 look_slot ..] = (next carry, next sub)
+  // (CTAs with fewer warps: the last warp takes the remaining roles in turn.)
   __device__ void expand_step_keys(Key key) {
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      uint32_t w = lane < 4 ? stream_word(key, lane, 4u) : 0u;
-      Key k1; k1.a = __shfl_sync(FULL, w, 0); k1.b = __shfl_sync(FULL, w, 1);
-      if (lane < 4) s.keys[lane] = w;
-      const uint32_t nl = m.n_leaves;
-      if (lane < 2 * (int)nl) s.keys[4 + lane] = stream_word(k1, lane, 2u * nl);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int w_plan = W > 1 ? 1 : 0, w_next = W > 2 ? 2 : W - 1;
+    if (warp == 0 || warp == w_plan) {
+      const uint32_t w = lane < 4 ? stream_word(key, lane, 4u) : 0u;        // lanes 0..3: k1.a k1.b k2.a k2.b
+      if (warp == 0) {
+        Key k1; k1.a = __shfl_sync(FULL, w, 0); k1.b = __shfl_sync(FULL, w, 1);
+        if (lane < 4) s.keys[lane] = w;
+        const uint32_t nl = m.n_leaves;
+        if (lane < 2 * (int)nl) s.keys[4 + lane] = stream_word(k1, lane, 2u * nl);
+      }
+      if (warp == w_plan) {
+        Key k2; k2.a = __shfl_sync(FULL, w, 2); k2.b = __shfl_sync(FULL, w, 3);
+        if (lane < 4) s.keys[KEY_PLAN + lane] = stream_word(k2, lane, 4u);   // k_hi.a k_hi.b k_lo.a k_lo.b
+      }
     }
+    if (look_slot >= 0 && warp == w_next && lane < 4) s.keys[KEY_NEXT + 4 * look_slot + lane] = stream_word(look_carry, lane, 4u);
+    look_slot = -1;
+    plan_cached = true;
     __syncthreads();
   }
 
@@ -631,10 +717,15 @@ struct ChainCtx {
 
   // langevin kernel, kernels.py:53-64
   __device__ void langevin(int i, Key key, const sgmcmc_step_coef& cf) {
+    SG_TA(t_l);
     expand_step_keys(key);
+    SG_TB(1, t_l);
     Key k2; k2.a = s.keys[2]; k2.b = s.keys[3];
     diffuse(1, i, cf, 4);
+    SG_TB(2, t_l);
     estimate(i, k2, false);
+    plan_cached = false;
+    SG_TB(13, t_l);
     if (m.diffusion == SGMCMC_DIFF_BAOAB || m.diffusion == SGMCMC_DIFF_BADODAB) diffuse(2, i, cf, 4);
   }
 
@@ -658,8 +749,8 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
   extern __shared__ __align__(16) float smem_raw[];
   const int W = blockDim.x >> 5;
   const int PP = ((m.P > m.DS ? m.P : m.DS) + 3) & ~3;
-  const Smem s = carve(smem_raw, PP, m.DS, W);
   const unsigned cs = cluster_size();
+  const Smem s = carve(smem_raw, PP, m.DS, W, (int)cs);
   const int c = blockIdx.x / cs;               // one chain per cluster (cs = 1: per CTA)
   const bool writer = cluster_rank() == 0;     // the replicas are identical; rank 0 writes samples and state back
   const int P = m.P;
@@ -717,15 +808,28 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
     }
   } else {
     if (run.step_keys == nullptr) { carry.a = st.key[2 * c]; carry.b = st.key[2 * c + 1]; }
+    bool have_next = false;
+    sgmcmc_step_coef cf_next = run.coef[0];
     for (int sidx = 0; sidx < run.K; ++sidx) {
+      SG_TA(t_s);
       const int i = run.i0 + sidx;
-      const sgmcmc_step_coef cf = run.coef[(size_t)sidx * run.coef_stride];
+      const sgmcmc_step_coef cf = cf_next;                       // loaded one iteration ahead (global-memory latency)
+      if (run.coef_stride && sidx + 1 < run.K) cf_next = run.coef[(size_t)(sidx + 1) * run.coef_stride];
       Key sub;
       if (run.step_keys) { sub.a = run.step_keys[2 * c]; sub.b = run.step_keys[2 * c + 1]; }
+      else if (have_next) {                                      // split one iteration ahead by expand_step_keys
+        const uint32_t* nx = s.keys + KEY_NEXT + 4 * (sidx & 1);
+        carry.a = nx[0]; carry.b = nx[1]; sub.a = nx[2]; sub.b = nx[3];
+      }
       else { Key nk; split2(carry, nk, sub); carry = nk; }      // samplers.py:49 / optimizer.py:46
+      have_next = false;
+      if (run.step_keys == nullptr && sidx + 1 < run.K && !(EXT && m.diffusion == SGMCMC_DIFF_ADAM_OPT)) {
+        ctx.look_slot = (sidx + 1) & 1; ctx.look_carry = carry; have_next = true;
+      }
+      SG_TB(0, t_s);
       if (EXT && m.diffusion == SGMCMC_DIFF_ADAM_OPT) {
         // optimizer.py:45-51: value and gradient on the minibatch drawn with `sub` itself, then the Adam step
-        ctx.partial_sums(sub, run.lp_out != nullptr);
+        ctx.partial_sums(sub, run.lp_out != nullptr, m.full_batch != 0);   // batch == N: all rows, scale 1 (optimizer.py:47)
         ctx.finish_from_sums();
         if (run.lp_out) {
           const float lp = ctx.log_post_value();
@@ -735,6 +839,7 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
         continue;
       }
       ctx.transition(i, sub, cf);
+      SG_TB(14, t_s);
       const bool thinned = run.thin > 1;
       if (thinned && (sidx + 1) % run.thin != 0) continue;
       if (run.samples && writer) {
@@ -746,6 +851,7 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
         float* mo = run.moments + (size_t)c * 3 * P;
         for (int e = threadIdx.x; e < P; e += blockDim.x) { const float x = s.theta[e] - mo[2 * P + e]; mo[e] += x; mo[P + e] = fmaf(x, x, mo[P + e]); }
       }
+      SG_TB(9, t_s);
     }
   }
 

@@ -48,6 +48,29 @@ def normal(key, shape=()):
     return out.reshape(tuple(shape))
 
 
+def uniform(key, shape=()):
+    """random.uniform(key, shape) on [0, 1) in fp32 -> CUDA torch tensor."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    n = int(np.prod(shape)) if len(shape) else 1
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    k, kp = _key_arg(key)
+    _native.check(lib.sgmcmc_uniform(kp, n, C.c_void_p(out.data_ptr()), _stream(torch)))
+    return out.reshape(tuple(shape))
+
+
+def bernoulli_rows(key, p):
+    """vmap(random.bernoulli)(random.split(key, N), p) -> CUDA int32 [N] (models/logistic_regression.py:59-61)."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    p = p.to(device="cuda", dtype=torch.float32).contiguous()
+    out = torch.empty(p.shape[0], dtype=torch.int32, device="cuda")
+    k, kp = _key_arg(key)
+    _native.check(lib.sgmcmc_bernoulli_rows(kp, int(p.shape[0]), C.c_void_p(p.data_ptr()), C.c_void_p(out.data_ptr()),
+                                            _stream(torch)))
+    return out
+
+
 def choice_indices(key, n: int, batch: int):
     """random.choice(key, arange(n), (batch,)) -> CUDA int32 tensor (gradient_estimation.py:32)."""
     torch = _native.require_cuda()

@@ -304,3 +304,18 @@ def test_big_family_errors(cuda):
     assert isinstance(out, list) and isinstance(out[0], tuple) and out[0][0].shape == (2,) + th0[0].shape
     with pytest.raises(TypeError):                                 # geometry is fixed once bound
         s(P.PRNGKey(0), 2, mlp_params([t[:5] if t.ndim == 1 else t[:5] for t in th0]))
+
+
+def test_pmf_rejects_out_of_range_ids(cuda):
+    """1-based (MovieLens-style) or negative ids would index past U / V in the gradient scatter: refused at ingestion."""
+    from sgmcmcjax_b200 import _native
+    from sgmcmcjax_b200 import samplers as NS
+
+    fam, fns, data, th0 = pmf_case()
+    ij, r = data
+    for bad in (ij + np.array([1, 0], np.int32), ij + np.array([0, 1], np.int32), ij - np.array([1, 0], np.int32)):
+        assert bad[:, 0].max() >= 30 or bad[:, 1].max() >= 40 or bad.min() < 0
+        s = NS.build_sgld_sampler(1e-5, fns[0], fns[1], (bad, r), 50, pbar=False)
+        with pytest.raises(_native.NativeError, match="id outside"):
+            s(P.PRNGKey(0), 2, pmf_params(th0))
+    NS.build_sgld_sampler(1e-5, fns[0], fns[1], (ij, r), 50, pbar=False)(P.PRNGKey(0), 2, pmf_params(th0))

@@ -708,3 +708,28 @@ def test_ksd_row_blocks_sum_to_whole_and_golden(cuda):
     assert abs(whole - parts) <= 1e-9 * abs(whole)
     assert abs(whole - float(OK.imq_ksd_sum(X, G))) <= 1e-5 * abs(whole)
     assert float(NKSD.imq_KSD_partial(X, G, 5, 5).cpu()[0]) == 0.0
+
+
+# ------------------------------------------------------------------------------ data generation
+def test_gen_data_matches_reference_key_tree(cuda):
+    """models.logistic_regression.gen_data == the restatement of logistic_regression.py:30-62 (genCovMat, Cholesky mixing,
+    per-row Bernoulli keys): identical PRNG draws, fp32 library rounding in the Cholesky / matmul only."""
+    from oracle import gen_data as OG
+    from sgmcmcjax_b200 import random as R
+    from sgmcmcjax_b200.models import logistic_regression as L
+
+    for seed, dim, n in [(42, 10, 5000), (7, 100, 2000), (0, 3, 1)]:
+        key = P.PRNGKey(seed)
+        th_r, X_r, y_r = OG.gen_data(key, dim, n)
+        th, X, y = L.gen_data(key, dim, n)
+        np.testing.assert_allclose(th.cpu().numpy(), th_r, rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(L.genCovMat(P.split(key, 4)[2], dim, 0.4), OG.gen_cov_mat(P.split(key, 4)[2], dim, 0.4), rtol=0, atol=0)
+        close(X.cpu().numpy(), X_r, rtol=1e-5, what="X = Z chol(Sigma)")
+        yy = y.cpu().numpy()
+        assert yy.dtype == np.int32 and (yy != y_r).mean() <= 2e-3          # flips only where |u - p| is at rounding level
+    # the uniform / per-row Bernoulli primitives are bit-exact
+    k = P.PRNGKey(5)
+    assert np.array_equal(R.uniform(k, (1001,)).cpu().numpy(), P.uniform(k, (1001,)))
+    p = P.uniform(P.PRNGKey(6), (3000,))
+    import torch
+    assert np.array_equal(R.bernoulli_rows(k, torch.from_numpy(p)).cpu().numpy(), OG.bernoulli_rows(k, p))

@@ -61,6 +61,25 @@ def test_adam_iterations_match_oracle(cuda, case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", ["gauss2", "logreg"])
+def test_adam_full_batch_uses_all_rows(cuda, case):
+    """batch_size == N: the estimator's static full-batch bypass (gradient_estimation.py:41-42) under the optimiser
+    (optimizer.py:41-60) - every row once, no index draw, scale 1."""
+    from sgmcmcjax_b200 import optimizer as NO
+    from test_gpu_parity import as_params, close, gauss_case, leaves_of, logreg_case
+
+    fam, fns, data, th0 = logreg_case(n=1500, d=20) if case == "logreg" else gauss_case(True, n=1000, d=7)
+    n = data[0].shape[0]
+    opt = NO.build_optax_optimizer(NO.adam(1e-2), fns[0], fns[1], data, n)
+    key = P.PRNGKey(9)
+    params, lps = opt(key, 8, as_params(th0))
+    ref, ref_lps = O.run_adam(fam, data, n, 1e-2, key, 8, th0)
+    for got, r in zip(leaves_of(params), ref):
+        close(got, r, rtol=2e-5, what=f"full-batch adam params {case}")
+    np.testing.assert_allclose(lps, ref_lps, rtol=2e-5)
+
+
+@pytest.mark.gpu
 def test_reference_optimizer_test(cuda):
     """tests/test_optimizers.py:23-36 verbatim: Adam, lr 1e-2, batch 10 % of N = 10k, 10k iterations."""
     from sgmcmcjax_b200 import optimizer as NO

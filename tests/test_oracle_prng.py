@@ -73,3 +73,28 @@ def test_erfinv_matches_true_erfinv_to_polynomial_accuracy():
     x = np.linspace(-0.999, 0.999, 2001).astype(np.float32)
     np.testing.assert_allclose(P.erf_inv_f32(x), erfinv(x.astype(np.float64)), rtol=1e-5, atol=1e-7)
     assert np.isinf(P.erf_inv_f32(np.float32(1.0))) and np.isinf(P.erf_inv_f32(np.float32(-1.0)))
+
+
+def test_gen_data_restatement_key_tree_and_structure():
+    """oracle/gen_data.py restates models/logistic_regression.py:12-62: one uniform decides the whole covariance
+    (the reference reuses the key), labels come from per-row keys split(key, N)."""
+    from oracle import gen_data as G
+
+    key = P.PRNGKey(42)
+    ks = P.split(key, 4)
+    theta, X, y = G.gen_data(key, 6, 400)
+    np.testing.assert_array_equal(theta, P.normal(ks[1], (6,)) * np.float32(np.sqrt(np.float32(10.0))))
+    cov = G.gen_cov_mat(ks[2], 6, 0.4)
+    u = P.uniform(ks[2], ())
+    base = np.float32(np.float32(np.float32(u * np.float32(2.0)) * np.float32(0.4)) - np.float32(0.4))
+    assert abs(base) < 0.4 and np.allclose(np.diag(cov), 1.0)
+    for k in range(1, 6):
+        np.testing.assert_allclose(np.diag(cov, k), float(base) ** k, rtol=1e-6)
+    assert np.array_equal(cov, cov.T)
+    np.testing.assert_allclose(X, P.normal(ks[3], (400, 6)) @ np.linalg.cholesky(cov.astype(np.float64)).astype(np.float32), rtol=1e-5, atol=1e-6)
+    # label i: uniform(split(key', N)[i], ()) < sigmoid(theta . x_i)
+    keys = P.split(ks[0], 400)
+    p = 1.0 / (1.0 + np.exp(-(X @ theta).astype(np.float64)))
+    for i in (0, 1, 57, 399):
+        assert y[i] == int(P.uniform(keys[i], ()) < p[i])
+    assert y.dtype == np.int32 and 0.2 < y.mean() < 0.8
