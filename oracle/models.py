@@ -144,6 +144,28 @@ class BayesianMLP:
         return grads
 
 
+def _mlp_log_post(self, leaves, batch, n_data, dtype=np.float64):
+    """logprior + Ndata * mean_i loglik_i (util.py:43-44); loglik = sum_k y_k log_softmax(z)_k (NN_model.py:48-50),
+    logprior = sum of N(0, 1) log-densities of every entry (NN_model.py:53-58)."""
+    x, y = batch
+    a = np.asarray(x, dtype=dtype)
+    y = np.asarray(y, dtype=dtype)
+    ws = [np.asarray(w, dtype=dtype) for w in leaves[0::2]]
+    bs = [np.asarray(b, dtype=dtype) for b in leaves[1::2]]
+    for w, b in zip(ws[:-1], bs[:-1]):
+        a = _softmax(a @ w.T + b)
+    z = a @ ws[-1].T + bs[-1]
+    zmax = z.max(axis=-1, keepdims=True)
+    logsm = z - zmax - np.log(np.exp(z - zmax).sum(axis=-1, keepdims=True))
+    lik = (y * logsm).sum(dtype=dtype)
+    n_par = sum(l.size for l in leaves)
+    pri = -0.5 * sum((np.asarray(l, dtype=dtype) ** 2).sum(dtype=dtype) for l in leaves) - 0.5 * np.log(2 * np.pi) * n_par
+    return dtype(pri + dtype(n_data) * lik / dtype(y.shape[0]))
+
+
+BayesianMLP.log_post = _mlp_log_post
+
+
 class PMF:
     """Probabilistic matrix factorisation (ours, not the reference's).
     leaves (U[n_users,d], V[n_items,d]); data (ij int32[N,2], r f32[N]);
@@ -169,3 +191,17 @@ class PMF:
         np.add.at(gv, jj, e[:, None] * ui)
         return [(scale * gu - dtype(self.lam) * u).astype(dtype),
                 (scale * gv - dtype(self.lam) * v).astype(dtype)]
+
+
+def _pmf_log_post(self, leaves, batch, n_data, dtype=np.float64):
+    """logprior + Ndata * mean_i loglik_i with loglik = -alpha/2 (r - U_i.V_j)^2, logprior = -lam/2 (|U|^2 + |V|^2)."""
+    ij, r = batch
+    u, v = (np.asarray(l, dtype=dtype) for l in leaves)
+    ii, jj = np.asarray(ij)[:, 0], np.asarray(ij)[:, 1]
+    res = np.asarray(r, dtype=dtype) - (u[ii] * v[jj]).sum(axis=1)
+    lik = (-0.5 * self.alpha * res * res).sum(dtype=dtype)
+    pri = -0.5 * self.lam * ((u * u).sum(dtype=dtype) + (v * v).sum(dtype=dtype))
+    return dtype(pri + dtype(n_data) * lik / dtype(len(ii)))
+
+
+PMF.log_post = _pmf_log_post

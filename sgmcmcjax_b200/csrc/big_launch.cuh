@@ -15,7 +15,7 @@ cudaError_t launch_big_inst(const BigModel& m, const BigRun& run, int blocks, si
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  kern<<<blocks, BigThreads<FAMILY>::value, smem, stream>>>(m, run);
+  kern<<<blocks, big_threads<FAMILY>(m), smem, stream>>>(m, run);
   return cudaGetLastError();
 }
 #endif

@@ -16,7 +16,11 @@
 //
 // Families
 //   PMF: theta = (U[nu, r], V[ni, r]); rating n = (i, j, y) packed as one int4;
-//       loglik = -alpha/2 (y - U_i.V_j)^2, prior N(0, 1/lam): sparse row gather + scatter-add.
+//       loglik = -alpha/2 (y - U_i.V_j)^2, prior N(0, 1/lam): sparse row gather.  A minibatch of B ratings touches at
+//       most 2 B of the nu + ni factor rows, so its raw gradient is kept COMPACT in shared memory (PmfCompact below:
+//       one slot of r floats per touched row, filled by the row's owner in a fixed order - no float atomics, no dense
+//       P-vector that is zeroed, scattered into and read back every step; the diffusion pass looks the slot up).
+//       Full passes over all N ratings (SVRG refresh, K2, the full-batch bypass) scatter-add into a dense buffer.
 //   MLP (models/bayesian_NN/NN_model.py:31-58): see mlp_grad.cuh.
 #pragma once
 #include "prng.cuh"
@@ -27,11 +31,13 @@ namespace sg {
 // PMF: CTA shape of one chain.  Measured on C4 (512 chains, SGNHT, ms per 4 steps): 1024 threads x 64 registers 1.37 (the
 // elementwise passes spill the values they load, so every load is waited for at once), 512 x 128 regs 1.15,
 // 2 CTAs x 256 threads x 128 regs with 4 threefry blocks staged per thread 1.08 (default), 4 CTAs x 128 threads 1.11.
+// With the compact minibatch gradient (<= 190 KB of shared memory for C4) one CTA of 512 threads x 128 registers per SM;
+// models that fall back to the dense buffer keep 2 CTAs x 256 threads (big_threads() picks at launch time).
 #ifndef SG_BIG_THREADS_PMF
-#define SG_BIG_THREADS_PMF 256
+#define SG_BIG_THREADS_PMF 512
 #endif
 #ifndef SG_BIG_MINBLOCKS_PMF
-#define SG_BIG_MINBLOCKS_PMF 2
+#define SG_BIG_MINBLOCKS_PMF 1
 #endif
 template <int FAMILY> struct BigThreads { static constexpr int value = SG_BIG_THREADS_PMF; static constexpr int min_blocks = SG_BIG_MINBLOCKS_PMF; };
 // MLP: warps 0..15 run the gradient (4 per TMEM lane quarter).  SG_MLP_PRODUCER_WARPS > 0 adds warps that generate
@@ -53,12 +59,20 @@ struct BigModel {
   float scale;              // fp32(n_data) / fp32(batch)
   float hyper[4];
   int dims[8];              // PMF: {n_users, n_items, rank};  MLP: {n_layers, size_0, ..., size_L}
-  float coef[4];            // PMF: {alpha, lam};  MLP: {-, prior precision (1)}
+  float coef[4];            // PMF: {alpha, lam, 0};  MLP: {-, prior precision (1), constant of logprior = -P/2 log(2 pi)}
   const void* data0;        // PMF: int4 [N] {i, j, bits(y), 0};  MLP: float [N][size_0]
   const void* data1;        // MLP: float [N][size_L] (one-hot / soft labels)
   const float* cv_center;   // [P]  (CV only)
   const float* cv_grad;     // [P]
+  int pmf_compact;          // PMF: the minibatch gradient lives compact in shared memory (PmfCompact)
+  unsigned pmf_magic;       // ceil(2^32 / rank): row of element e = umulhi(e, magic)   (e < 2^24)
 };
+
+// threads per CTA of big_sampler_kernel<FAMILY> for this model
+template <int FAMILY> inline int big_threads(const BigModel& m) {
+  if (FAMILY == SGMCMC_FAMILY_PMF) return m.pmf_compact ? 512 : 256;
+  return BigThreads<FAMILY>::value;
+}
 
 struct BigRun {
   sgmcmc_state st;
@@ -75,6 +89,7 @@ struct BigRun {
   const float* fg_thetas;    // [M, P] (mode 3)
   float* fg_out;             // [M, P]
   float* noise;              // [C, P] scratch for noise generated one update ahead (families with producer warps), or nullptr
+  float* lp_out;             // [C][K] log-posterior values of the optimiser iterations (SGMCMC_DIFF_ADAM_OPT), or nullptr
 };
 
 // Work for the noise-producer warps during a likelihood pass: normal(split(split(key)[0], n_leaves)[leaf], (n_leaf,))
@@ -85,6 +100,7 @@ struct BigSmem {
   uint32_t keys[2 * (4 + 2 * MAXL)];
   float alpha[MAXL];
   float red[32];
+  float lp;                  // sum of the minibatch log-likelihood VALUES of the current estimate (optimiser only)
 };
 
 template <int FAMILY> struct FamilyGrad;   // lik_pass(...) specialisations below / in mlp_grad.cuh
@@ -223,12 +239,54 @@ template <int FAMILY> struct BigUnroll { static constexpr int value = SG_BIG_UNR
 template <> struct BigUnroll<SGMCMC_FAMILY_MLP> { static constexpr int value = SG_BIG_UNROLL_MLP; };       // 512 threads: 128 registers
 
 // ---------------------------------------------------------------------------------------
+// PMF: compact minibatch gradient in shared memory.
+//   ri / rj / e / ec [B]   the minibatch in stream order n: user, item, alpha (y - U_i.V_j) at theta and at the CV centre
+//   head[nu + ni]          per factor row (U rows first): the last rating that joined its list, -1 = untouched
+//   nxt[2][B]              list links (side 0: by user, side 1: by item)
+//   slot[nu + ni]          compact slot of a touched row, -1 = untouched (the diffusion pass reads 0)
+//   gc[2 B][r]             raw gradient rows  sum_n e_n other_row(n) [- ec_n other_centre_row(n)], summed in stream order
+// Every touched row has exactly one owner - the rating at the head of its list - which walks the list in increasing n,
+// so the sum order is fixed: the result is deterministic (unlike float atomics) and costs no read-modify-write traffic.
+struct PmfCompact {
+  float *gc, *e, *ec;
+  int *head, *nslots;
+  short *slot, *nxt;
+  unsigned short *ri, *rj;
+};
+__host__ __device__ inline size_t pmf_compact_bytes(int nu, int ni, int r, unsigned batch) {
+  size_t b = (size_t)2 * batch * r * 4 + (size_t)2 * batch * 4;          // gc, e, ec
+  b += (size_t)(nu + ni) * 4 + 16;                                         // head, nslots
+  b += (size_t)(nu + ni) * 2 + (size_t)2 * batch * 2 + (size_t)2 * batch * 2 + 16;   // slot, nxt, ri, rj
+  return (b + 15) & ~(size_t)15;
+}
+__host__ __device__ inline bool pmf_compact_ok(int nu, int ni, int r, unsigned batch, int full_batch, size_t smem_limit) {
+  return !full_batch && batch <= 16383u && nu <= 65535 && ni <= 65535 && (r == 8 || r == 16 || r == 20 || r == 32) &&
+         pmf_compact_bytes(nu, ni, r, batch) + 1024 <= smem_limit;
+}
+__device__ __forceinline__ PmfCompact pmf_compact_view(void* fam_smem, int nu, int ni, int r, unsigned batch) {
+  PmfCompact c;
+  float* f = reinterpret_cast<float*>(fam_smem);
+  c.gc = f;                       f += (size_t)2 * batch * r;
+  c.e = f;                        f += batch;
+  c.ec = f;                       f += batch;
+  int* ip = reinterpret_cast<int*>(f);
+  c.head = ip;                    ip += nu + ni;
+  c.nslots = ip;                  ip += 4;
+  short* sp = reinterpret_cast<short*>(ip);
+  c.slot = sp;                    sp += (nu + ni + 1) & ~1;
+  c.nxt = sp;                     sp += 2 * batch;
+  c.ri = reinterpret_cast<unsigned short*>(sp);   sp += batch;
+  c.rj = reinterpret_cast<unsigned short*>(sp);
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------
 // PMF likelihood pass
 // One rating (i, j, y) at rank 4 R4: g[U_i] += e V_j, g[V_j] += e U_i with e = alpha (y - U_i.V_j); the factor rows sit in
 // registers, every load of the rating issues back to back, accumulation by float4 L2 atomics.  The control-variate
 // term (minus the same at the centre) is a second round so that the live registers stay at 2 R4 float4.
 template <int R4>
-__device__ __forceinline__ void pmf_rating_half(const float* th, float* g, int offV, int i, int j, float y, float alpha, float sign) {
+__device__ __forceinline__ float pmf_rating_half(const float* th, float* g, int offV, int i, int j, float y, float alpha, float sign) {
   const int r = 4 * R4;
   const float4* u = reinterpret_cast<const float4*>(th + (size_t)i * r);
   const float4* v = reinterpret_cast<const float4*>(th + offV + (size_t)j * r);
@@ -249,25 +307,165 @@ __device__ __forceinline__ void pmf_rating_half(const float* th, float* g, int o
     atomicAdd(gu + k, make_float4(e * vv[k].x, e * vv[k].y, e * vv[k].z, e * vv[k].w));
     atomicAdd(gv + k, make_float4(e * uu[k].x, e * uu[k].y, e * uu[k].z, e * uu[k].w));
   }
+  return y - dot;
 }
+// returns the residual y - U_i . V_j at theta (the log-likelihood value is -alpha/2 residual^2)
 template <int R4>
-__device__ __forceinline__ void pmf_rating(const float* theta, const float* center, float* g, int offV, int i, int j, float y,
-                                           float alpha) {
-  pmf_rating_half<R4>(theta, g, offV, i, j, y, alpha, 1.0f);
+__device__ __forceinline__ float pmf_rating(const float* theta, const float* center, float* g, int offV, int i, int j, float y,
+                                            float alpha) {
+  const float res = pmf_rating_half<R4>(theta, g, offV, i, j, y, alpha, 1.0f);
   if (center) pmf_rating_half<R4>(center, g, offV, i, j, y, alpha, -1.0f);
+  return res;
 }
 
 template <>
 struct FamilyGrad<SGMCMC_FAMILY_PMF> {
-  static constexpr size_t smem_bytes(const BigModel&) { return 0; }
+  static size_t smem_bytes(const BigModel& m) {
+    return m.pmf_compact ? pmf_compact_bytes(m.dims[0], m.dims[1], m.dims[2], m.batch) : 0;
+  }
   static constexpr bool kNoiseProducers = false;
-  __device__ static void cta_init(const BigModel&, void*) {}
+  __device__ static void cta_init(const BigModel& m, void* fam_smem) {
+    if (!m.pmf_compact) return;
+    const PmfCompact c = pmf_compact_view(fam_smem, m.dims[0], m.dims[1], m.dims[2], m.batch);
+    for (int t = threadIdx.x; t < m.dims[0] + m.dims[1]; t += blockDim.x) { c.head[t] = -1; c.slot[t] = -1; }
+    if (threadIdx.x == 0) *c.nslots = 0;
+    __syncthreads();
+  }
   __device__ static void cta_fini(const BigModel&, void*) {}
 
-  __device__ static void lik_pass(const BigModel& m, void* /*fam_smem*/, const float* theta, const float* center,
+  // alpha (y - U_i . V_j) for one rating; factor rows as R4 float4 each
+  template <int R4>
+  __device__ __forceinline__ static float resid(const float* th, int offV, int i, int j, float y, float alpha) {
+    const int r = 4 * R4;
+    const float4* u = reinterpret_cast<const float4*>(th + (size_t)i * r);
+    const float4* v = reinterpret_cast<const float4*>(th + offV + (size_t)j * r);
+    float4 uu[R4], vv[R4];
+#pragma unroll
+    for (int k = 0; k < R4; ++k) { uu[k] = u[k]; vv[k] = v[k]; }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < R4; ++k) {
+      dot = fmaf(uu[k].x, vv[k].x, dot); dot = fmaf(uu[k].y, vv[k].y, dot);
+      dot = fmaf(uu[k].z, vv[k].z, dot); dot = fmaf(uu[k].w, vv[k].w, dot);
+    }
+    return alpha * (y - dot);
+  }
+
+  // owner of a touched row: sum its list in increasing stream position into one compact slot
+  template <int R4>
+  __device__ __forceinline__ static void owner_row(const PmfCompact& c, const float* theta, const float* center, int offV,
+                                                   int side, int n, int row_slot, unsigned batch) {
+    const int r = 4 * R4;
+    const short* nxt = c.nxt + (size_t)side * batch;
+    float4 acc[R4];
+#pragma unroll
+    for (int k = 0; k < R4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int last = -1;
+    for (;;) {                                              // lists are short (B / rows ~ 1): selection in stream order
+      int best = 0x7fffffff;
+      for (int mm = n; mm >= 0; mm = nxt[mm]) best = (mm > last && mm < best) ? mm : best;
+      if (best == 0x7fffffff) break;
+      last = best;
+      // d/dU_i = e V_j, d/dV_j = e U_i: the OTHER side's row of rating `best`
+      const size_t off = side ? (size_t)c.ri[best] * r : (size_t)offV + (size_t)c.rj[best] * r;
+      const float4* o = reinterpret_cast<const float4*>(theta + off);
+      const float ev = c.e[best];
+#pragma unroll
+      for (int k = 0; k < R4; ++k) {
+        const float4 x = o[k];
+        acc[k].x = fmaf(ev, x.x, acc[k].x); acc[k].y = fmaf(ev, x.y, acc[k].y);
+        acc[k].z = fmaf(ev, x.z, acc[k].z); acc[k].w = fmaf(ev, x.w, acc[k].w);
+      }
+      if (center) {                                         // control variate: minus the same at the centre
+        const float4* oc = reinterpret_cast<const float4*>(center + off);
+        const float ecv = -c.ec[best];
+#pragma unroll
+        for (int k = 0; k < R4; ++k) {
+          const float4 x = oc[k];
+          acc[k].x = fmaf(ecv, x.x, acc[k].x); acc[k].y = fmaf(ecv, x.y, acc[k].y);
+          acc[k].z = fmaf(ecv, x.z, acc[k].z); acc[k].w = fmaf(ecv, x.w, acc[k].w);
+        }
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(c.gc + (size_t)row_slot * r);
+#pragma unroll
+    for (int k = 0; k < R4; ++k) dst[k] = acc[k];
+  }
+
+  // Minibatch estimate into the compact buffer.  Phase 0 forgets the previous minibatch's rows; phase A draws the
+  // ratings, takes the residuals and links every rating into the lists of its two rows; phase C: the head of each list
+  // owns the row, takes a slot and sums the list.
+  template <int R4>
+  __device__ static void compact_pass(const BigModel& m, const PmfCompact& c, const float* theta, const float* center,
+                                      const RandintPlan& plan, float* lp) {
+    const int r = 4 * R4, nu = m.dims[0], offV = m.leaf_off[1];
+    const unsigned B = m.batch, h = (B + 1u) >> 1;
+    const int4* __restrict__ rat = reinterpret_cast<const int4*>(m.data0);
+    const float alpha = m.coef[0];
+    SG_GLOBAL_PTR(theta); SG_GLOBAL_PTR(rat);
+    if (center) SG_GLOBAL_PTR(center);
+    (void)r;
+    if (*c.nslots > 0) {                                    // rows of the previous minibatch (still in ri / rj)
+      for (unsigned n = threadIdx.x; n < B; n += blockDim.x) {
+        const int ru = c.ri[n], rv = nu + c.rj[n];
+        c.head[ru] = -1; c.slot[ru] = -1; c.head[rv] = -1; c.slot[rv] = -1;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *c.nslots = 0;
+    float lpv = 0.f;
+    for (unsigned b = threadIdx.x; b < h; b += blockDim.x) {
+      unsigned i0, i1;
+      randint_block(plan, b, i0, i1);
+      const bool two = b + h < B;
+      const int4 q0 = __ldg(rat + i0);
+      const int4 q1 = __ldg(rat + (two ? i1 : i0));
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (t == 1 && !two) break;
+        const int4 q = t ? q1 : q0;
+        const unsigned n = t ? b + h : b;
+        const float y = __int_as_float(q.z);
+        const float ev = resid<R4>(theta, offV, q.x, q.y, y, alpha);
+        c.e[n] = ev;
+        if (center) c.ec[n] = resid<R4>(center, offV, q.x, q.y, y, alpha);
+        c.ri[n] = (unsigned short)q.x; c.rj[n] = (unsigned short)q.y;
+        c.nxt[n] = (short)atomicExch(c.head + q.x, (int)n);
+        c.nxt[B + n] = (short)atomicExch(c.head + nu + q.y, (int)n);
+        lpv = fmaf(-0.5f * ev, ev / alpha, lpv);            // -alpha/2 (y - U_i.V_j)^2
+      }
+    }
+    if (lp) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) lpv += __shfl_xor_sync(FULL, lpv, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(lp, lpv);
+    }
+    __syncthreads();
+    for (unsigned cnd = threadIdx.x; cnd < 2u * B; cnd += blockDim.x) {
+      const int side = cnd >= B, n = (int)(side ? cnd - B : cnd);
+      const int row = side ? nu + c.rj[n] : c.ri[n];
+      if (c.head[row] != n) continue;
+      const int sl = atomicAdd(c.nslots, 1);
+      c.slot[row] = (short)sl;
+      owner_row<R4>(c, theta, center, offV, side, n, sl, B);
+    }
+  }
+
+  __device__ static void lik_pass(const BigModel& m, void* fam_smem, const float* theta, const float* center,
                                   bool sequential, const RandintPlan& plan, unsigned seq_base, unsigned count, float* g,
-                                  bool /*fresh*/, const NoiseJob& /*job*/) {
+                                  bool /*fresh*/, const NoiseJob& /*job*/, float* lp = nullptr, bool compact = false) {
     const int r = m.dims[2];
+    if (compact) {                                   // minibatch of a model with the compact gradient (BigCtx::estimate)
+      const PmfCompact c = pmf_compact_view(fam_smem, m.dims[0], m.dims[1], r, m.batch);
+      switch (r >> 2) {
+        case 2: compact_pass<2>(m, c, theta, center, plan, lp); break;
+        case 4: compact_pass<4>(m, c, theta, center, plan, lp); break;
+        case 5: compact_pass<5>(m, c, theta, center, plan, lp); break;
+        default: compact_pass<8>(m, c, theta, center, plan, lp); break;
+      }
+      return;
+    }
+    float lpv = 0.f;                                 // sum of -alpha/2 (y - U_i.V_j)^2 over this thread's ratings (if lp)
     const int offV = m.leaf_off[1];
     const int4* __restrict__ rat = reinterpret_cast<const int4*>(m.data0);
     SG_GLOBAL_PTR(theta); SG_GLOBAL_PTR(g); SG_GLOBAL_PTR(rat);
@@ -289,12 +487,14 @@ struct FamilyGrad<SGMCMC_FAMILY_PMF> {
         for (int t = 0; t < cnt; ++t) {
           const int4 q = t ? q1 : q0;
           const float y = __int_as_float(q.z);
+          float res;
           switch (r4) {
-            case 2: pmf_rating<2>(theta, center, g, offV, q.x, q.y, y, alpha); break;
-            case 4: pmf_rating<4>(theta, center, g, offV, q.x, q.y, y, alpha); break;
-            case 5: pmf_rating<5>(theta, center, g, offV, q.x, q.y, y, alpha); break;
-            default: pmf_rating<8>(theta, center, g, offV, q.x, q.y, y, alpha); break;
+            case 2: res = pmf_rating<2>(theta, center, g, offV, q.x, q.y, y, alpha); break;
+            case 4: res = pmf_rating<4>(theta, center, g, offV, q.x, q.y, y, alpha); break;
+            case 5: res = pmf_rating<5>(theta, center, g, offV, q.x, q.y, y, alpha); break;
+            default: res = pmf_rating<8>(theta, center, g, offV, q.x, q.y, y, alpha); break;
           }
+          lpv = fmaf(-0.5f * alpha * res, res, lpv);
         }
         continue;
       }
@@ -306,6 +506,7 @@ struct FamilyGrad<SGMCMC_FAMILY_PMF> {
         float dot = 0.f;
         for (int k = 0; k < r; ++k) dot = fmaf(u[k], v[k], dot);
         const float e = alpha * (y - dot);
+        lpv = fmaf(-0.5f * e, y - dot, lpv);
         float ec = 0.f;
         const float *uc = nullptr, *vc = nullptr;
         if (center) {
@@ -323,6 +524,11 @@ struct FamilyGrad<SGMCMC_FAMILY_PMF> {
           atomicAdd(gv + k, dv);
         }
       }
+    }
+    if (lp) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) lpv += __shfl_xor_sync(FULL, lpv, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(lp, lpv);
     }
   }
 };
@@ -342,11 +548,23 @@ struct BigCtx {
   // [+ fb + prior * centre] on the fly and zeroes the buffer for the next accumulation (no separate finalise
   // and zero passes over the P-vector).  At launch boundaries the buffer holds the finalised param_grad.
   bool grad_raw = false;
+  bool raw_compact = false;   // PMF: the raw sums are the compact shared-memory rows (PmfCompact), not the gradient buffer
+  PmfCompact pc{};
   float gscale = 1.0f;
+  float* lp_acc = nullptr;    // shared-memory accumulator of the minibatch log-likelihood values (optimiser), or nullptr
   float* noise = nullptr;     // this chain's row of the look-ahead noise buffer (nullptr: generate in place)
   bool noise_ready = false;   // noise[] holds the draws of the NEXT langevin step
 
-  __device__ BigCtx(const BigModel& mm, BigSmem& ss, void* fs) : m(mm), s(ss), fam_smem(fs) {}
+  __device__ BigCtx(const BigModel& mm, BigSmem& ss, void* fs) : m(mm), s(ss), fam_smem(fs) {
+    if (FAMILY == SGMCMC_FAMILY_PMF && mm.pmf_compact) pc = pmf_compact_view(fs, mm.dims[0], mm.dims[1], mm.dims[2], mm.batch);
+  }
+
+  // raw likelihood sum of global element ge from the compact rows: 0 for a row the minibatch did not touch
+  __device__ __forceinline__ float compact_raw(unsigned ge) const {
+    const unsigned row = __umulhi(ge, m.pmf_magic);
+    const int sl = pc.slot[row];
+    return sl >= 0 ? pc.gc[(unsigned)sl * (unsigned)m.dims[2] + (ge - row * (unsigned)m.dims[2])] : 0.f;
+  }
 
   __device__ __forceinline__ bool is_cv() const { return m.estimator != SGMCMC_EST_STANDARD; }
 
@@ -360,16 +578,17 @@ struct BigCtx {
 
   // Gradient consumption in the diffusion passes, specialised at compile time so that the loaders are straight-line
   // batches of independent loads (a branch between two loads serialises them on their memory latency):
-  //   MODE 0: the buffer holds the finalised gradient; 1: raw sum, standard estimator; 2: raw sum, CV / SVRG.
+  //   MODE 0: the buffer holds the finalised gradient; 1: raw sum, standard estimator; 2: raw sum, CV / SVRG;
+  //   3 / 4: as 1 / 2 with the raw sum in the compact shared-memory rows (PMF).
   template <int MODE>
   __device__ __forceinline__ void ld_grad(Elt& t, const float* gbuf, unsigned e, unsigned ge) const {
-    t.g = __ldcg(gbuf + e);
-    if (MODE == 2) { t.fb = fb[ge]; t.cen = center[ge]; }
+    if (MODE >= 3) t.g = compact_raw(ge); else t.g = __ldcg(gbuf + e);
+    if (MODE == 2 || MODE == 4) { t.fb = fb[ge]; t.cen = center[ge]; }
   }
   template <int MODE>
   __device__ static __forceinline__ float gval(const Elt& t, float gs, float prior) {
     if (MODE == 0) return t.g;
-    if (MODE == 2) return t.fb + (gs * t.g - prior * (t.x - t.cen));            // gradient_estimation.py:72, no cancellation
+    if (MODE == 2 || MODE == 4) return t.fb + (gs * t.g - prior * (t.x - t.cen));   // gradient_estimation.py:72, no cancellation
     return gs * t.g - prior * t.x;
   }
 
@@ -397,10 +616,14 @@ struct BigCtx {
   __device__ void finalize() {
     if (!grad_raw) return;
     SG_CTX_SPACES();
-    plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v{}; v.g = __ldcg(grad + e); v.x = theta[e]; return v; },
-                  [&](unsigned e, const Elt& v) { grad[e] = gfin(v.g, v.x, e); });
+    if (FAMILY == SGMCMC_FAMILY_PMF && raw_compact)
+      plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v{}; v.g = compact_raw(e); v.x = theta[e]; return v; },
+                    [&](unsigned e, const Elt& v) { grad[e] = gfin(v.g, v.x, e); });
+    else
+      plain_pass<U>((unsigned)m.P, [&](unsigned e) { Elt v{}; v.g = __ldcg(grad + e); v.x = theta[e]; return v; },
+                    [&](unsigned e, const Elt& v) { grad[e] = gfin(v.g, v.x, e); });
     __syncthreads();
-    grad_raw = false;
+    grad_raw = false; raw_compact = false;
   }
 
   // estimate_gradient: on entry the gradient buffer is all zero unless is_init
@@ -425,16 +648,19 @@ struct BigCtx {
         __syncthreads();
       }
     }
-    if (is_init) zero(grad);
+    // PMF minibatch estimates of a compact model never touch the dense buffer (it need not be zero either)
+    const bool cmp = FAMILY == SGMCMC_FAMILY_PMF && m.pmf_compact;
+    if (is_init && !cmp) zero(grad);
     RandintPlan plan{};
     if (m.estimator == SGMCMC_EST_STANDARD && m.full_batch && !is_init) {
       // static full-batch bypass, gradient_estimation.py:41-42 (init_gradient still subsamples, :31-35)
-      FamilyGrad<FAMILY>::lik_pass(m, fam_smem, theta, nullptr, true, plan, 0u, m.n_data, grad, true, job);
+      FamilyGrad<FAMILY>::lik_pass(m, fam_smem, theta, nullptr, true, plan, 0u, m.n_data, grad, true, job, lp_acc);
       gscale = 1.0f;
     } else {
       plan = randint_plan(k2, m.n_data, m.batch);
-      FamilyGrad<FAMILY>::lik_pass(m, fam_smem, theta, cv ? center : nullptr, false, plan, 0u, m.batch, grad, true, job);
+      FamilyGrad<FAMILY>::lik_pass(m, fam_smem, theta, cv ? center : nullptr, false, plan, 0u, m.batch, grad, true, job, lp_acc, cmp);
       gscale = m.scale;
+      raw_compact = cmp;
     }
     __syncthreads();
     grad_raw = true;
@@ -464,6 +690,10 @@ struct BigCtx {
   __device__ void diffuse(int phase, int i, const sgmcmc_step_coef& cf, int key_slot, float* sample) {
     SG_T0();
     if (!grad_raw) diffuse_mode<0>(phase, i, cf, key_slot, sample);
+    else if (FAMILY == SGMCMC_FAMILY_PMF && raw_compact) {
+      if (!is_cv()) diffuse_mode<(FAMILY == SGMCMC_FAMILY_PMF ? 3 : 1)>(phase, i, cf, key_slot, sample);
+      else diffuse_mode<(FAMILY == SGMCMC_FAMILY_PMF ? 4 : 2)>(phase, i, cf, key_slot, sample);
+    }
     else if (!is_cv()) diffuse_mode<1>(phase, i, cf, key_slot, sample);
     else diffuse_mode<2>(phase, i, cf, key_slot, sample);
     SG_T1(0);
@@ -477,6 +707,8 @@ struct BigCtx {
     const float gs = gscale, prior = m.coef[1];
     const sgmcmc_step_coef cfv = cf;
     const bool use_noise = noise_ready && phase == 1 && !bug;   // draws of this step were generated during the last estimate
+    // the consumed buffer is zeroed for the next accumulation - unless minibatch estimates never accumulate into it
+    const bool zg = !(FAMILY == SGMCMC_FAMILY_PMF && m.pmf_compact);
     if (phase == 2 || bug) {                      // baoab / badodab update2: v += dt/2 * g
       const bool consume = phase == 1;
       plain_pass<U>((unsigned)m.P,
@@ -484,11 +716,11 @@ struct BigCtx {
                     [&](unsigned e, const Elt& t) {
                       const float gg = gval<MODE>(t, gs, prior);
                       aux1[e] = fmaf(cfv.hh, gg, t.a);
-                      if (consume) { grad[e] = 0.f; if (sample) __stcs(sample + e, t.x); }
+                      if (consume) { if (zg) grad[e] = 0.f; if (sample) __stcs(sample + e, t.x); }
                       else grad[e] = gg;           // keep the finalised value: the next update reads it as is
                     });
       __syncthreads();
-      grad_raw = false;
+      grad_raw = false; raw_compact = false;
       return;
     }
     for (int leaf = 0; leaf < m.n_leaves; ++leaf) {
@@ -511,7 +743,7 @@ struct BigCtx {
       auto ld_xg = [&](unsigned e) { Elt t{}; t.x = x[e]; ld_grad<MODE>(t, g, e, off + e); return t; };
       auto ld_xvg = [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; ld_grad<MODE>(t, g, e, off + e); return t; };
       auto ld_xvvg = [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; t.b = v2[e]; ld_grad<MODE>(t, g, e, off + e); return t; };
-      auto emit = [&](unsigned e, float xn) { x[e] = xn; g[e] = 0.f; if (smp) __stcs(smp + e, xn); };
+      auto emit = [&](unsigned e, float xn) { x[e] = xn; if (zg) g[e] = 0.f; if (smp) __stcs(smp + e, xn); };
       const float* xi_buf = noise + off;
       // st(e, t, xi) for every element with its N(0,1) draw: from the look-ahead buffer, or generated in place
       auto noisy = [&](Key key, auto ld, auto st) {
@@ -585,7 +817,7 @@ struct BigCtx {
           float ss = 0.f;
           plain_pass<U>(n, ld_xvg, [&](unsigned e, const Elt& t) {
             const float ve = fmaf(cfv.hh, gval<MODE>(t, gs, prior), t.a);
-            v[e] = ve; x[e] = fmaf(cfv.hh, ve, t.x); g[e] = 0.f;
+            v[e] = ve; x[e] = fmaf(cfv.hh, ve, t.x); if (zg) g[e] = 0.f;
             ss = fmaf(ve, ve, ss);
           });
           alpha = alpha + cfv.hh * (sqrtf(big_block_sum(ss, s.red)) - (float)n);
@@ -609,8 +841,40 @@ struct BigCtx {
       }
     }
     __syncthreads();
-    grad_raw = false;                             // consumed: the buffer is all zero now
+    grad_raw = false; raw_compact = false;        // consumed: the buffer is all zero now (or never used: compact)
     noise_ready = false;
+  }
+
+  // One iteration of optimizer.py:45-51 after estimate(): optax.adam ASCENT step on the raw minibatch sums in the
+  // gradient buffer (cf.ca = 1 - b1^t, cf.cb = 1 - b2^t, cf.h = learning rate; oracle/optimizer.py), the buffer zeroed for
+  // the next estimate.  Returns the log-posterior VALUE at the parameters the gradient was taken at (util.py:43-44):
+  // logprior(theta) + Ndata * mean_i loglik_i, the likelihood values summed by the family's pass into s.lp.
+  __device__ float adam_step(const sgmcmc_step_coef& cf) {
+    SG_CTX_SPACES();
+    const float gs = gscale, prior = m.coef[1];
+    const float b1 = m.hyper[0], b2 = m.hyper[1], eps = m.hyper[2];
+    const sgmcmc_step_coef cfv = cf;
+    float sx2 = 0.f;
+    const bool cmp = FAMILY == SGMCMC_FAMILY_PMF && raw_compact;
+    plain_pass<U>((unsigned)m.P,
+                  [&](unsigned e) {
+                    Elt t{}; t.x = theta[e]; t.a = aux1[e]; t.b = aux2[e];
+                    t.g = cmp ? compact_raw(e) : __ldcg(grad + e);
+                    return t;
+                  },
+                  [&](unsigned e, const Elt& t) {
+                    const float gg = gs * t.g - prior * t.x;
+                    const float mm = b1 * t.a + (1.0f - b1) * gg;
+                    const float vv = b2 * t.b + (1.0f - b2) * (gg * gg);
+                    aux1[e] = mm; aux2[e] = vv; grad[e] = 0.f;
+                    theta[e] = t.x + cfv.h * (mm / cfv.ca) / (sqrtf(vv / cfv.cb) + eps);
+                    sx2 = fmaf(t.x, t.x, sx2);
+                  });
+    const float tot = big_block_sum(sx2, s.red);
+    const float lp = m.coef[2] - 0.5f * prior * tot + gs * s.lp;
+    __syncthreads();
+    grad_raw = false; raw_compact = false;
+    return lp;
   }
 
   // `next_key` / `has_next`: the key of the NEXT langevin step of this chain, if it is already known (look-ahead noise)
@@ -704,6 +968,17 @@ __global__ void __launch_bounds__(BigThreads<FAMILY>::value, BigThreads<FAMILY>:
       const sgmcmc_step_coef cf = run.coef[(size_t)sidx * run.coef_stride];
       Key sub, next_sub{0u, 0u};
       bool has_next = false;
+      if (m.diffusion == SGMCMC_DIFF_ADAM_OPT) {
+        // optimizer.py:45-51: key, subkey = split(key); value and gradient on the minibatch drawn with subkey itself
+        Key nk; split2(carry, nk, sub); carry = nk;
+        if (threadIdx.x == 0) s.lp = 0.f;
+        __syncthreads();
+        ctx.lp_acc = &s.lp;
+        ctx.estimate(i, sub, false);
+        const float lp = ctx.adam_step(cf);
+        if (run.lp_out && threadIdx.x == 0) run.lp_out[(size_t)c * run.K + sidx] = lp;
+        continue;
+      }
       if (run.step_keys) { sub.a = run.step_keys[2 * c]; sub.b = run.step_keys[2 * c + 1]; }
       else {
         Key nk; split2(carry, nk, sub); carry = nk;             // samplers.py:49

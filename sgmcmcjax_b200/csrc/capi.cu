@@ -418,9 +418,8 @@ int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
     return fail(SGMCMC_E_UNSUPPORTED, "unknown model family");
   if (cfg->estimator < 0 || cfg->estimator > SGMCMC_EST_SVRG) return fail(SGMCMC_E_INVALID, "bad estimator");
   if (cfg->diffusion < 0 || cfg->diffusion > SGMCMC_DIFF_ADAM_OPT) return fail(SGMCMC_E_INVALID, "bad diffusion");
-  if (cfg->diffusion == SGMCMC_DIFF_ADAM_OPT && (cfg->estimator != SGMCMC_EST_STANDARD || (int64_t)cfg->batch > cfg->n_data ||
-                                                 cfg->family == SGMCMC_FAMILY_PMF || cfg->family == SGMCMC_FAMILY_MLP))
-    return fail(SGMCMC_E_UNSUPPORTED, "the optimiser covers the vector families with the standard minibatch estimator");
+  if (cfg->diffusion == SGMCMC_DIFF_ADAM_OPT && (cfg->estimator != SGMCMC_EST_STANDARD || (int64_t)cfg->batch > cfg->n_data))
+    return fail(SGMCMC_E_UNSUPPORTED, "the optimiser runs on the standard minibatch estimator");
   if (cfg->n_data <= 0 || cfg->n_data > 0x7fffffffLL) return fail(SGMCMC_E_INVALID, "n_data out of range");
   if (cfg->batch <= 0) return fail(SGMCMC_E_INVALID, "batch must be positive");
   if (cfg->n_leaves < 1 || cfg->n_leaves > SGMCMC_MAX_LEAVES) return fail(SGMCMC_E_INVALID, "n_leaves out of range");
@@ -465,6 +464,15 @@ int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
     for (int k = 0; k < 8; ++k) bm.dims[k] = cfg->dims[k];
     bm.coef[0] = cfg->lik_coef[0];
     bm.coef[1] = cfg->prior_coef[0];
+    // constant of the log-prior VALUE (optimiser only): N(0, 1) log-densities carry -1/2 log(2 pi) per entry (NN_model.py:53-58)
+    bm.coef[2] = cfg->family == SGMCMC_FAMILY_MLP ? (float)(-0.5 * 1.8378770664093453 * (double)P) : 0.0f;
+    if (cfg->family == SGMCMC_FAMILY_PMF) {
+      // compact minibatch gradient in shared memory (csrc/big_sampler.cuh PmfCompact) when it fits beside the 227 KB limit
+      const size_t limit = (size_t)227 * 1024 - ((sizeof(sg::BigSmem) + 127) & ~(size_t)127);
+      bm.pmf_compact = !env_int("SGMCMC_PMF_DENSE", 0) &&
+                       sg::pmf_compact_ok(cfg->dims[0], cfg->dims[1], cfg->dims[2], bm.batch, bm.full_batch, limit) ? 1 : 0;
+      bm.pmf_magic = (unsigned)((0x100000000ULL + (unsigned)cfg->dims[2] - 1) / (unsigned)cfg->dims[2]);
+    }
     *out = h;
     return SGMCMC_OK;
   }
@@ -694,6 +702,11 @@ int sgmcmc_optimize(sgmcmc_handle* h, sgmcmc_state* st, int32_t i0, int32_t k, c
   if (h->cfg.diffusion != SGMCMC_DIFF_ADAM_OPT) return fail(SGMCMC_E_STATE, "the handle was not created with SGMCMC_DIFF_ADAM_OPT");
   if (k < 0 || i0 < 0 || !coef || !st->key) return fail(SGMCMC_E_INVALID, "bad argument");
   if (k == 0) return SGMCMC_OK;
+  if (h->big) {
+    sg::BigRun run{};
+    run.st = *st; run.i0 = i0; run.K = k; run.coef = coef; run.coef_stride = 1; run.lp_out = lp_out; run.thin = 1;
+    return dispatch_big(h, run, st->n_chains, (cudaStream_t)stream);
+  }
   sg::VecRun run{};
   run.st = *st; run.i0 = i0; run.K = k; run.coef = coef; run.coef_stride = 1; run.lp_out = lp_out;
   return dispatch_vec(h, run, (cudaStream_t)stream);

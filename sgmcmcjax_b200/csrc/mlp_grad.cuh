@@ -484,7 +484,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
   // ---------------------------------------------------------------------------------------------------
   // one sub-batch of nb <= plan.rows rows whose table indices are in ms.idx[0..nb)
   __device__ __noinline__ static void sub_batch(const BigModel& m, MlpSmem& ms, uint8_t* base, const float* th, float sign,
-                                                int nb, float* g, bool overwrite) {
+                                                int nb, float* g, bool overwrite, float* lp = nullptr) {
     const int L = m.dims[0];
     const int* sz = m.dims + 1;                       // sz[0..L]
     const float* Y = reinterpret_cast<const float*>(m.data1);
@@ -548,6 +548,12 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           for (int c = 0; c < w; ++c) sum += expf(Z[tid * zs + c] - mx);
           const float inv = ys / sum;
           for (int c = 0; c < w; ++c) dz[tid * dzs + c] = __ldg(yr + c) - inv * expf(Z[tid * zs + c] - mx);
+          if (lp) {                                    // loglik = sum_c y_c log_softmax(z)_c  (NN_model.py:48-50)
+            const float lse = mx + logf(sum);
+            float v = 0.f;
+            for (int c = 0; c < w; ++c) v = fmaf(__ldg(yr + c), Z[tid * zs + c] - lse, v);
+            atomicAdd(lp, v);
+          }
         } else {
           for (int c = 0; c < w; ++c) dz[tid * dzs + c] = 0.f;      // padded rows contribute nothing
         }
@@ -669,7 +675,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
 
   __device__ static void lik_pass(const BigModel& m, void* fam_smem, const float* theta, const float* center,
                                   bool sequential, const RandintPlan& plan, unsigned seq_base, unsigned count, float* g,
-                                  bool fresh, const NoiseJob& job) {
+                                  bool fresh, const NoiseJob& job, float* lp = nullptr, bool /*compact*/ = false) {
     if (threadIdx.x >= MLP_THREADS) {
       // noise-producer warps: the Gaussian draws of the NEXT diffusion update (its key tree is data independent,
       // diffusion_util.py:66), generated while the worker warps run the GEMM phase; the caller's __syncthreads() after
@@ -704,7 +710,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       }
       mlptc::worker_sync();
       // the first sub-batch into an all-zero buffer stores dW1 instead of read-modify-writing it
-      sub_batch(m, ms, base, theta, 1.0f, nb, g, fresh && base_row == 0);
+      sub_batch(m, ms, base, theta, 1.0f, nb, g, fresh && base_row == 0, lp);
       if (center) sub_batch(m, ms, base, center, -1.0f, nb, g, false);
     }
   }

@@ -4,8 +4,10 @@ The reference takes any ``optax.GradientTransformation``; optax is not part of t
 an arbitrary Python transformation, so the optimiser is the one the reference's docs and tests use, Adam
 (``optax.adam(learning_rate)``; tests/test_optimizers.py:27-31), described by the small ``adam(...)`` object below.
 The loop (``key, subkey = split(key)``; value and gradient of the log-posterior on the minibatch drawn with ``subkey``;
-Adam ascent step) runs as ONE kernel launch, one CTA per chain, the Adam moments in shared memory.  Its main use here is
-the centring value of the control-variate samplers.  Vector families only.
+Adam ascent step) runs as ONE kernel launch, one CTA per chain: the vector families keep the Adam moments in shared memory
+(csrc/vec_sampler.cuh), the Bayesian MLP and PMF stream them with the parameters (csrc/big_sampler.cuh ``adam_step``).
+Its main use here is the centring value of the control-variate samplers: the ``*CV`` samplers of
+the big families need a MAP estimate as much as logistic regression does.
 """
 from __future__ import annotations
 

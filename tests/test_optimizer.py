@@ -95,3 +95,46 @@ def test_reference_optimizer_test(cuda):
     p3, lp3 = optimizer(keys, 50, np.zeros((3, 100), np.float32))
     p1, lp1 = optimizer(keys[1], 50, np.zeros(100, np.float32))
     assert np.array_equal(p3[1], p1) and np.array_equal(lp3[1], lp1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["mlp", "pmf"])
+def test_adam_iterations_match_oracle_big_families(cuda, case):
+    """optimizer.py:41-60 on the Bayesian MLP and PMF (csrc/big_sampler.cuh adam_step): parameters and the log-posterior
+    VALUES (util.py:43-44 with_val) against oracle/optimizer.py; pytree in, same pytree out."""
+    from sgmcmcjax_b200 import optimizer as NO
+    from test_gpu_big_families import CASES, close, flat, tree_leaves
+
+    make, to_params, batch = CASES[case]
+    fam, fns, data, th0 = make()
+    opt = NO.build_optax_optimizer(NO.adam(1e-2), fns[0], fns[1], data, batch)
+    key = P.PRNGKey(4)
+    params, lps = opt(key, 10, to_params(th0))
+    ref, ref_lps = O.run_adam(fam, data, batch, 1e-2, key, 10, th0)
+    assert type(params) is type(to_params(th0))
+    close(flat(tree_leaves(params)), flat(ref), rtol=3e-5, what=f"adam params {case}")
+    np.testing.assert_allclose(np.asarray(lps), ref_lps, rtol=3e-5)
+    # two chains at once == two single runs
+    keys = P.split(P.PRNGKey(5), 2)
+    multi = to_params([np.stack([t, t * np.float32(1.05)]) for t in th0])
+    p2, lp2 = opt(keys, 6, multi)
+    p1, lp1 = opt(keys[1], 6, to_params([t * np.float32(1.05) for t in th0]))
+    close(flat([l[1] for l in tree_leaves(p2)]), flat(tree_leaves(p1)), rtol=1e-5, what="chain 1 of 2")
+    np.testing.assert_allclose(np.asarray(lp2)[1], np.asarray(lp1), rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_map_centre_for_pmf_control_variates(cuda):
+    """The use the optimiser exists for: a MAP estimate as the centring value of a *CV sampler.
+    After 300 Adam iterations the log-posterior has risen and BADODAB-CV centred there runs finite."""
+    from sgmcmcjax_b200 import optimizer as NO
+    from sgmcmcjax_b200 import samplers as NS
+    from test_gpu_big_families import pmf_case, pmf_params, tree_leaves
+
+    fam, fns, data, th0 = pmf_case(60, 80, 8, 4000, seed=3)
+    theta_map, lps = NO.build_optax_optimizer(NO.adam(5e-2), fns[0], fns[1], data, 400)(P.PRNGKey(0), 300, pmf_params(th0))
+    lps = np.asarray(lps)
+    assert lps[-20:].mean() > lps[:20].mean()
+    sampler = NS.build_badodabCV_sampler(1e-3, fns[0], fns[1], data, 400, theta_map, pbar=False)
+    out = sampler(P.PRNGKey(1), 20, theta_map)
+    assert all(np.isfinite(l).all() for l in tree_leaves(out))
