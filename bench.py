@@ -319,7 +319,11 @@ def extra_workloads(args, torch, lib, hbm_peak, X, y, theta_true):
     from sgmcmcjax_b200 import optimizer as NO
     (Um, Vm), lps = NO.build_optax_optimizer(NO.adam(2e-2), F.loglikelihood, F.logprior, (ij, rt), 1000)(random.PRNGKey(6), 300, (U, V))
     lps = lps.float().cpu().numpy() if hasattr(lps, "cpu") else np.asarray(lps)
-    s = samplers.build_badodabCV_sampler(1e-3, F.loglikelihood, F.logprior, (ij, rt), 1000, (Um, Vm), pbar=False)
+    # dt = 1e-4 here (SURVEY 8d quotes 1e-3 from the reference's 5-dimensional test): the reference's thermostat update
+    # alpha += dt/2 (|v| - v.size) (diffusions.py:326,334) drifts by -dt/2 * 18860 per step on a leaf of 18,860 entries; at
+    # dt = 1e-3 the friction turns into exp(+0.9) growth per step within ~100 steps and the chain overflows - a property
+    # of that update rule on large leaves, reproduced faithfully.  The cost per step does not depend on dt.
+    s = samplers.build_badodabCV_sampler(1e-4, F.loglikelihood, F.logprior, (ij, rt), 1000, (Um, Vm), pbar=False)
     thm_ = torch.cat([Um.reshape(-1), Vm.reshape(-1)])[None].repeat(Cp, 1).contiguous()
     ms, nl = _time_engine(torch, s.engine, lib, keys_p, thm_, 16, 3, 3)
     report("C4 PMF 943x1682 rank 20 BADODAB-CV batch=1000", ms, Cp, 16, 1, pmf_bytes + 8 * Pp, nl,

@@ -16,11 +16,14 @@
 //
 // Families
 //   PMF: theta = (U[nu, r], V[ni, r]); rating n = (i, j, y) packed as one int4;
-//       loglik = -alpha/2 (y - U_i.V_j)^2, prior N(0, 1/lam): sparse row gather.  A minibatch of B ratings touches at
-//       most 2 B of the nu + ni factor rows, so its raw gradient is kept COMPACT in shared memory (PmfCompact below:
+//       loglik = -alpha/2 (y - U_i.V_j)^2, prior N(0, 1/lam): sparse row gather + scatter-add (float4 L2 atomics) into
+//       the dense gradient buffer.  Opt-in alternative (SGMCMC_PMF_COMPACT=1): a minibatch of B ratings touches at most
+//       2 B of the nu + ni factor rows, so its raw gradient can be kept COMPACT in shared memory (PmfCompact below:
 //       one slot of r floats per touched row, filled by the row's owner in a fixed order - no float atomics, no dense
 //       P-vector that is zeroed, scattered into and read back every step; the diffusion pass looks the slot up).
-//       Full passes over all N ratings (SVRG refresh, K2, the full-batch bypass) scatter-add into a dense buffer.
+//       Deterministic, and it removes 2 of the 7 state accesses per element - but measured slower (capi.cu), because the
+//       kernel is bound by instruction issue in the RNG, not by traffic.  Full passes over all N ratings (SVRG refresh,
+//       K2, the full-batch bypass) always use the dense buffer.
 //   MLP (models/bayesian_NN/NN_model.py:31-58): see mlp_grad.cuh.
 #pragma once
 #include "prng.cuh"
@@ -31,8 +34,8 @@ namespace sg {
 // PMF: CTA shape of one chain.  Measured on C4 (512 chains, SGNHT, ms per 4 steps): 1024 threads x 64 registers 1.37 (the
 // elementwise passes spill the values they load, so every load is waited for at once), 512 x 128 regs 1.15,
 // 2 CTAs x 256 threads x 128 regs with 4 threefry blocks staged per thread 1.08 (default), 4 CTAs x 128 threads 1.11.
-// With the compact minibatch gradient (<= 190 KB of shared memory for C4) one CTA of 512 threads x 128 registers per SM;
-// models that fall back to the dense buffer keep 2 CTAs x 256 threads (big_threads() picks at launch time).
+// Default: 2 CTAs x 256 threads x 128 registers per SM; with the opt-in compact minibatch gradient (<= 190 KB of shared
+// memory for C4) one CTA of 512 threads (big_threads() picks at launch time; the kernel is compiled for <= 512).
 #ifndef SG_BIG_THREADS_PMF
 #define SG_BIG_THREADS_PMF 512
 #endif

@@ -469,7 +469,10 @@ int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
     if (cfg->family == SGMCMC_FAMILY_PMF) {
       // compact minibatch gradient in shared memory (csrc/big_sampler.cuh PmfCompact) when it fits beside the 227 KB limit
       const size_t limit = (size_t)227 * 1024 - ((sizeof(sg::BigSmem) + 127) & ~(size_t)127);
-      bm.pmf_compact = !env_int("SGMCMC_PMF_DENSE", 0) &&
+      // Opt-in (SGMCMC_PMF_COMPACT=1): bit-reproducible gradients, but measured SLOWER on C4 (4.63 vs 3.93 ms per
+      // 512 chains x 16 SGNHT steps): its 190 KB leave one CTA per SM, so the latency-bound gather phases no longer
+      // overlap a second chain's issue-bound diffusion pass, and the slot lookup adds instructions to that pass.
+      bm.pmf_compact = env_int("SGMCMC_PMF_COMPACT", 0) &&
                        sg::pmf_compact_ok(cfg->dims[0], cfg->dims[1], cfg->dims[2], bm.batch, bm.full_batch, limit) ? 1 : 0;
       bm.pmf_magic = (unsigned)((0x100000000ULL + (unsigned)cfg->dims[2] - 1) / (unsigned)cfg->dims[2]);
     }
@@ -870,7 +873,13 @@ int sgmcmc_ksd_imq_tc(const float* x, const float* g, int32_t n, int32_t d, int3
   CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)2 * d * sizeof(double), s));
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  kt::colsum_kernel<<<std::min(n, sms * 8), 128, 0, s>>>(x, g, n, d, sums);
+  if (d % 4 == 0 && d / 4 <= 256 && (((uintptr_t)x | (uintptr_t)g) & 15) == 0) {
+    const int d4 = d / 4, rpi = std::max(1, 256 / d4), threads = 256;
+    const int blocks = std::max(1, std::min((n + rpi - 1) / rpi, sms * 4));
+    kt::colsum4_kernel<<<blocks, threads, (size_t)rpi * d4 * 8 * sizeof(double), s>>>((const float4*)x, (const float4*)g, n, d4, sums);
+  } else {
+    kt::colsum_kernel<<<std::min(n, sms * 8), 128, 0, s>>>(x, g, n, d, sums);
+  }
   CUDA_TRY(cudaGetLastError()); ++g_launches;
   kt::split_kernel<<<(n + 7) / 8, 256, 0, s>>>(x, g, n, d, dp, sums, Z, rt);
   CUDA_TRY(cudaGetLastError()); ++g_launches;

@@ -319,3 +319,35 @@ def test_pmf_rejects_out_of_range_ids(cuda):
         with pytest.raises(_native.NativeError, match="id outside"):
             s(P.PRNGKey(0), 2, pmf_params(th0))
     NS.build_sgld_sampler(1e-5, fns[0], fns[1], (ij, r), 50, pbar=False)(P.PRNGKey(0), 2, pmf_params(th0))
+
+
+@pytest.mark.parametrize("name,dt,kw", [KERNELS[0], KERNELS[2], KERNELS[5], KERNELS[9], KERNELS[11]],
+                         ids=["sgld", "sgld_SVRG", "sgnht", "badodabCV", "sghmcCV"])
+def test_pmf_compact_gradient_mode(cuda, monkeypatch, name, dt, kw):
+    """SGMCMC_PMF_COMPACT=1: the minibatch gradient as compact shared-memory rows summed by row owners in stream order
+    (csrc/big_sampler.cuh PmfCompact).  Same single-step bars against the oracle as the default scatter-add path, the
+    two paths agree, and the compact path is bit-reproducible (no float atomics)."""
+    fam, fns, data, th0 = pmf_case(60, 80, 8, 3000, seed=8)                 # rank 8: whole float4 factor rows
+    center = [np.asarray(t * np.float32(0.98) + np.float32(0.003)) for t in th0]
+    runs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SGMCMC_PMF_COMPACT", mode)
+        ok, (init_fn, kernel, get_params) = build_pair(name, dt, kw, fam, fns, data, 200, center, pmf_params)
+        key = P.PRNGKey(0)
+        key, sub = P.split(key)
+        ost = ok.init_fn(sub, th0)
+        nst = init_fn(sub, pmf_params(th0))
+        g_ref, g_got = compare_state(ost, nst, get_params, f"{name} compact={mode} init")
+        assert np.abs(g_got - g_ref).max() / max(np.abs(g_ref).max(), 1.0) <= grad_tol(name)
+        for i in range(3):
+            key, sub = P.split(key)
+            nst = kernel(i, sub, inject(ost, nst))
+            ost = ok.kernel(i, sub, ost)
+            g_ref, g_got = compare_state(ost, nst, get_params, f"{name} compact={mode} step {i}")
+            assert np.abs(g_got - g_ref).max() / max(np.abs(g_ref).max(), 1.0) <= grad_tol(name)
+        _, sampler = build_pair(name, dt, kw, fam, fns, data, 200, center, pmf_params, sampler=True)
+        runs[mode] = [tree_leaves(sampler(P.PRNGKey(3), 6, pmf_params(th0))) for _ in range(2)]
+    for a, b in zip(runs["1"][0], runs["1"][1]):
+        assert np.array_equal(a, b)                                        # deterministic
+    for a, b in zip(runs["1"][0], runs["0"][0]):
+        close(a, b, rtol=2e-5, what=f"{name}: compact vs scatter-add trajectory")
