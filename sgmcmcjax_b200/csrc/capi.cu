@@ -864,7 +864,7 @@ int sgmcmc_ksd_imq_tc(const float* x, const float* g, int32_t n, int32_t d, int3
     return fail(SGMCMC_E_INVALID, "bad argument");
   if (((uintptr_t)workspace & 255) != 0) return fail(SGMCMC_E_INVALID, "workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  const int dp = kt::ksd_padded_dim(d);
+  const int dp = kt::padded_dim(d);
   uint8_t* w = (uint8_t*)workspace;
   float* Z = (float*)w;                       w += kt::align_up(kt::z_floats(n, d) * sizeof(float), 256);
   float4* rt = (float4*)w;                    w += kt::align_up((size_t)n * sizeof(float4), 256);

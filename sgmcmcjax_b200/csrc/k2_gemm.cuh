@@ -9,6 +9,11 @@
 //
 //   k2_scores_kernel   S = Theta . X~^T on a 128 x 128 tile (K = D), epilogue w = -sigmoid(S) -> tf32 hi / lo, written
 //                      chunk-major ([2][i-chunks][M][16]) so that it is the K-major A operand of the second kernel.
+//                      Two sets of TMEM accumulators (2 x 256 columns): the MMAs of tile t + 1 run under the epilogue of
+//                      tile t.  An epilogue warp's 32 rows x 16 columns are 2 KB of CONTIGUOUS W: staged in shared
+//                      memory (bank-conflict-free rotated 16-byte chunks) and written by one cp.async.bulk - the
+//                      per-lane stores of the first version (16 bytes at a 64-byte stride: 32 write transactions per
+//                      warp instruction) cost the load/store unit ~8 k of the 16 k cycles of a tile.
 //   k2_accum_kernel    G[m-tile][D] += W . X~ (K = the Nc rows of the chunk, 16 per stage), B operand = X~^T split and
 //                      stored [2][i-chunks][DN][16] once per data table; CTAs split K, fp32 atomics into G.
 //
@@ -27,9 +32,33 @@ constexpr int A_STAGE_BYTES = 4 * CHUNK_BYTES;
 constexpr int B_STAGES = 6;            // accumulate kernel: <= 32 KB stages
 constexpr int THREADS = 576;           // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 
-struct TailA { uint64_t full[A_STAGES], empty[A_STAGES], tmem_full, tmem_empty; uint32_t tmem_base, pad; };
+struct TailA { uint64_t full[A_STAGES], empty[A_STAGES], tmem_full[2], tmem_empty[2]; uint32_t tmem_base, pad; };
+constexpr int A_EPI_WARPS = 16;
+constexpr size_t A_STAGING = (size_t)A_EPI_WARPS * 2 * 32 * KC * 4;      // per epilogue warp: hi and lo block of 32 rows x 16 floats
 struct TailB { uint64_t full[B_STAGES], empty[B_STAGES], tmem_full; uint32_t tmem_base, pad; };
-constexpr size_t SMEM_A = 1024 + (size_t)A_STAGES * A_STAGE_BYTES + sizeof(TailA);
+constexpr size_t SMEM_A = 1024 + (size_t)A_STAGES * A_STAGE_BYTES + A_STAGING + sizeof(TailA);
+
+// logistic function with the MUFU exponential and reciprocal (relative error ~3e-7: inside the 2e-5 parity bar of K2)
+__device__ __forceinline__ float sigmoid_mufu(float z) {
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.44269504089f * fabsf(z)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+  return z >= 0.0f ? r : t * r;
+}
+// 16-byte chunk c (0..3) of sixteen floats, c a run-time value: selects instead of a dynamically indexed register array
+__device__ __forceinline__ float4 chunk_of(const float (&v)[16], int c) {
+  float4 r;
+  r.x = c == 0 ? v[0] : c == 1 ? v[4] : c == 2 ? v[8] : v[12];
+  r.y = c == 0 ? v[1] : c == 1 ? v[5] : c == 2 ? v[9] : v[13];
+  r.z = c == 0 ? v[2] : c == 1 ? v[6] : c == 2 ? v[10] : v[14];
+  r.w = c == 0 ? v[3] : c == 1 ? v[7] : c == 2 ? v[11] : v[15];
+  return r;
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 inline size_t b_stage_bytes(int dn) { return 2 * (size_t)CHUNK_BYTES + 2 * (size_t)dn * KC * 4; }
 inline size_t smem_b(int dn) { return 1024 + (size_t)B_STAGES * b_stage_bytes(dn) + sizeof(TailB); }
 
@@ -97,7 +126,8 @@ k2_scores_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                  int dp, int i0, int nc, float* __restrict__ W) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  TailA* tail = reinterpret_cast<TailA*>(smem + (size_t)A_STAGES * A_STAGE_BYTES);
+  uint8_t* staging = smem + (size_t)A_STAGES * A_STAGE_BYTES;
+  TailA* tail = reinterpret_cast<TailA*>(staging + A_STAGING);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MT = (m + TILE - 1) / TILE, IT = (nc + TILE - 1) / TILE;
   const long long total = (long long)MT * IT;
@@ -105,8 +135,7 @@ k2_scores_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < A_STAGES; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
-    mbar_init(&tail->tmem_full, 1);
-    mbar_init(&tail->tmem_empty, 16);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tail->tmem_full[b], 1); mbar_init(&tail->tmem_empty[b], A_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(&tail->tmem_base, 512); tmem_relinquish(); }
@@ -136,9 +165,11 @@ k2_scores_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, acc_phase = 0;
-      for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-        mbar_wait(&tail->tmem_empty, acc_phase ^ 1);
+      uint32_t stage = 0, phase = 0, u = 0;
+      for (long long t = blockIdx.x; t < total; t += gridDim.x, ++u) {
+        const uint32_t buf = u & 1u, use = (u >> 1) & 1u;      // accumulator set, parity of its use count
+        const uint32_t acc = tmem_base + buf * 256u;
+        mbar_wait(&tail->tmem_empty[buf], use ^ 1u);
         tc_fence_after();
         for (int c = 0; c < chunks; ++c) {
           mbar_wait(&tail->full[stage], phase);
@@ -149,55 +180,76 @@ k2_scores_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
           const uint64_t dx = make_desc_sw64(sb + 2 * CHUNK_BYTES);          // [Xh | Xl]: 256 rows
           for (int k = 0; k < slices; ++k) {
             const uint32_t accum = (c | k) ? 1u : 0u;
-            umma_tf32(tmem_base, dth + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc_n(256), accum);   // Th.Xh | Th.Xl
-            umma_tf32(tmem_base, dtl + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc_n(128), 1u);      // += Tl.Xh
+            umma_tf32(acc, dth + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc_n(256), accum);   // Th.Xh | Th.Xl
+            umma_tf32(acc, dtl + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc_n(128), 1u);      // += Tl.Xh
           }
           tc_commit(&tail->empty[stage]);
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tail->tmem_full);
-        acc_phase ^= 1;
+        tc_commit(&tail->tmem_full[buf]);
       }
     }
   } else {
     const int q = warp & 3, cgrp = (warp - 2) >> 2;
     const int row_in_tile = q * 32 + lane;
-    uint32_t acc_phase = 0;
     const size_t seg_stride = (size_t)nic * m * KC;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    float* s_hi = reinterpret_cast<float*>(staging + (size_t)(warp - 2) * 2 * 32 * KC * 4);   // [32 rows][16]
+    float* s_lo = s_hi + 32 * KC;
+    uint32_t u = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++u) {
+      const uint32_t buf = u & 1u, use = (u >> 1) & 1u;
       const int mt = (int)(t / IT), it = (int)(t % IT);
       const int gm = mt * TILE + row_in_tile;
-      mbar_wait(&tail->tmem_full, acc_phase);
+      const int gm0 = mt * TILE + q * 32;                     // first row of this warp
+      mbar_wait(&tail->tmem_full[buf], use);
       tc_fence_after();
-      const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+      const uint32_t tl = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int cb = cgrp * 32; cb < cgrp * 32 + 32; cb += 8) {
-        uint32_t p0[8], p1[8];
-        tmem_ld8(tl + cb, p0);                                 // Th.Xh + Tl.Xh
-        tmem_ld8(tl + TILE + cb, p1);                          // Th.Xl
+      for (int cb = cgrp * 32; cb < cgrp * 32 + 32; cb += KC) {
+        uint32_t p0[16], p1[16];
+        tmem_ld16(tl + cb, p0);                                // Th.Xh + Tl.Xh
+        tmem_ld16(tl + TILE + cb, p1);                         // Th.Xl
         tmem_ld_wait();
-        const int ic = (it * TILE + cb) / KC;                  // row chunk of these 8 columns
-        if (gm < m && ic < nic) {
-          float hi[8], lo[8];
+        const int ic = (it * TILE + cb) / KC;                  // row chunk of these 16 columns
+        if (ic >= nic) continue;                               // warp-uniform
+        float hi[16], lo[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float sc = __uint_as_float(p1[e]) + __uint_as_float(p0[e]);
-            const float w = -sigmoid_f(sc);
-            hi[e] = tf32_rna(w);
-            lo[e] = tf32_rna(w - hi[e]);
+        for (int e = 0; e < 16; ++e) {
+          const float w = -sigmoid_mufu(__uint_as_float(p1[e]) + __uint_as_float(p0[e]));
+          hi[e] = tf32_rna(w);
+          lo[e] = tf32_rna(w - hi[e]);
+        }
+        float* dst = W + ((size_t)ic * m + gm0) * KC;          // this warp's 32 rows x 16 floats: 2 KB contiguous
+        if (gm0 + 32 <= m) {
+          if (lane == 0) bulk_wait_read();                     // the previous block has left the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                        // lane l, instruction k: chunk (k + l / 2) % 4 - no bank conflicts
+            const int c = (k + (lane >> 1)) & 3;
+            *reinterpret_cast<float4*>(s_hi + lane * KC + 4 * c) = chunk_of(hi, c);
+            *reinterpret_cast<float4*>(s_lo + lane * KC + 4 * c) = chunk_of(lo, c);
           }
-          float* dst = W + ((size_t)ic * m + gm) * KC + (cb & (KC - 1));
-          *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(dst + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-          *reinterpret_cast<float4*>(dst + seg_stride) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<float4*>(dst + seg_stride + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            bulk_store(dst, s_hi, 32 * KC * 4);
+            bulk_store(dst + seg_stride, s_lo, 32 * KC * 4);
+            bulk_commit();
+          }
+        } else if (gm < m) {                                   // ragged last row tile: per-lane stores
+          float* d = dst + (size_t)lane * KC;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            *reinterpret_cast<float4*>(d + 4 * c) = make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            *reinterpret_cast<float4*>(d + seg_stride + 4 * c) = make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tail->tmem_empty);
-      acc_phase ^= 1;
+      if (lane == 0) mbar_arrive(&tail->tmem_empty[buf]);
     }
+    if (lane == 0) bulk_wait_read();                           // shared memory must outlive the bulk reads
   }
   tc_fence_before();
   __syncthreads();

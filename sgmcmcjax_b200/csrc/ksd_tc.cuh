@@ -14,16 +14,7 @@
 // a_hi = rna_tf32(a), a_lo = rna_tf32(a - a_hi);  a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi
 // (error ~2^-21 |a||b|, fp32 accumulation in TMEM).  The N^2 sum is accumulated in fp64.
 //
-// Row terms inside the contraction.  The operands carry four extra columns (the zero pad of the last K-chunk, so no
-// extra MMA work for D = 100) that differ between the row side (I) and the column side (J):
-//     x rows: [-xx_i/2, 1, -gx_i, 0]   x cols: [1, -xx_j/2, 0, -gx_j]      g rows: [0, 0, r_i, 1]   g cols: [0, 0, 1, r_j]
-// so that the tensor core itself delivers
-//     P1 = x_I.x_J - (xx_i + xx_j)/2 = -dd/2,    P23 = x_I.g_J + g_I.x_J - gx_i - gx_j = -gd,    P4 = g_I.g_J + r_i + r_j = gg
-// (x.g and g.x accumulate into ONE accumulator: three TMEM accumulators instead of four), and the epilogue is nine
-// instructions per pair with no per-column shared-memory term:  b = 1 - 2 P1,  k0 = P4 b^-1/2 + (D - P23 + 6 P1 / b) b^-3/2.
-// The 3xTF32 split carries the extra columns at fp32 accuracy (a "1" is hi = 1, lo = 0).
-//
-// Operand matrix  Z[4][chunks][n][16]  fp32, followed by the COLUMN-side variant of the last chunk  Zc[4][n][16] (columns zero padded to whole 16-float chunks; chunk-major so that the
+// Operand matrix  Z[4][chunks][n][16]  fp32 (columns zero padded to whole 16-float chunks; chunk-major so that the
 // 128-row x 16-float TMA box of one (segment, chunk) is 8 KB of contiguous global memory), segments
 // 0 = xc_hi, 1 = xc_lo, 2 = gc_hi, 3 = gc_lo; row terms rt[n] = (xx, gx, r, |g|^2).
 // Exact diagonal: for i == j the reference has x_i - x_j = 0 exactly, k0 = |g_i|^2 + D; the 3xTF32 residual
@@ -55,6 +46,7 @@ struct SmemTail {                  // after the stage buffers
   uint64_t full[STAGES], empty[STAGES], tmem_full, tmem_empty;
   uint32_t tmem_base;
   uint32_t pad;
+  float4 colterm[2][TILE];
 };
 constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
 
@@ -213,8 +205,7 @@ static __global__ void colsum4_kernel(const float4* __restrict__ X, const float4
   }
 }
 
-// One warp per row: centre, split into tf32 hi / lo, row terms; the four row-term columns dp-4 .. dp-1 (see the header) in
-// the row-side variant (inside Z) and, for the whole last chunk, the column-side variant Zc.
+// One warp per row: centre, split into tf32 hi / lo, row terms.
 static __global__ void split_kernel(const float* __restrict__ X, const float* __restrict__ G, int n, int d, int dp,
                              const double* __restrict__ sums, float* __restrict__ Z, float4* __restrict__ rt) {
   const int lane = threadIdx.x & 31;
@@ -224,9 +215,6 @@ static __global__ void split_kernel(const float* __restrict__ X, const float* __
   float xx = 0.f, gx = 0.f, r = 0.f, mm = 0.f, g2 = 0.f;
   const int n_chunks = (dp + KC - 1) / KC;
   const int dpc = n_chunks * KC;                 // columns incl. the zero pad of the last chunk
-  const size_t blk = (size_t)n * KC;             // one (segment, chunk) block: [n][KC], a 128-row TMA box is 8 KB contiguous
-  const size_t seg_stride = (size_t)n_chunks * blk;
-  float* Zc = Z + 4 * seg_stride;                // column-side variant of the last chunk: [4 segments][n][KC]
   for (int c = lane; c < dpc; c += 32) {
     float xh = 0.f, xl = 0.f, gh = 0.f, gl = 0.f;
     if (c < d) {
@@ -239,13 +227,10 @@ static __global__ void split_kernel(const float* __restrict__ X, const float* __
       gh = tf32_rna(gc); gl = tf32_rna(gc - gh);
       xx = fmaf(xc, xc, xx); gx = fmaf(gc, xc, gx); r = fmaf(mg, gc, r); mm = fmaf(mg, mg, mm);
     }
-    if (c >= dp - 4 && c < dp) continue;         // row-term columns: written below, once the sums are complete
+    // chunk-major layout: every (segment, chunk) is one contiguous [n][KC] block, so a 128-row TMA box is 8 KB contiguous
+    const size_t blk = (size_t)n * KC;
     float* z = Z + ((size_t)(c / KC) * n + row) * KC + (c % KC);
-    z[0] = xh; z[seg_stride] = xl; z[2 * seg_stride] = gh; z[3 * seg_stride] = gl;
-    if (c / KC == n_chunks - 1) {
-      float* zc = Zc + (size_t)row * KC + (c % KC);
-      zc[0] = xh; zc[blk] = xl; zc[2 * blk] = gh; zc[3 * blk] = gl;
-    }
+    z[0] = xh; z[(size_t)n_chunks * blk] = xl; z[2 * (size_t)n_chunks * blk] = gh; z[3 * (size_t)n_chunks * blk] = gl;
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
@@ -253,23 +238,7 @@ static __global__ void split_kernel(const float* __restrict__ X, const float* __
     r += __shfl_xor_sync(0xffffffffu, r, o);   mm += __shfl_xor_sync(0xffffffffu, mm, o);
     g2 += __shfl_xor_sync(0xffffffffu, g2, o);
   }
-  const float rr = r + 0.5f * mm;
-  if (lane == 0) rt[row] = make_float4(xx, gx, rr, g2);
-  if (lane < 4) {
-    // column dp-4+lane of:   x rows [-xx/2, 1, -gx, 0]   x cols [1, -xx/2, 0, -gx]   g rows [0, 0, rr, 1]   g cols [0, 0, 1, rr]
-    const float xr = lane == 0 ? -0.5f * xx : lane == 1 ? 1.0f : lane == 2 ? -gx : 0.0f;
-    const float xcv = lane == 0 ? 1.0f : lane == 1 ? -0.5f * xx : lane == 2 ? 0.0f : -gx;
-    const float gr = lane == 2 ? rr : lane == 3 ? 1.0f : 0.0f;
-    const float gcv = lane == 2 ? 1.0f : lane == 3 ? rr : 0.0f;
-    const int c = dp - 4 + lane;
-    float* z = Z + ((size_t)(c / KC) * n + row) * KC + (c % KC);
-    float* zc = Zc + (size_t)row * KC + (c % KC);
-    float h;
-    h = tf32_rna(xr);  z[0] = h;               z[seg_stride] = tf32_rna(xr - h);
-    h = tf32_rna(gr);  z[2 * seg_stride] = h;  z[3 * seg_stride] = tf32_rna(gr - h);
-    h = tf32_rna(xcv); zc[0] = h;              zc[blk] = tf32_rna(xcv - h);
-    h = tf32_rna(gcv); zc[2 * blk] = h;        zc[3 * blk] = tf32_rna(gcv - h);
-  }
+  if (lane == 0) rt[row] = make_float4(xx, gx, r + 0.5f * mm, g2);
 }
 
 // ------------------------------------------------------------------------------------------ tiles
@@ -296,27 +265,15 @@ __device__ __forceinline__ float imq_k0_tc(float dd, float gg, float gd, float d
   return gg * r + (gd + dim) * r3 - 3.0f * dd * r3 * r2;
 }
 
-// k0 from the augmented products: p1 = -dd/2, p23 = -gd, gg
-__device__ __forceinline__ float imq_k0_aug(float p1, float p23, float gg, float dim) {
-  const float b = fmaf(-2.0f, p1, 1.0f);
-  float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-  const float r2 = r * r;
-  const float r3 = r2 * r;
-  const float u = fmaf(6.0f * p1, r2, dim - p23);          // (gd + D) - 3 dd / b
-  return fmaf(gg, r, u * r3);
-}
-
 // Paired products.  The column-side chunks of a stage are laid out [xh_J | gh_J | xl_J | gl_J], so that one N = 256
 // MMA multiplies a row-side segment with TWO adjacent column-side segments and writes two adjacent TMEM
 // accumulators: half the MMA instructions, and the A operand is read from shared memory once per 256 columns
 // (12 KB of operand traffic per 128 tensor cycles instead of 8 KB per 64, the 128 B/clk shared-memory port).
-//   TMEM columns: [0,128) x_I.x_J   [128,256) x_I.g_J + g_I.x_J   [256,384) g_I.g_J     (384 of the 512 allocated)
-// The x_I pairs write columns [0,256), the g_I pairs columns [128,384): both accumulate the cross term in the middle.
+//   TMEM columns: [0,128) x_I.x_J   [128,256) x_I.g_J   [256,384) g_I.x_J   [384,512) g_I.g_J
 // table: (TMEM column of the pair, row-side segment 0 xh 1 xl 2 gh 3 gl, column-side pair 0 = [xh|gh], 1 = [xl|gl])
 static __constant__ int16_t PROD[6][3] = {
     {0, 0, 0}, {0, 0, 1}, {0, 1, 0},          // x_I . [x_J | g_J]  (3xTF32: hi.hi, hi.lo, lo.hi)
-    {128, 2, 0}, {128, 2, 1}, {128, 3, 0}     // g_I . [x_J | g_J]
+    {256, 2, 0}, {256, 2, 1}, {256, 3, 0}     // g_I . [x_J | g_J]
 };
 __device__ __forceinline__ int col_slot(int seg) { return ((seg & 1) << 1) | (seg >> 1); }   // xh 0, gh 1, xl 2, gl 3
 
@@ -361,10 +318,8 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
 #pragma unroll
           for (int seg = 0; seg < 4; ++seg) {
             const int blk_row = (seg * n_chunks + c) * n;          // first row of block (segment, chunk) in the [.., KC] view
-            // the last chunk holds the row-term columns, which differ on the column side: variant block Zc[seg]
-            const int col_row = c == n_chunks - 1 ? (4 * n_chunks + seg) * n : blk_row;
             tma_load_2d(sbase + seg * CHUNK_BYTES, &zmap, 0, blk_row + I * TILE, &tail->full[stage]);
-            tma_load_2d(sbase + (4 + col_slot(seg)) * CHUNK_BYTES, &zmap, 0, col_row + J * TILE, &tail->full[stage]);
+            tma_load_2d(sbase + (4 + col_slot(seg)) * CHUNK_BYTES, &zmap, 0, blk_row + J * TILE, &tail->full[stage]);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -377,7 +332,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       for (long long u = blockIdx.x; u < n_local; u += gridDim.x) {
         mbar_wait(&tail->tmem_empty, acc_phase ^ 1);
         tc_fence_after();
-        uint32_t started = 0;                                  // bit a set once pair a (0: x_I, 1: g_I) has been issued
+        uint32_t started = 0;                                  // bit a set once accumulator a holds data
         for (int c = 0; c < n_chunks; ++c) {
           mbar_wait(&tail->full[stage], phase);
           tc_fence_after();
@@ -386,21 +341,13 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
           const int slices = valid / UMMA_K;
 #pragma unroll
           for (int p = 0; p < 6; ++p) {
-            const int a = PROD[p][0] >> 7;                         // 0: columns [0,256), 1: columns [128,384)
+            const int a = PROD[p][0] >> 8;                         // 0: columns [0,256), 1: columns [256,512)
             const uint64_t da = make_desc_sw64(sbase + PROD[p][1] * CHUNK_BYTES);
             const uint64_t db = make_desc_sw64(sbase + (4 + 2 * PROD[p][2]) * CHUNK_BYTES);
             for (int k = 0; k < slices; ++k) {
               // advancing K inside the swizzle atom = +32 bytes on the start address (>>4 => +2)
-              if (a == 1 && !(started & 2u)) {
-                // first g_I MMA of the tile: ADD to the cross accumulator the x_I pair has started, START g.g -
-                // one instruction has one accumulate flag, so this slice is issued as two N = 128 halves
-                umma_tf32(tmem_base + 128, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_TF32_128x128, 1u);
-                umma_tf32(tmem_base + 256, da + (uint64_t)(k * 2), db + (uint64_t)((CHUNK_BYTES >> 4) + k * 2),
-                          IDESC_TF32_128x128, 0u);
-              } else {
-                umma_tf32(tmem_base + PROD[p][0], da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_TF32_128x256,
-                          (started >> a) & 1u);
-              }
+              umma_tf32(tmem_base + PROD[p][0], da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_TF32_128x256,
+                        (started >> a) & 1u);
               started |= 1u << a;
             }
           }
@@ -416,38 +363,58 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
     const int q = warp & 3;
     const int cgrp = (warp - 2) >> 2;                          // 0..3
     const int row_in_tile = q * 32 + lane;
+    const int et = threadIdx.x - 64;                           // 0..511
     const float dim = (float)d;
     double acc = 0.0;
     uint32_t acc_phase = 0;
+    int buf = 0;
     for (long long u = blockIdx.x; u < n_local; u += gridDim.x) {
       int I, J;
       tile_of(part + (long long)nparts * u, T, I, J);
       const int gi = I * TILE + row_in_tile;
-      const bool diag_tile = I == J;
-      const float g2i = (diag_tile && gi < n) ? rt[gi].w : 0.f;   // |g_i|^2: the exact i == j pair
+      const int gjc = J * TILE + et;
+      if (et < TILE) tail->colterm[buf][et] = gjc < n ? rt[gjc] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 ri = gi < n ? rt[gi] : make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("bar.sync 1, 512;" ::: "memory");          // colterm[buf] visible to the 16 epilogue warps
       mbar_wait(&tail->tmem_full, acc_phase);
       tc_fence_after();
       float tsum = 0.f;
+      const uint32_t colterm_s = smem_u32(&tail->colterm[buf][0]);   // read with ld.shared (the generic path is slower)
+      auto colterm = [&](int j) {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(colterm_s + 16u * (uint32_t)j));
+        return v;
+      };
+      const bool diag_tile = I == J;
       const int jmax = min(TILE, n - J * TILE);
       const bool interior = !diag_tile && (I + 1) * TILE <= n && jmax == TILE;   // no masks, no exact diagonal
       const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cb = cgrp * 32; cb < cgrp * 32 + 32; cb += 8) {
-        uint32_t p1[8], p2[8], p3[8];
-        tmem_ld8(tl + cb, p1);                  // x_I.x_J - (xx_i + xx_j) / 2
-        tmem_ld8(tl + TILE + cb, p2);           // x_I.g_J + g_I.x_J - gx_i - gx_j
-        tmem_ld8(tl + 2 * TILE + cb, p3);       // g_I.g_J + r_i + r_j
+        uint32_t p1[8], p2[8], p3[8], p4[8];
+        tmem_ld8(tl + cb, p1);                  // x_I.x_J
+        tmem_ld8(tl + 3 * TILE + cb, p2);       // g_I.g_J
+        tmem_ld8(tl + TILE + cb, p3);           // x_I.g_J
+        tmem_ld8(tl + 2 * TILE + cb, p4);       // g_I.x_J
         tmem_ld_wait();
         if (interior) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            tsum += imq_k0_aug(__uint_as_float(p1[e]), __uint_as_float(p2[e]), __uint_as_float(p3[e]), dim);
+          for (int e = 0; e < 8; ++e) {
+            const float4 cj = colterm(cb + e);
+            const float dd = fmaf(-2.0f, __uint_as_float(p1[e]), ri.x + cj.x);
+            const float gg = __uint_as_float(p2[e]) + (ri.z + cj.z);
+            const float gd = (ri.y + cj.y) - (__uint_as_float(p3[e]) + __uint_as_float(p4[e]));
+            tsum += imq_k0_tc(dd, gg, gd, dim);
+          }
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float a1 = __uint_as_float(p1[e]), a2 = __uint_as_float(p2[e]), a3 = __uint_as_float(p3[e]);
-            if (diag_tile && cb + e == row_in_tile) { a1 = 0.f; a2 = 0.f; a3 = g2i; }   // i == j: dd = gd = 0, gg = |g_i|^2
-            const float k0 = imq_k0_aug(a1, a2, a3, dim);
+            const float4 cj = colterm(cb + e);
+            float dd = fmaf(-2.0f, __uint_as_float(p1[e]), ri.x + cj.x);
+            float gg = __uint_as_float(p2[e]) + (ri.z + cj.z);
+            float gd = (ri.y + cj.y) - (__uint_as_float(p3[e]) + __uint_as_float(p4[e]));
+            if (diag_tile && cb + e == row_in_tile) { dd = 0.f; gd = 0.f; gg = ri.w; }   // i == j: exact
+            const float k0 = imq_k0_tc(dd, gg, gd, dim);
             tsum += (gi < n && cb + e < jmax) ? k0 : 0.f;
           }
         }
@@ -457,6 +424,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       if (lane == 0) mbar_arrive(&tail->tmem_empty);           // accumulators may be overwritten
       acc += (double)tsum * (I == J ? 1.0 : 2.0);
       acc_phase ^= 1;
+      buf ^= 1;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -471,10 +439,8 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
 // ------------------------------------------------------------------------------------------ host
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int padded_dim(int d) { return (d + 7) & ~7; }
-inline int ksd_padded_dim(int d) { return (d + 4 + 7) & ~7; }      // + the four row-term columns (dp-4 .. dp-1)
-// Z [4 segments][chunks][n][KC] and the column-side variant of the last chunk Zc [4 segments][n][KC]
-inline size_t z_floats(int n, int d) { return (size_t)4 * ((ksd_padded_dim(d) + KC - 1) / KC + 1) * KC * (size_t)n; }
-// workspace: Z | Zc floats | row terms [n] float4 | column sums [2 d] doubles
+inline size_t z_floats(int n, int d) { return (size_t)4 * ((padded_dim(d) + KC - 1) / KC) * KC * (size_t)n; }
+// workspace: Z [4 segments][chunks][n][KC] floats | row terms [n] float4 | column sums [2 d] doubles
 inline size_t workspace_bytes(int n, int d) {
   return align_up(z_floats(n, d) * sizeof(float), 256) + align_up((size_t)n * sizeof(float4), 256) +
          align_up((size_t)2 * d * sizeof(double), 256);

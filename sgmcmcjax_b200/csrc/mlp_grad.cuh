@@ -501,6 +501,16 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
 
     { SG_T0(); layer1_forward(m, ms, region, th, nb, R, act(1), astr(1)); SG_T1(1); }
     SG_T0();
+    // W_2 (sz[2] x sz[1] floats, 4 KB for 784-100-10) is read by every thread of the layer-2 forward and of the dZ_1
+    // back-propagation: from global memory those loops are bound by L2 latency (measured 43 us of the 76 us "small
+    // layers" phase in the quad dZ_1 loop alone).  Stage it once per sub-batch in the part of xs the bias-gradient
+    // scratch (first 8 KB) leaves free; xs is idle until layer1_backward streams X.
+    float* w2s = nullptr;
+    if (L >= 2 && (size_t)sz[2] * sz[1] * sizeof(float) + 8192 <= plan.xs_bytes) {
+      w2s = reinterpret_cast<float*>(xs + 8192);
+      const float* W2g = th + m.leaf_off[2];
+      for (int o = tid; o < sz[2] * sz[1]; o += MLP_THREADS) w2s[o] = W2g[o];
+    }
 
     // =================================================================== softmax + small layers forward
     for (int l = 1; l < L; ++l) {
@@ -519,7 +529,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       SG_T1(4);
       float* Zn = act(l + 1);
       const int zs = astr(l + 1), wn = sz[l + 1];
-      const float* Wn = th + m.leaf_off[2 * l];
+      const float* Wn = (l == 1 && w2s) ? w2s : th + m.leaf_off[2 * l];       // staged by the time of the barrier above
       const float* bn = th + m.leaf_off[2 * l + 1];
       for (int o = tid; o < R * wn; o += MLP_THREADS) {            // z_{l+1}[b][n] = a_l[b] . W[n] + b[n]
         const int b = o % R, n = o / R;
@@ -574,7 +584,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       const int w = sz[l], wp = sz[l - 1];
       const float* A = act(l - 1);
       const int as = astr(l - 1);
-      const float* Wl = th + m.leaf_off[2 * (l - 1)];
+      const float* Wl = (l == 2 && w2s) ? w2s : th + m.leaf_off[2 * (l - 1)];
       float* gW = g + m.leaf_off[2 * (l - 1)];
       float* gb = g + m.leaf_off[2 * (l - 1) + 1];
       SG_T0();

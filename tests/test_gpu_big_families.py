@@ -347,7 +347,8 @@ def test_pmf_compact_gradient_mode(cuda, monkeypatch, name, dt, kw):
             assert np.abs(g_got - g_ref).max() / max(np.abs(g_ref).max(), 1.0) <= grad_tol(name)
         _, sampler = build_pair(name, dt, kw, fam, fns, data, 200, center, pmf_params, sampler=True)
         runs[mode] = [tree_leaves(sampler(P.PRNGKey(3), 6, pmf_params(th0))) for _ in range(2)]
-    for a, b in zip(runs["1"][0], runs["1"][1]):
-        assert np.array_equal(a, b)                                        # deterministic
+    if "SVRG" not in name:                 # the SVRG refresh is a FULL pass: dense buffer, float atomics in either mode
+        for a, b in zip(runs["1"][0], runs["1"][1]):
+            assert np.array_equal(a, b)                                    # deterministic
     for a, b in zip(runs["1"][0], runs["0"][0]):
         close(a, b, rtol=2e-5, what=f"{name}: compact vs scatter-add trajectory")
