@@ -27,6 +27,14 @@
 namespace sg {
 
 constexpr int MLP_ROWS = 128;      // largest sub-batch (MMA M of the forward contraction)
+#ifndef SG_MLP_W_LDCG
+#define SG_MLP_W_LDCG 0
+#endif
+// SG_MLP_ISSUER_WARP: a 17th warp issues every tcgen05.mma of the two layer-1 GEMMs; the 512 workers hand a filled stage
+// over with an mbarrier arrive instead of a block barrier followed by thread 0 issuing 12 MMAs while 511 threads wait
+#ifndef SG_MLP_ISSUER_WARP
+#define SG_MLP_ISSUER_WARP 0
+#endif
 constexpr int MLP_THREADS = 512;   // gradient worker threads (warps 0..15); the CTA has 8 more noise-producer warps
 constexpr int MLP_KC = 32;         // forward K chunk (floats): one 128-byte swizzled row
 constexpr size_t MLP_SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
@@ -36,7 +44,9 @@ __host__ __device__ inline int mlp_n16(int w) { return (w + 15) & ~15; }
 
 struct MlpSmem {
   uint64_t bar[2];             // stage-free barriers (tcgen05.commit arrives)
-  uint32_t parity[2];          // their next phase parity, carried from one GEMM to the next
+  uint64_t ready[2];           // stage-filled barriers: one arrival per worker thread (SG_MLP_ISSUER_WARP)
+  uint32_t parity[2];          // next phase parity of bar[], carried from one GEMM to the next (worker side)
+  uint32_t rparity[2];         // next phase parity of ready[] (issuer side)
   uint32_t tmem_base;
   uint32_t pad;
   int idx[MLP_ROWS];
@@ -179,7 +189,9 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     MlpSmem& ms = *reinterpret_cast<MlpSmem*>(fam_smem);
     if (threadIdx.x == 0) {
       mlptc::mbar_init(&ms.bar[0], 1); mlptc::mbar_init(&ms.bar[1], 1);
+      mlptc::mbar_init(&ms.ready[0], MLP_THREADS); mlptc::mbar_init(&ms.ready[1], MLP_THREADS);
       ms.parity[0] = ms.parity[1] = 0;
+      ms.rparity[0] = ms.rparity[1] = 0;
       mlptc::fence_barrier_init();
     }
     if (threadIdx.x < 32) { mlptc::tmem_alloc(&ms.tmem_base, (uint32_t)mlp_plan(m.dims, m.batch).tmem_cols); mlptc::tmem_relinquish(); }
@@ -223,6 +235,34 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     const int s0p8 = (s0 + 7) & ~7;
     const uint32_t idesc = idesc_tf32(s1n, false);
     const uint32_t tmem = ms.tmem_base;
+#if SG_MLP_ISSUER_WARP
+    if (tid >= MLP_THREADS) {
+      // MMA issuer (one thread of the extra warp): chunk c is in stage c & 1 once all 512 workers have arrived on
+      // ready[c & 1]; 12 MMAs per chunk and the commit that frees the stage - off the workers' critical path
+      if (tid == MLP_THREADS) {
+        uint32_t rp[2] = {ms.rparity[0], ms.rparity[1]};
+        for (int c = 0; c < n_chunks; ++c) {
+          const int st = c & 1;
+          mbar_wait(&ms.ready[st], rp[st]); rp[st] ^= 1;
+          tc_fence_after();
+          uint8_t* sb = region + (size_t)st * stage_bytes;
+          uint8_t* whi = sb + 2 * MLP_ROWS * 128;
+          const int slices = min(MLP_KC, s0p8 - c * MLP_KC) / 8;
+          const uint64_t dxh = desc_k_sw128(smem_u32(sb)), dxl = desc_k_sw128(smem_u32(sb + MLP_ROWS * 128));
+          const uint64_t dwh = desc_k_sw128(smem_u32(whi)), dwl = desc_k_sw128(smem_u32(whi + (size_t)s1n * 128));
+          for (int sl = 0; sl < slices; ++sl) {
+            const uint64_t adv = (uint64_t)(sl * 2);
+            umma_tf32(tmem, dxl + adv, dwh + adv, idesc, (c | sl) ? 1u : 0u);
+            umma_tf32(tmem, dxh + adv, dwl + adv, idesc, 1u);
+            umma_tf32(tmem, dxh + adv, dwh + adv, idesc, 1u);
+          }
+          tc_commit(&ms.bar[st]);
+        }
+        ms.rparity[0] = rp[0]; ms.rparity[1] = rp[1];
+      }
+      return;
+    }
+#endif
     uint32_t par[2] = {ms.parity[0], ms.parity[1]};
 
     // this thread's items: rows tid >> 3 and (tid >> 3) + 64 of X and of W1 (if in range); 16-byte chunk tid & 7
@@ -251,8 +291,13 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         const int kk = min(k, s0 - 4);
         xv0 = __ldg(reinterpret_cast<const float4*>(xp0 + kk));
         xv1 = __ldg(reinterpret_cast<const float4*>(xp1 + kk));
+#if SG_MLP_W_LDCG   // experiment: explicit ld.global.cg (L2) instead of generic loads for the W1 operand
+        const float2 a0 = __ldcg(reinterpret_cast<const float2*>(wp0 + kk)), a1 = __ldcg(reinterpret_cast<const float2*>(wp0 + kk + 2));
+        const float2 b0 = __ldcg(reinterpret_cast<const float2*>(wp1 + kk)), b1 = __ldcg(reinterpret_cast<const float2*>(wp1 + kk + 2));
+#else
         const float2 a0 = *reinterpret_cast<const float2*>(wp0 + kk), a1 = *reinterpret_cast<const float2*>(wp0 + kk + 2);
         const float2 b0 = *reinterpret_cast<const float2*>(wp1 + kk), b1 = *reinterpret_cast<const float2*>(wp1 + kk + 2);
+#endif
         wv0 = make_float4(a0.x, a0.y, a1.x, a1.y);      // NO use of the loaded values here: masking happens in step(),
         wv1 = make_float4(b0.x, b0.y, b1.x, b1.y);      // a use right after the load would stall the thread on it
         return;
@@ -290,11 +335,20 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       SG_TB(10, tt);
       fence_proxy_async();                      // BEFORE the next loads are issued: the fence would wait for them too
       SG_TB(11, tt);
+#if SG_MLP_ISSUER_WARP
+      tc_fence_before();
+      mbar_arrive(&ms.ready[st]);               // no barrier among the workers: the issuer warp takes it from here
+      SG_TB(12, tt);
+      if (c + 2 < n_chunks) fetch(c + 2, xv0, xv1, wv0, wv1);               // two chunks of loads stay in flight
+      SG_TB(14, tt);
+      if (false) {
+#else
       mlptc::worker_sync();
       SG_TB(12, tt);
       if (c + 2 < n_chunks) fetch(c + 2, xv0, xv1, wv0, wv1);               // two chunks of loads stay in flight
       SG_TB(14, tt);
       if (tid == 0) {
+#endif
         tc_fence_after();
         const int slices = min(MLP_KC, s0p8 - c * MLP_KC) / 8;
         const uint64_t dxh = desc_k_sw128(smem_u32(xhi)), dxl = desc_k_sw128(smem_u32(xlo));
@@ -372,8 +426,41 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     const uint32_t tmem = ms.tmem_base;
     const uint8_t* bhi = region;
     const uint8_t* blo = region + (size_t)(rows / 8) * 4096;
-    uint32_t par[2] = {ms.parity[0], ms.parity[1]};
     const size_t stage_bytes = 2 * 8 * 256 * sizeof(float);      // [hi 8 KB | lo 8 KB]
+#if SG_MLP_ISSUER_WARP
+    if (tid >= MLP_THREADS) {
+      if (tid == MLP_THREADS) {                                   // MMA issuer, as in layer1_forward
+        uint32_t rp[2] = {ms.rparity[0], ms.rparity[1]};
+        for (int t0 = 0; t0 < n_tiles; t0 += tiles_per_pass) {
+          const int pass_tiles = min(tiles_per_pass, n_tiles - t0);
+          const int npp = (pass_tiles + 1) >> 1;
+          const int units = G * npp;
+          for (int u = 0; u < units; ++u) {
+            const int st = u & 1;
+            mbar_wait(&ms.ready[st], rp[st]); rp[st] ^= 1;
+            tc_fence_after();
+            const uint8_t* sb = xs + (size_t)st * stage_bytes;
+            const int g = u / npp, p = u - g * npp;
+            const uint64_t dbh = desc_mn_sw128_32b(smem_u32(bhi) + (uint32_t)g * 4096u, 1024u, 512u);
+            const uint64_t dbl = desc_mn_sw128_32b(smem_u32(blo) + (uint32_t)g * 4096u, 1024u, 512u);
+            for (int t = 0; t < 2; ++t) {
+              if (2 * p + t >= pass_tiles) break;
+              const uint64_t dah = desc_mn_sw128_32b(smem_u32(sb) + (uint32_t)t * 4096u, 1024u, 512u);
+              const uint64_t dal = desc_mn_sw128_32b(smem_u32(sb) + 8192u + (uint32_t)t * 4096u, 1024u, 512u);
+              const uint32_t acc = tmem + (uint32_t)((2 * p + t) * s1n);
+              umma_tf32(acc, dal, dbh, idesc, g ? 1u : 0u);
+              umma_tf32(acc, dah, dbl, idesc, 1u);
+              umma_tf32(acc, dah, dbh, idesc, 1u);
+            }
+            tc_commit(&ms.bar[st]);
+          }
+        }
+        ms.rparity[0] = rp[0]; ms.rparity[1] = rp[1];
+      }
+      return;
+    }
+#endif
+    uint32_t par[2] = {ms.parity[0], ms.parity[1]};
 
     // loader mapping for one unit = 8 batch rows x 256 columns: row tid >> 6, 16-byte chunk tid & 63
     const int lr = tid >> 6, c4 = tid & 63;
@@ -409,9 +496,16 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         *reinterpret_cast<float4*>(sb + soff) = hi;
         *reinterpret_cast<float4*>(sb + 8192 + soff) = lo;
         fence_proxy_async();                                   // before the next load is issued (the fence would wait for it)
+#if SG_MLP_ISSUER_WARP
+        tc_fence_before();
+        mbar_arrive(&ms.ready[st]);
+        if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
+        if (false) {
+#else
         mlptc::worker_sync();
         if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
         if (tid == 0) {
+#endif
           tc_fence_after();
           const int g = u / npp, p = u - g * npp;
           const uint64_t dbh = desc_mn_sw128_32b(smem_u32(bhi) + (uint32_t)g * 4096u, 1024u, 512u);
@@ -493,6 +587,13 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     const int R = plan.rows;
     uint8_t* region = base;
     uint8_t* xs = base + plan.region_bytes;
+#if SG_MLP_ISSUER_WARP
+    if (tid >= MLP_THREADS) {                         // the issuer warp only takes part in the two tensor-core phases
+      layer1_forward(m, ms, region, th, nb, R, nullptr, 0);
+      layer1_backward(m, ms, region, xs, sign, nb, R, g + m.leaf_off[0], overwrite);
+      return;
+    }
+#endif
     float* fbase = reinterpret_cast<float*>(xs + plan.xs_bytes);
     auto act = [&](int l) { return fbase + plan.act_off(l); };
     auto astr = [&](int l) { return mlp_stride(sz[l]); };
@@ -686,7 +787,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
   __device__ static void lik_pass(const BigModel& m, void* fam_smem, const float* theta, const float* center,
                                   bool sequential, const RandintPlan& plan, unsigned seq_base, unsigned count, float* g,
                                   bool fresh, const NoiseJob& job, float* lp = nullptr, bool /*compact*/ = false) {
-    if (threadIdx.x >= MLP_THREADS) {
+    if (!SG_MLP_ISSUER_WARP && threadIdx.x >= MLP_THREADS) {
       // noise-producer warps: the Gaussian draws of the NEXT diffusion update (its key tree is data independent,
       // diffusion_util.py:66), generated while the worker warps run the GEMM phase; the caller's __syncthreads() after
       // the pass publishes them
@@ -703,6 +804,16 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(&ms + 1) + 1023) & ~(uintptr_t)1023);
     const unsigned rows = (unsigned)mlp_plan(m.dims, m.batch).rows;
     const unsigned h = (count + 1u) >> 1;
+#if SG_MLP_ISSUER_WARP
+    if (threadIdx.x >= MLP_THREADS) {                 // issuer warp: same sub-batch sequence, tensor-core phases only
+      for (unsigned base_row = 0; base_row < count; base_row += rows) {
+        const int nb = (int)min(rows, count - base_row);
+        sub_batch(m, ms, base, theta, 1.0f, nb, g, fresh && base_row == 0, nullptr);
+        if (center) sub_batch(m, ms, base, center, -1.0f, nb, g, false, nullptr);
+      }
+      return;
+    }
+#endif
     for (unsigned base_row = 0; base_row < count; base_row += rows) {
       const int nb = (int)min(rows, count - base_row);
       mlptc::worker_sync();

@@ -119,3 +119,36 @@ def test_ess_of_an_ar1_process():
         want = c * k * (1 - rho) / (1 + rho)
         assert ess.shape == (2,)
         assert np.all(np.abs(ess / want - 1.0) < 0.2), (rho, ess, want)
+
+
+def test_dataset_loaders_read_the_standard_formats(tmp_path):
+    """sgmcmcjax_b200.datasets: MNIST IDX files -> the arrays NN_data.py:26-42 builds; MovieLens
+    u.data -> 0-based PMF data."""
+    import gzip
+    import struct
+
+    from sgmcmcjax_b200 import datasets as D
+
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(7, 28, 28), dtype=np.uint8)
+    lab = rng.integers(0, 10, size=7, dtype=np.uint8)
+    pi, pl = tmp_path / "img-idx3-ubyte.gz", tmp_path / "lab-idx1-ubyte"
+    with gzip.open(pi, "wb") as f:
+        f.write(struct.pack(">HBBIII", 0, 0x08, 3, 7, 28, 28) + img.tobytes())
+    with open(pl, "wb") as f:
+        f.write(struct.pack(">HBBI", 0, 0x08, 1, 7) + lab.tobytes())
+    X, y = D.load_mnist_idx(str(pi), str(pl))
+    assert X.dtype == np.float32 and X.shape == (7, 784) and y.shape == (7, 10) and y.dtype == np.float32
+    np.testing.assert_array_equal(X, img.reshape(7, -1).astype(np.float32) / np.float32(255.0))
+    assert (y.argmax(1) == lab).all() and (y.sum(1) == 1).all()
+    with pytest.raises(ValueError):
+        D.one_hot([3, 10], 10)
+
+    pu = tmp_path / "u.data"
+    pu.write_text("1\t5\t3\t881250949\n3\t2\t5\t891717742\n2\t5\t1\t878887116\n")
+    (ij, r), (nu, ni) = D.load_movielens_100k(str(pu))
+    assert ij.dtype == np.int32 and ij.tolist() == [[0, 4], [2, 1], [1, 4]] and r.tolist() == [3.0, 5.0, 1.0]
+    assert (nu, ni) == (3, 5)
+    pu.write_text("0\t5\t3\t1\n")
+    with pytest.raises(ValueError):
+        D.load_movielens_100k(str(pu))
