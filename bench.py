@@ -587,7 +587,9 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="skip the 1024-chains-per-GPU context run at N > 1")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--inner", type=int, default=10, help="chain-steps per launch (= per bench step)")
-    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--e2e-steps", type=int, default=200,
+                    help="Nsamples of the end-to-end sampler(key, Nsamples, params) call (its init_fn, launch and copy "
+                         "set-up costs are inside the timed region and amortise over these steps)")
     ap.add_argument("--ksd-n", type=int, default=KSD_N)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of host work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
