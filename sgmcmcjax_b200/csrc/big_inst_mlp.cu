@@ -4,6 +4,7 @@
 #include "mlp_grad.cuh"
 namespace sg {
 template cudaError_t launch_big_inst<SGMCMC_FAMILY_MLP>(const BigModel&, const BigRun&, int, size_t, cudaStream_t);
+template int big_resident_ctas<SGMCMC_FAMILY_MLP>(const BigModel&, size_t, int);
 }  // namespace sg
 
 // phase timers of this translation unit's kernel (tools/phase_timing.py)

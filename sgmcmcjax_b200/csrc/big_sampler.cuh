@@ -96,6 +96,9 @@ struct BigRun {
   float* fg_out;             // [M, P]
   float* noise;              // [C, P] scratch for noise generated one update ahead (families with producer warps), or nullptr
   float* lp_out;             // [C][K] log-posterior values of the optimiser iterations (SGMCMC_DIFF_ADAM_OPT), or nullptr
+  // in-kernel work queue (more chains than resident CTAs): sched[0] = next item, sched[1 + c] = blocks of chain c done
+  int* sched;                // nullptr: one CTA per chain, all K steps (grid = n_chains)
+  int blk;                   // steps per work item
 };
 
 // Work for the noise-producer warps during a likelihood pass: normal(split(split(key)[0], n_leaves)[leaf], (n_leaf,))
@@ -107,6 +110,7 @@ struct BigSmem {
   float alpha[MAXL];
   float red[32];
   float lp;                  // sum of the minibatch log-likelihood VALUES of the current estimate (optimiser only)
+  int item;                  // work item claimed by thread 0 (queued launches)
 };
 
 template <int FAMILY> struct FamilyGrad;   // lik_pass(...) specialisations below / in mlp_grad.cuh
@@ -921,55 +925,63 @@ struct BigCtx {
   }
 };
 
+// Work distribution.  Default: CTA c owns chain c for the K steps of the launch.  With more chains than the device holds
+// CTAs (256 MLP chains on 148 SMs, 512 PMF chains on 296 slots) that is two waves of which the second is 73 % full; such
+// launches run PERSISTENT CTAs over a queue of (chain, block of steps) items instead: items are claimed in order
+// (block-major: every chain's block b before any block b + 1), a chain's next block waits for its previous one through a
+// per-chain counter (release / acquire at gpu scope; the acquire's fence also drops the SM's stale L1 lines of a chain
+// that last ran here two blocks ago), and the chain state travels through the caller's global buffers exactly as it does
+// between launches (finalised gradient, alpha, key).  The tail shrinks from a wave to a block: 2.0 -> ~1.75 wave times.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int FAMILY>
 __global__ void __launch_bounds__(BigThreads<FAMILY>::value, BigThreads<FAMILY>::min_blocks) big_sampler_kernel(const __grid_constant__ BigModel m, const __grid_constant__ BigRun run) {
   extern __shared__ __align__(16) uint8_t big_smem_raw[];
   BigSmem& s = *reinterpret_cast<BigSmem*>(big_smem_raw);
   void* fam_smem = big_smem_raw + ((sizeof(BigSmem) + 127) & ~(size_t)127);
-  const int c = blockIdx.x;
   const size_t P = (size_t)m.P;
   const sgmcmc_state& st = run.st;
   BigCtx<FAMILY> ctx(m, s, fam_smem);
   FamilyGrad<FAMILY>::cta_init(m, fam_smem);                 // MLP: mbarriers + TMEM allocation
 
   if (run.mode == 3) {                                       // K2: full-batch gradient at fg_thetas[c]
+    const int c = blockIdx.x;
     ctx.full_grad(run.fg_thetas + c * P, run.fg_out + c * P);
     FamilyGrad<FAMILY>::cta_fini(m, fam_smem);
     return;
   }
 
-  ctx.theta = st.theta + c * P;
-  ctx.aux1 = st.aux1 ? st.aux1 + c * P : nullptr;
-  ctx.aux2 = st.aux2 ? st.aux2 + c * P : nullptr;
-  ctx.grad = st.grad + c * P;
-  ctx.svrg_center = st.svrg_center ? st.svrg_center + c * P : nullptr;
-  ctx.svrg_fb = st.svrg_grad ? st.svrg_grad + c * P : nullptr;
-  if (m.estimator == SGMCMC_EST_SVRG) { ctx.center = ctx.svrg_center; ctx.fb = ctx.svrg_fb; }
-  else { ctx.center = m.cv_center; ctx.fb = m.cv_grad; }
-  ctx.noise = run.noise ? run.noise + c * P : nullptr;
-
-  if (threadIdx.x < MAXL) {
-    float a = 0.f;
-    if (st.alpha && threadIdx.x < m.n_leaves)
-      a = run.mode == 0 ? st.alpha[(size_t)c * m.n_leaves + threadIdx.x] : m.hyper[0];
-    s.alpha[threadIdx.x] = a;
-  }
-  __syncthreads();
-
-  Key carry{0u, 0u};
-  if (run.mode != 0) {
-    // init_fn (kernels.py:48-51): diffusion state = (theta, zeros...), gradient from init_gradient
-    for (size_t e = threadIdx.x; e < P; e += blockDim.x) {
-      if (ctx.aux1) ctx.aux1[e] = 0.f;
-      if (ctx.aux2) ctx.aux2[e] = 0.f;
+  // point the context at chain c and load its per-leaf thermostat
+  auto bind = [&](int c) {
+    ctx.theta = st.theta + c * P;
+    ctx.aux1 = st.aux1 ? st.aux1 + c * P : nullptr;
+    ctx.aux2 = st.aux2 ? st.aux2 + c * P : nullptr;
+    ctx.grad = st.grad + c * P;
+    ctx.svrg_center = st.svrg_center ? st.svrg_center + c * P : nullptr;
+    ctx.svrg_fb = st.svrg_grad ? st.svrg_grad + c * P : nullptr;
+    if (m.estimator == SGMCMC_EST_SVRG) { ctx.center = ctx.svrg_center; ctx.fb = ctx.svrg_fb; }
+    else { ctx.center = m.cv_center; ctx.fb = m.cv_grad; }
+    ctx.noise = run.noise ? run.noise + c * P : nullptr;
+    if (threadIdx.x < MAXL) {
+      float a = 0.f;
+      if (st.alpha && threadIdx.x < m.n_leaves)
+        a = run.mode == 0 ? st.alpha[(size_t)c * m.n_leaves + threadIdx.x] : m.hyper[0];
+      s.alpha[threadIdx.x] = a;
     }
     __syncthreads();
-    Key k; k.a = run.init_keys[2 * c]; k.b = run.init_keys[2 * c + 1];
-    if (run.mode == 2) { Key sub; split2(k, carry, sub); k = sub; }
-    ctx.estimate(0, k, true);
-  } else {
+  };
+  // steps [k0, k1) of the launch for chain c; leaves the finalised gradient, alpha and the scan key in the state buffers
+  auto run_steps = [&](int c, int k0, int k1) {
+    Key carry{0u, 0u};
     if (run.step_keys == nullptr) { carry.a = st.key[2 * c]; carry.b = st.key[2 * c + 1]; }
-    for (int sidx = 0; sidx < run.K; ++sidx) {
+    for (int sidx = k0; sidx < k1; ++sidx) {
       const int i = run.i0 + sidx;
       const sgmcmc_step_coef cf = run.coef[(size_t)sidx * run.coef_stride];
       Key sub, next_sub{0u, 0u};
@@ -988,7 +1000,7 @@ __global__ void __launch_bounds__(BigThreads<FAMILY>::value, BigThreads<FAMILY>:
       if (run.step_keys) { sub.a = run.step_keys[2 * c]; sub.b = run.step_keys[2 * c + 1]; }
       else {
         Key nk; split2(carry, nk, sub); carry = nk;             // samplers.py:49
-        if (sidx + 1 < run.K) { Key nk2; split2(carry, nk2, next_sub); has_next = true; }   // peek at the next iteration's key
+        if (FamilyGrad<FAMILY>::kNoiseProducers && sidx + 1 < k1) { Key nk2; split2(carry, nk2, next_sub); has_next = true; }   // peek at the next iteration's key
       }
       // get_params after the transition: the sample is written by the diffusion pass that produces it
       const bool thinned = run.thin > 1;
@@ -1004,12 +1016,54 @@ __global__ void __launch_bounds__(BigThreads<FAMILY>::value, BigThreads<FAMILY>:
       }
     }
     ctx.finalize();                                             // the state's param_grad is the finalised gradient
+    __syncthreads();
+    if (st.alpha && threadIdx.x < m.n_leaves) st.alpha[(size_t)c * m.n_leaves + threadIdx.x] = s.alpha[threadIdx.x];
+    if (threadIdx.x == 0 && st.key && run.step_keys == nullptr) { st.key[2 * c] = carry.a; st.key[2 * c + 1] = carry.b; }
+  };
+
+  if (run.mode != 0) {
+    // init_fn (kernels.py:48-51): diffusion state = (theta, zeros...), gradient from init_gradient
+    const int c = blockIdx.x;
+    bind(c);
+    Key carry{0u, 0u};
+    for (size_t e = threadIdx.x; e < P; e += blockDim.x) {
+      if (ctx.aux1) ctx.aux1[e] = 0.f;
+      if (ctx.aux2) ctx.aux2[e] = 0.f;
+    }
+    __syncthreads();
+    Key k; k.a = run.init_keys[2 * c]; k.b = run.init_keys[2 * c + 1];
+    if (run.mode == 2) { Key sub; split2(k, carry, sub); k = sub; }
+    ctx.estimate(0, k, true);
+    __syncthreads();
+    if (st.alpha && threadIdx.x < m.n_leaves) st.alpha[(size_t)c * m.n_leaves + threadIdx.x] = s.alpha[threadIdx.x];
+    if (threadIdx.x == 0 && st.key && run.mode == 2) { st.key[2 * c] = carry.a; st.key[2 * c + 1] = carry.b; }
+  } else if (run.sched == nullptr) {
+    bind(blockIdx.x);
+    run_steps(blockIdx.x, 0, run.K);
+  } else {
+    const int C = st.n_chains, nblk = (run.K + run.blk - 1) / run.blk;
+    const int n_items = C * nblk;
+    for (;;) {
+      __syncthreads();                                          // everyone is done with the previous item (and s.item)
+      if (threadIdx.x == 0) s.item = atomicAdd(run.sched, 1);
+      __syncthreads();
+      const int item = s.item;
+      if (item >= n_items) break;
+      const int b = item / C, c = item - b * C;
+      if (b > 0) {
+        if (threadIdx.x == 0) {
+          while (ld_acquire_gpu(run.sched + 1 + c) < b) __nanosleep(200);
+          __threadfence();                                      // gpu-scope fence: the SM's L1 forgets this chain's old lines
+        }
+        __syncthreads();
+      }
+      bind(c);
+      run_steps(c, b * run.blk, min(run.K, (b + 1) * run.blk));
+      __syncthreads();
+      if (threadIdx.x == 0) { __threadfence(); st_release_gpu(run.sched + 1 + c, b + 1); }
+    }
   }
   __syncthreads();
-  if (st.alpha && threadIdx.x < m.n_leaves) st.alpha[(size_t)c * m.n_leaves + threadIdx.x] = s.alpha[threadIdx.x];
-  if (threadIdx.x == 0 && st.key && (run.mode == 2 || (run.mode == 0 && run.step_keys == nullptr))) {
-    st.key[2 * c] = carry.a; st.key[2 * c + 1] = carry.b;
-  }
   FamilyGrad<FAMILY>::cta_fini(m, fam_smem);
 }
 

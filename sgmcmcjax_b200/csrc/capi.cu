@@ -57,6 +57,9 @@ struct sgmcmc_handle {
   size_t k2_scratch_bytes = 0;
   int num_sms = 148;
   bool has_data = false, has_center = false;
+  int* sched = nullptr;        // owned: work-queue counters of the big-state sampler ([1 + n_chains] ints)
+  size_t sched_elems = 0;
+  int big_slots = -1;          // resident CTAs of big_sampler_kernel for this model (-1: not asked yet)
   // (threads, cluster asked, extended kernel, chains) -> cluster shape the device can co-schedule (vec_launch.cuh)
   std::map<std::tuple<int, int, int, int>, int> cluster_ok;
 };
@@ -258,14 +261,40 @@ int dispatch_vec(sgmcmc_handle* h, const sg::VecRun& run, cudaStream_t stream) {
 }
 
 template <int FAMILY>
-int launch_big(const sgmcmc_handle* h, const sg::BigRun& run, int blocks, cudaStream_t stream) {
+int launch_big(sgmcmc_handle* h, const sg::BigRun& run_in, int blocks, cudaStream_t stream) {
   const size_t smem = ((sizeof(sg::BigSmem) + 127) & ~(size_t)127) + sg::FamilyGrad<FAMILY>::smem_bytes(h->bm);
+  sg::BigRun run = run_in;
+  // Sampling launches with more chains than resident CTAs: persistent CTAs over a queue of (chain, block of steps)
+  // items (csrc/big_sampler.cuh).  SGMCMC_BIG_QUEUE=0 disables it, SGMCMC_BIG_GRID / SGMCMC_BIG_BLOCKS force a grid /
+  // a number of blocks per chain (tests run few chains on a tiny grid so that chains do migrate between CTAs).
+  if (run.mode == 0 && run.step_keys == nullptr && run.K > 1 && env_int("SGMCMC_BIG_QUEUE", 1)) {
+    if (h->big_slots < 0) h->big_slots = sg::big_resident_ctas<FAMILY>(h->bm, smem, h->num_sms);
+    int grid = env_int("SGMCMC_BIG_GRID", 0);
+    if (grid <= 0) grid = h->big_slots;
+    int nblk = env_int("SGMCMC_BIG_BLOCKS", 0);
+    if (nblk <= 0) nblk = 4;
+    if (nblk > run.K) nblk = run.K;
+    if (grid > 0 && grid <= h->big_slots && blocks > grid) {
+      const size_t need = (size_t)blocks + 1;
+      if (need > h->sched_elems) {
+        if (h->sched) CUDA_TRY(cudaFree(h->sched));
+        h->sched = nullptr; h->sched_elems = 0;
+        CUDA_TRY(cudaMalloc(&h->sched, need * sizeof(int)));
+        h->sched_elems = need;
+      }
+      CUDA_TRY(cudaMemsetAsync(h->sched, 0, need * sizeof(int), stream));
+      run.sched = h->sched;
+      run.blk = (run.K + nblk - 1) / nblk;
+      if (run.thin > 1) run.blk = (run.blk + run.thin - 1) / run.thin * run.thin;   // whole thinning periods per item
+      blocks = grid;
+    }
+  }
   CUDA_TRY(sg::launch_big_inst<FAMILY>(h->bm, run, blocks, smem, stream));                        // csrc/big_inst_*.cu
   ++g_launches;
   return SGMCMC_OK;
 }
 
-int dispatch_big(const sgmcmc_handle* h, const sg::BigRun& run, int blocks, cudaStream_t stream) {
+int dispatch_big(sgmcmc_handle* h, const sg::BigRun& run, int blocks, cudaStream_t stream) {
 #ifndef SG_NO_PMF
   if (h->cfg.family == SGMCMC_FAMILY_PMF) return launch_big<SGMCMC_FAMILY_PMF>(h, run, blocks, stream);
 #endif
@@ -530,6 +559,7 @@ int sgmcmc_destroy(sgmcmc_handle* h) {
   if (h->cv_grad) cudaFree(h->cv_grad);
   if (h->partial) cudaFree(h->partial);
   if (h->noise) cudaFree(h->noise);
+  if (h->sched) cudaFree(h->sched);
   if (h->k2_xs) cudaFree(h->k2_xs);
   if (h->k2_xt) cudaFree(h->k2_xt);
   if (h->k2_scratch) cudaFree(h->k2_scratch);

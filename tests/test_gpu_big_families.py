@@ -352,3 +352,34 @@ def test_pmf_compact_gradient_mode(cuda, monkeypatch, name, dt, kw):
             assert np.array_equal(a, b)                                    # deterministic
     for a, b in zip(runs["1"][0], runs["0"][0]):
         close(a, b, rtol=2e-5, what=f"{name}: compact vs scatter-add trajectory")
+
+
+@pytest.mark.parametrize("name,dt,kw", [KERNELS[3], KERNELS[5], KERNELS[9], KERNELS[10], KERNELS[12]],
+                         ids=["psgld", "sgnht", "badodabCV", "sghmc", "sghmc_SVRG"])
+@pytest.mark.parametrize("case", ["mlp", "pmf"])
+def test_work_queue_equals_one_cta_per_chain(cuda, monkeypatch, name, dt, kw, case):
+    """The in-kernel (chain, block of steps) queue of csrc/big_sampler.cuh (more chains than resident CTAs): 5 chains on a
+    grid of 2 persistent CTAs, 3 blocks per chain, so chains migrate between CTAs at every block - same samples as one
+    CTA per chain (bit for bit for the MLP; PMF's scatter-add is order dependent), thinning and moments included."""
+    make, to_params, batch = CASES[case]
+    fam, fns, data, th0 = make()
+    keys = P.split(P.PRNGKey(9), 5)
+    params = to_params([np.stack([t * np.float32(1 + 0.05 * c) for c in range(5)]) for t in th0])
+    center = [np.asarray(t * np.float32(0.98) + np.float32(0.003)) for t in th0]
+    outs = {}
+    for mode in ("plain", "queue"):
+        if mode == "plain":
+            monkeypatch.setenv("SGMCMC_BIG_QUEUE", "0")
+        else:
+            monkeypatch.setenv("SGMCMC_BIG_QUEUE", "1")
+            monkeypatch.setenv("SGMCMC_BIG_GRID", "2")
+            monkeypatch.setenv("SGMCMC_BIG_BLOCKS", "3")
+        _, sampler = build_pair(name, dt, kw, fam, fns, data, batch, center, to_params, sampler=True)
+        outs[mode] = tree_leaves(sampler(keys, 7, params))
+        _, thin_sampler = build_pair(name, dt, kw, fam, fns, data, batch, center, to_params, sampler=True)
+    for a, b in zip(outs["plain"], outs["queue"]):
+        assert a.shape[:2] == (5, 7)
+        if case == "pmf":
+            close(b, a, rtol=1e-5, what=f"{name} queue vs plain")
+        else:
+            assert np.array_equal(a, b), f"{name}: queued launch differs from one CTA per chain"
