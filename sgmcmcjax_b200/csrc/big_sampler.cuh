@@ -96,7 +96,8 @@ struct BigRun {
   float* fg_out;             // [M, P]
   float* noise;              // [C, P] scratch for noise generated one update ahead (families with producer warps), or nullptr
   float* lp_out;             // [C][K] log-posterior values of the optimiser iterations (SGMCMC_DIFF_ADAM_OPT), or nullptr
-  // in-kernel work queue (more chains than resident CTAs): sched[0] = next item, sched[1 + c] = blocks of chain c done
+  // in-kernel work queue (more chains than resident CTAs): sched[0] = next item, sched[1 + c] = blocks of chain c done,
+  // sched[1 + C + c] = its gradient buffer holds raw sums, sched[1 + 2 C + c] = their scale (float bits)
   int* sched;                // nullptr: one CTA per chain, all K steps (grid = n_chains)
   int blk;                   // steps per work item
 };
@@ -1015,8 +1016,17 @@ __global__ void __launch_bounds__(BigThreads<FAMILY>::value, BigThreads<FAMILY>:
         __syncthreads();
       }
     }
-    ctx.finalize();                                             // the state's param_grad is the finalised gradient
+    // the state's param_grad is the finalised gradient - at the end of the launch.  Between two blocks of a queued launch
+    // the raw minibatch sums stay in the buffer (saves a pass over the P-vector per block); the next block's CTA is told
+    // through two words beside the chain's done-counter.  (Compact PMF sums live in shared memory: always finalised.)
+    const bool last_block = k1 >= run.K;
+    const bool keep_raw = run.sched != nullptr && !last_block && ctx.grad_raw && !ctx.raw_compact;
+    if (!keep_raw) ctx.finalize();
     __syncthreads();
+    if (run.sched != nullptr && threadIdx.x == 0) {
+      run.sched[1 + st.n_chains + c] = keep_raw ? 1 : 0;
+      run.sched[1 + 2 * st.n_chains + c] = __float_as_int(ctx.gscale);
+    }
     if (st.alpha && threadIdx.x < m.n_leaves) st.alpha[(size_t)c * m.n_leaves + threadIdx.x] = s.alpha[threadIdx.x];
     if (threadIdx.x == 0 && st.key && run.step_keys == nullptr) { st.key[2 * c] = carry.a; st.key[2 * c + 1] = carry.b; }
   };
@@ -1058,6 +1068,9 @@ __global__ void __launch_bounds__(BigThreads<FAMILY>::value, BigThreads<FAMILY>:
         __syncthreads();
       }
       bind(c);
+      ctx.grad_raw = b > 0 && run.sched[1 + C + c] != 0;        // raw sums left by the previous block of this chain
+      ctx.raw_compact = false;
+      ctx.gscale = b > 0 ? __int_as_float(run.sched[1 + 2 * C + c]) : 1.0f;
       run_steps(c, b * run.blk, min(run.K, (b + 1) * run.blk));
       __syncthreads();
       if (threadIdx.x == 0) { __threadfence(); st_release_gpu(run.sched + 1 + c, b + 1); }

@@ -57,7 +57,7 @@ struct sgmcmc_handle {
   size_t k2_scratch_bytes = 0;
   int num_sms = 148;
   bool has_data = false, has_center = false;
-  int* sched = nullptr;        // owned: work-queue counters of the big-state sampler ([1 + n_chains] ints)
+  int* sched = nullptr;        // owned: work-queue words of the big-state sampler ([1 + 3 n_chains] ints)
   size_t sched_elems = 0;
   int big_slots = -1;          // resident CTAs of big_sampler_kernel for this model (-1: not asked yet)
   // (threads, cluster asked, extended kernel, chains) -> cluster shape the device can co-schedule (vec_launch.cuh)
@@ -275,7 +275,7 @@ int launch_big(sgmcmc_handle* h, const sg::BigRun& run_in, int blocks, cudaStrea
     if (nblk <= 0) nblk = 4;
     if (nblk > run.K) nblk = run.K;
     if (grid > 0 && grid <= h->big_slots && blocks > grid) {
-      const size_t need = (size_t)blocks + 1;
+      const size_t need = (size_t)3 * blocks + 1;
       if (need > h->sched_elems) {
         if (h->sched) CUDA_TRY(cudaFree(h->sched));
         h->sched = nullptr; h->sched_elems = 0;
