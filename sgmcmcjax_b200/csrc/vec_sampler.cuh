@@ -189,7 +189,7 @@ __device__ __forceinline__ float reduce8(const float (&p)[8], int lane) {
 // EXT = false is the lean instantiation of the plain samplers (the bench kernel); the row-sharded mode and the
 // optimiser's log-posterior values live in the EXT = true instantiation only (they cost registers in the hot loop:
 // measured +6 % on the C2 step when they shared one kernel).
-template <int FAMILY, int CV, int NCH, bool EXT = false>
+template <int FAMILY, int CV, int NCH, bool EXT = false, bool LAT = false>
 __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, const RandintPlan& plan,
                                          unsigned seq_base, unsigned count, const float* s_theta, const float* s_center,
                                          float* s_part, float* lp_part_in = nullptr, const int* s_idx = nullptr) {
@@ -225,7 +225,7 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
   for (unsigned b0 = gwarp * lpw; b0 < h; b0 += W * lpw) {
     const unsigned b = b0 + lane;
     int jA = -1, jB = -1;
-    if (!EXT && s_idx) {                                   // drawn ahead in the cluster barrier's shadow (ChainCtx::shadow)
+    if (LAT && s_idx) {                                    // drawn ahead in the cluster barrier's shadow (ChainCtx::shadow)
       jA = s_idx[warp * 64 + lane]; jB = s_idx[warp * 64 + 32 + lane];
     } else if ((unsigned)lane < lpw && b < h) {
       unsigned iA, iB;
@@ -457,7 +457,9 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // ---------------------------------------------------------------------------------------
-template <int FAMILY, int CV, int NCH, bool EXT = false>
+// LAT = true: the latency-oriented instantiation launched for clusters (few chains): it carries shadow() - the next
+// step's keys, noise and indices prepared under the cluster barrier; the many-chain kernels stay lean (LAT = false).
+template <int FAMILY, int CV, int NCH, bool EXT = false, bool LAT = false>
 struct ChainCtx {
   const VecModel& m;
   Smem s;
@@ -517,7 +519,9 @@ struct ChainCtx {
       fold_parts(s, m.DS, buf, EXT && want_lp);
       return;
     }
-    if (plan_cached) {                                   // split(k2) was taken next to the leaf keys
+    if (LAT && ahead) {
+      // indices drawn one step ahead: no plan needed
+    } else if (plan_cached) {                            // split(k2) was taken next to the leaf keys
       plan.k_hi.a = s.keys[KEY_PLAN]; plan.k_hi.b = s.keys[KEY_PLAN + 1];
       plan.k_lo.a = s.keys[KEY_PLAN + 2]; plan.k_lo.b = s.keys[KEY_PLAN + 3];
       plan.span = m.n_data; plan.batch = m.batch; plan.mult = m.randint_mult;
@@ -526,12 +530,12 @@ struct ChainCtx {
       plan = randint_plan(k2, m.n_data, m.batch);
     }
     SG_TB(3, t_ps);
-    const bool use_idx = !EXT && ahead;                  // the indices of this estimate were drawn one step ahead
+    const bool use_idx = LAT && ahead;                   // the indices of this estimate were drawn one step ahead
     ahead = false;
-    row_pass<FAMILY, CV, NCH, EXT>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part, want_lp ? s.red : nullptr,
-                                   use_idx ? s.idx : nullptr);
+    row_pass<FAMILY, CV, NCH, EXT, LAT>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part, want_lp ? s.red : nullptr,
+                                        use_idx ? s.idx : nullptr);
     SG_TB(4, t_ps);
-    if (!EXT && next_slot >= 0 && cluster_size() > 1) {
+    if (LAT && next_slot >= 0 && cluster_size() > 1) {
       fold_parts(s, m.DS, buf, false, [this]() { shadow(); });
     } else {
       fold_parts(s, m.DS, buf, EXT && want_lp);
@@ -673,7 +677,7 @@ struct ChainCtx {
 
   // N(0,1) draw of element e = (leaf, d): generated here, or taken from the draws shadow() made one step ahead
   __device__ __forceinline__ float noise(Key lk, int e, int d, int D) const {
-    return xi_ready ? s.xi[e] : normal_at(lk, d, D);
+    return (LAT && xi_ready) ? s.xi[e] : normal_at(lk, d, D);
   }
 
   // diffusion update, phase 1 = `update` (before the new gradient), phase 2 = `update2`
@@ -787,8 +791,8 @@ struct ChainCtx {
   // langevin kernel, kernels.py:53-64
   __device__ void langevin(int i, Key key, const sgmcmc_step_coef& cf) {
     SG_TA(t_l);
-    xi_ready = ahead;                                    // shadow() of the previous step prepared this one
-    if (!ahead) expand_step_keys(key);
+    xi_ready = LAT && ahead;                             // shadow() of the previous step prepared this one
+    if (!(LAT && ahead)) expand_step_keys(key); else look_slot = -1;   // shadow() already split the next carry
     SG_TB(1, t_l);
     Key k2; k2.a = s.keys[2]; k2.b = s.keys[3];
     diffuse(1, i, cf, 4);
@@ -815,7 +819,7 @@ struct ChainCtx {
   }
 };
 
-template <int FAMILY, int CV, int NCH, bool EXT = false>
+template <int FAMILY, int CV, int NCH, bool EXT = false, bool LAT = false>
 __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel m, const VecRun run) {
   extern __shared__ __align__(16) float smem_raw[];
   const int W = blockDim.x >> 5;
@@ -848,7 +852,7 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
   }
   __syncthreads();
 
-  ChainCtx<FAMILY, CV, NCH, EXT> ctx(m, s);
+  ChainCtx<FAMILY, CV, NCH, EXT, LAT> ctx(m, s);
   Key carry{0u, 0u};
 
   if (EXT && run.sum_in) {                            // finish the previous estimate from the all-reduced sums
@@ -894,8 +898,11 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
       }
       else { Key nk; split2(carry, nk, sub); carry = nk; }      // samplers.py:49 / optimizer.py:46
       have_next = false;
+      ctx.next_slot = -1;
       if (run.step_keys == nullptr && sidx + 1 < run.K && !(EXT && m.diffusion == SGMCMC_DIFF_ADAM_OPT)) {
         ctx.look_slot = (sidx + 1) & 1; ctx.look_carry = carry; have_next = true;
+        // cluster launches: the next langevin step is prepared in the shadow of this step's cluster barrier
+        if (LAT && cs > 1 && m.diffusion != SGMCMC_DIFF_SGHMC) ctx.next_slot = (sidx + 1) & 1;
       }
       SG_TB(0, t_s);
       if (EXT && m.diffusion == SGMCMC_DIFF_ADAM_OPT) {
