@@ -187,14 +187,8 @@ int launch_vec_kernel(sgmcmc_handle* h, const sg::VecRun& run, VecShape shape, c
   const auto key = std::make_tuple(shape.warps * 32, shape.cluster, EXT ? 1 : 0, run.st.n_chains);
   const auto hit = h->cluster_ok.find(key);
   int used = hit != h->cluster_ok.end() ? hit->second : shape.cluster;
-  // clusters of the plain samplers at D <= 128 run the latency instantiation (next step prepared under the cluster barrier)
-  if (NCH == 1 && !EXT && used > 1 && !env_int("SGMCMC_NO_LOOKAHEAD", 0)) {
-    CUDA_TRY((sg::launch_vec_inst<FAMILY, CV, 1, false, true>(h->vm, run, shape.warps * 32, used, smem, stream,
-                                                              hit == h->cluster_ok.end(), &used)));
-  } else {
-    CUDA_TRY((sg::launch_vec_inst<FAMILY, CV, NCH, EXT>(h->vm, run, shape.warps * 32, used, smem, stream,   // csrc/vec_inst_*.cu
-                                                        hit == h->cluster_ok.end(), &used)));
-  }
+  CUDA_TRY((sg::launch_vec_inst<FAMILY, CV, NCH, EXT>(h->vm, run, shape.warps * 32, used, smem, stream,   // csrc/vec_inst_*.cu
+                                                      hit == h->cluster_ok.end(), &used)));
   h->cluster_ok[key] = used;
   ++g_launches;
   return SGMCMC_OK;

@@ -9,15 +9,15 @@ namespace sg {
 // with one cluster of `cluster` CTAs (1, 2, 4, 8 or 16) of `threads` threads per chain.  A cluster shape the device
 // cannot co-schedule for all chains at once is shrunk until it can (validate = true: asks cudaOccupancyMaxActiveClusters first; the caller
 // caches the answer, *cluster_used, and passes validate = false from then on).
-template <int FAMILY, int CV, int NCH, bool EXT, bool LAT = false>
+template <int FAMILY, int CV, int NCH, bool EXT>
 cudaError_t launch_vec_inst(const VecModel& m, const VecRun& run, int threads, int cluster, size_t smem, cudaStream_t stream,
                             bool validate, int* cluster_used);
 
 #ifdef SG_VEC_LAUNCH_IMPL
-template <int FAMILY, int CV, int NCH, bool EXT, bool LAT>
+template <int FAMILY, int CV, int NCH, bool EXT>
 cudaError_t launch_vec_inst(const VecModel& m, const VecRun& run, int threads, int cluster, size_t smem, cudaStream_t stream,
                             bool validate, int* cluster_used) {
-  auto kern = vec_sampler_kernel<FAMILY, CV, NCH, EXT, LAT>;
+  auto kern = vec_sampler_kernel<FAMILY, CV, NCH, EXT>;
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -55,7 +55,6 @@ cudaError_t launch_vec_inst(const VecModel& m, const VecRun& run, int threads, i
   return cudaLaunchKernelEx(&cfg, kern, m, run);
 }
 #define SG_VEC_INSTANTIATE(FAMILY, CV)                                                                              \
-  template cudaError_t launch_vec_inst<FAMILY, CV, 1, false, true>(const VecModel&, const VecRun&, int, int, size_t, cudaStream_t, bool, int*); \
   template cudaError_t launch_vec_inst<FAMILY, CV, 1, false>(const VecModel&, const VecRun&, int, int, size_t, cudaStream_t, bool, int*); \
   template cudaError_t launch_vec_inst<FAMILY, CV, 1, true>(const VecModel&, const VecRun&, int, int, size_t, cudaStream_t, bool, int*);  \
   template cudaError_t launch_vec_inst<FAMILY, CV, 2, false>(const VecModel&, const VecRun&, int, int, size_t, cudaStream_t, bool, int*); \

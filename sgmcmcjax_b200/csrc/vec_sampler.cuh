@@ -83,8 +83,6 @@ constexpr int SHARD_UPDATE2 = 1, SHARD_STEP = 2;
 struct Smem {
   float *theta, *aux1, *aux2, *grad, *center, *fb, *S, *part;
   float* recv;        // [2][cs][DS + 4]: folded partial sums (+ log-likelihood value term) PUSHED here by every CTA of the cluster
-  float* xi;          // [PP]: N(0,1) draws of the NEXT diffusion update, generated in the cluster barrier's shadow (cs > 1)
-  int* idx;           // [W][64]: this CTA's minibatch rows of the NEXT estimate (lanes' jA | jB), same shadow
   float* alpha;       // [MAXL]
   float* red;         // [32] block-reduction scratch
   uint32_t* keys;     // [2 * (4 + 2*MAXL)] step keys
@@ -101,8 +99,6 @@ __device__ __forceinline__ Smem carve(float* base, int PP, int DS, int W, int cs
   s.S = base;                base += DS + 4;     // [DS] sums, [DS] = log-likelihood value term (optimiser)
   s.part = base;             base += W * DS;
   s.recv = base;             base += cs > 1 ? 2 * cs * (DS + 4) : 0;
-  s.xi = base;               base += cs > 1 ? PP : 0;
-  s.idx = reinterpret_cast<int*>(base);   base += cs > 1 ? W * 64 : 0;
   s.alpha = base;            base += MAXL;
   s.red = base;              base += 32;
   s.keys = reinterpret_cast<uint32_t*>(base);
@@ -114,7 +110,7 @@ constexpr int SMEM_KEY_WORDS = 2 * (4 + 2 * MAXL);
 constexpr int KEY_PLAN = 4 + 2 * MAXL, KEY_NEXT = KEY_PLAN + 4;
 static_assert(KEY_NEXT + 8 <= SMEM_KEY_WORDS, "key slots");
 __host__ __device__ inline size_t vec_smem_bytes(int PP, int DS, int W, int cs) {
-  return sizeof(float) * (size_t)(6 * PP + (DS + 4) + W * DS + (cs > 1 ? 2 * cs * (DS + 4) + PP + W * 64 : 0) + MAXL + 32) +
+  return sizeof(float) * (size_t)(6 * PP + (DS + 4) + W * DS + (cs > 1 ? 2 * cs * (DS + 4) : 0) + MAXL + 32) +
          sizeof(uint32_t) * SMEM_KEY_WORDS;
 }
 
@@ -189,10 +185,10 @@ __device__ __forceinline__ float reduce8(const float (&p)[8], int lane) {
 // EXT = false is the lean instantiation of the plain samplers (the bench kernel); the row-sharded mode and the
 // optimiser's log-posterior values live in the EXT = true instantiation only (they cost registers in the hot loop:
 // measured +6 % on the C2 step when they shared one kernel).
-template <int FAMILY, int CV, int NCH, bool EXT = false, bool LAT = false>
+template <int FAMILY, int CV, int NCH, bool EXT = false>
 __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, const RandintPlan& plan,
                                          unsigned seq_base, unsigned count, const float* s_theta, const float* s_center,
-                                         float* s_part, float* lp_part_in = nullptr, const int* s_idx = nullptr) {
+                                         float* s_part, float* lp_part_in = nullptr) {
   float* lp_part = EXT ? lp_part_in : nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // the stream is dealt to the warps of the whole cluster: W = warps of all its CTAs, gwarp = this warp among them
@@ -225,9 +221,7 @@ __device__ __forceinline__ void row_pass(const VecModel& m, bool sequential, con
   for (unsigned b0 = gwarp * lpw; b0 < h; b0 += W * lpw) {
     const unsigned b = b0 + lane;
     int jA = -1, jB = -1;
-    if (LAT && s_idx) {                                    // drawn ahead in the cluster barrier's shadow (ChainCtx::shadow)
-      jA = s_idx[warp * 64 + lane]; jB = s_idx[warp * 64 + 32 + lane];
-    } else if ((unsigned)lane < lpw && b < h) {
+    if ((unsigned)lane < lpw && b < h) {
       unsigned iA, iB;
       if (sequential) { iA = seq_base + b; iB = seq_base + b + h; } else { randint_block(plan, b, iA, iB); }
       jA = (int)iA;
@@ -387,14 +381,7 @@ __global__ void zc_column_kernel(float* __restrict__ rows, unsigned n_rows, int 
 // part[W][DS] (+ red[W], the log-likelihood value terms, if with_lp) -> S[DS] (+ S[DS]); fixed summation order.
 // In a cluster: the local fold is pushed to recv[buf][rank] of every CTA, ONE cluster barrier, then every CTA adds
 // its recv[buf][0 .. cs) in rank order (see the header comment for why the double buffer makes one barrier enough).
-struct NoShadow { __device__ void operator()() const {} };
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-
-// `shadow` runs between the cluster barrier's arrive and its wait: state-independent work of the NEXT step (key tree,
-// noise, minibatch indices) that would otherwise sit on the step's critical path, done while the barrier resolves.
-template <class Shadow = NoShadow>
-__device__ __forceinline__ void fold_parts(const Smem& s, int DS, int& buf, bool with_lp = false, Shadow shadow = Shadow()) {
+__device__ __forceinline__ void fold_parts(const Smem& s, int DS, int& buf, bool with_lp = false) {
   const int W = blockDim.x >> 5;
   const unsigned cs = cluster_size();
   const int n = DS + (with_lp ? 1 : 0), stride = DS + 4;
@@ -418,9 +405,7 @@ __device__ __forceinline__ void fold_parts(const Smem& s, int DS, int& buf, bool
       for (unsigned r = 0; r < cs; ++r) cl.map_shared_rank(slot, r)[d] = t;
     }
     SG_TB(5, t_f);
-    cluster_arrive();
-    shadow();
-    cluster_wait();
+    cl.sync();
     SG_TB(6, t_f);
     const float* mine = s.recv + (size_t)buf * cs * stride;
     for (int d = threadIdx.x; d < n; d += blockDim.x) {
@@ -457,9 +442,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // ---------------------------------------------------------------------------------------
-// LAT = true: the latency-oriented instantiation launched for clusters (few chains): it carries shadow() - the next
-// step's keys, noise and indices prepared under the cluster barrier; the many-chain kernels stay lean (LAT = false).
-template <int FAMILY, int CV, int NCH, bool EXT = false, bool LAT = false>
+template <int FAMILY, int CV, int NCH, bool EXT = false>
 struct ChainCtx {
   const VecModel& m;
   Smem s;
@@ -467,10 +450,6 @@ struct ChainCtx {
   bool plan_cached = false; // keys[KEY_PLAN ..] hold split(k2) of the estimate about to run
   int look_slot = -1;       // >= 0: the next expand_step_keys also splits look_carry into keys[KEY_NEXT + 4 look_slot ..]
   Key look_carry{0u, 0u};
-  // cluster launches: work of the NEXT langevin step done in the shadow of this step's cluster barrier (shadow())
-  int next_slot = -1;       // >= 0: keys[KEY_NEXT + 4 next_slot ..] = (carry, sub) of the next sampler iteration
-  bool ahead = false;       // keys[0 ..], xi[] and idx[] already belong to the step that is starting
-  bool xi_ready = false;    // diffuse(): take the N(0,1) draws from xi[] instead of generating them
   __device__ ChainCtx(const VecModel& mm, const Smem& ss) : m(mm), s(ss) {}
 
   // full-batch gradient at s.theta into dst[] (sequential pass over every row)
@@ -519,9 +498,7 @@ struct ChainCtx {
       fold_parts(s, m.DS, buf, EXT && want_lp);
       return;
     }
-    if (LAT && ahead) {
-      // indices drawn one step ahead: no plan needed
-    } else if (plan_cached) {                            // split(k2) was taken next to the leaf keys
+    if (plan_cached) {                                   // split(k2) was taken next to the leaf keys
       plan.k_hi.a = s.keys[KEY_PLAN]; plan.k_hi.b = s.keys[KEY_PLAN + 1];
       plan.k_lo.a = s.keys[KEY_PLAN + 2]; plan.k_lo.b = s.keys[KEY_PLAN + 3];
       plan.span = m.n_data; plan.batch = m.batch; plan.mult = m.randint_mult;
@@ -530,54 +507,9 @@ struct ChainCtx {
       plan = randint_plan(k2, m.n_data, m.batch);
     }
     SG_TB(3, t_ps);
-    const bool use_idx = LAT && ahead;                   // the indices of this estimate were drawn one step ahead
-    ahead = false;
-    row_pass<FAMILY, CV, NCH, EXT, LAT>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part, want_lp ? s.red : nullptr,
-                                        use_idx ? s.idx : nullptr);
+    row_pass<FAMILY, CV, NCH, EXT>(m, false, plan, 0u, m.batch, s.theta, s.center, s.part, want_lp ? s.red : nullptr);
     SG_TB(4, t_ps);
-    if (LAT && next_slot >= 0 && cluster_size() > 1) {
-      fold_parts(s, m.DS, buf, false, [this]() { shadow(); });
-    } else {
-      fold_parts(s, m.DS, buf, EXT && want_lp);
-    }
-  }
-
-  // Between the cluster barrier's arrive and wait of this estimate: everything of the NEXT langevin step that does not
-  // depend on the state - its key tree (k1, k2, leaf keys, randint plan, and the carry split of the step after), its
-  // Gaussian draws xi[P] and this CTA's share of its minibatch indices.  The next step then starts at the update itself.
-  __device__ void shadow() {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    const uint32_t* nx = s.keys + KEY_NEXT + 4 * next_slot;
-    Key ncarry; ncarry.a = nx[0]; ncarry.b = nx[1];
-    Key nsub; nsub.a = nx[2]; nsub.b = nx[3];
-    __syncthreads();                                     // every thread has read (carry, sub); keys[] of this step are dead
-    look_slot = next_slot ^ 1; look_carry = ncarry;      // the step after next: split its carry now
-    expand_step_keys(nsub);                              // -> keys[0..3], leaf keys, plan keys, KEY_NEXT other slot; barrier
-    const int D = m.leaf_dim;
-    for (int e = threadIdx.x; e < m.P; e += blockDim.x) {
-      const int leaf = e / D, d = e - leaf * D;
-      s.xi[e] = normal_at(leaf_key(4, leaf), d, D);
-    }
-    // this warp's blocks of the next index stream (row_pass geometry: one batch of lpw blocks per warp)
-    RandintPlan plan;
-    plan.k_hi.a = s.keys[KEY_PLAN]; plan.k_hi.b = s.keys[KEY_PLAN + 1];
-    plan.k_lo.a = s.keys[KEY_PLAN + 2]; plan.k_lo.b = s.keys[KEY_PLAN + 3];
-    plan.span = m.n_data; plan.batch = m.batch; plan.mult = m.randint_mult;
-    const unsigned GW = (unsigned)W * cluster_size(), gwarp = cluster_rank() * (unsigned)W + warp;
-    const unsigned h = (m.batch + 1u) >> 1;
-    const unsigned lpw = h < GW * 32u ? (h + GW - 1u) / GW : 32u;
-    const unsigned b = gwarp * lpw + lane;
-    int jA = -1, jB = -1;
-    if ((unsigned)lane < lpw && b < h) {
-      unsigned iA, iB;
-      randint_block(plan, b, iA, iB);
-      jA = (int)iA;
-      if (b + h < m.batch) jB = (int)iB;
-    }
-    s.idx[warp * 64 + lane] = jA; s.idx[warp * 64 + 32 + lane] = jB;
-    ahead = true;
-    plan_cached = false;
-    __syncthreads();
+    fold_parts(s, m.DS, buf, EXT && want_lp);
   }
 
   // log_post VALUE on the minibatch whose sums are in s.S (value term in s.S[DS]) (util.py:43-44: logprior + Ndata * mean_i loglik_i)
@@ -675,11 +607,6 @@ struct ChainCtx {
     __syncthreads();
   }
 
-  // N(0,1) draw of element e = (leaf, d): generated here, or taken from the draws shadow() made one step ahead
-  __device__ __forceinline__ float noise(Key lk, int e, int d, int D) const {
-    return (LAT && xi_ready) ? s.xi[e] : normal_at(lk, d, D);
-  }
-
   // diffusion update, phase 1 = `update` (before the new gradient), phase 2 = `update2`
   __device__ void diffuse(int phase, int i, const sgmcmc_step_coef& cf, int key_slot) {
     const int D = m.leaf_dim;
@@ -696,7 +623,7 @@ struct ChainCtx {
         case SGMCMC_DIFF_SGLD:
           for (int d = threadIdx.x; d < D; d += blockDim.x) {
             const int e = off + d;
-            s.theta[e] = fmaf(cf.ca, noise(lk, e, d, D), fmaf(cf.h, s.grad[e], s.theta[e]));
+            s.theta[e] = fmaf(cf.ca, normal_at(lk, d, D), fmaf(cf.h, s.grad[e], s.theta[e]));
           }
           break;
         case SGMCMC_DIFF_PSGLD:
@@ -706,7 +633,7 @@ struct ChainCtx {
             const float v = alpha * s.aux1[e] + (1.0f - alpha) * (g * g);
             const float G = 1.0f / (sqrtf(v) + eps);
             s.aux1[e] = v;
-            s.theta[e] = s.theta[e] + cf.hh * G * g + sqrtf(cf.h * G) * noise(lk, e, d, D);
+            s.theta[e] = s.theta[e] + cf.hh * G * g + sqrtf(cf.h * G) * normal_at(lk, d, D);
           }
           break;
         case SGMCMC_DIFF_SGLDADAM:
@@ -718,7 +645,7 @@ struct ChainCtx {
             const float mh = mm / cf.ca, vh = vv / cf.cb;
             const float a = cf.h / (sqrtf(vh) + eps);
             s.aux1[e] = mm; s.aux2[e] = vv;
-            s.theta[e] = s.theta[e] + a * 0.5f * mh + sqrtf(a) * noise(lk, e, d, D);
+            s.theta[e] = s.theta[e] + a * 0.5f * mh + sqrtf(a) * normal_at(lk, d, D);
           }
           break;
         case SGMCMC_DIFF_SGHMC:
@@ -726,7 +653,7 @@ struct ChainCtx {
             const int e = off + d;
             const float v = s.aux1[e], alpha = m.hyper[0];
             s.theta[e] += v;
-            s.aux1[e] = v + cf.h * s.grad[e] - alpha * v + cf.ca * noise(lk, e, d, D);
+            s.aux1[e] = v + cf.h * s.grad[e] - alpha * v + cf.ca * normal_at(lk, d, D);
           }
           break;
         case SGMCMC_DIFF_BAOAB:
@@ -734,7 +661,7 @@ struct ChainCtx {
             const int e = off + d;
             float v = fmaf(cf.hh, s.grad[e], s.aux1[e]);
             float x = s.theta[e] + v * cf.h * 0.5f;
-            v = cf.ca * v + cf.cb * noise(lk, e, d, D);
+            v = cf.ca * v + cf.cb * normal_at(lk, d, D);
             x = x + v * cf.h * 0.5f;
             s.aux1[e] = v; s.theta[e] = x;
           }
@@ -750,7 +677,7 @@ struct ChainCtx {
           for (int d = threadIdx.x; d < D; d += blockDim.x) {
             const int e = off + d;
             float v = s.aux1[e];
-            v = v - alpha * v + cf.h * s.grad[e] + cf.ca * noise(kn, e, d, D);
+            v = v - alpha * v + cf.h * s.grad[e] + cf.ca * normal_at(kn, d, D);
             s.aux1[e] = v; s.theta[e] += v;
             ss = fmaf(v, v, ss);
           }
@@ -774,7 +701,7 @@ struct ChainCtx {
           ss = 0.f;
           for (int d = threadIdx.x; d < D; d += blockDim.x) {
             const int e = off + d;
-            const float v = c1 * s.aux1[e] + c2 * noise(lk, e, d, D);
+            const float v = c1 * s.aux1[e] + c2 * normal_at(lk, d, D);
             s.aux1[e] = v; ss = fmaf(v, v, ss);
           }
           alpha = alpha + cf.hh * (sqrtf(block_sum(ss, s.red)) - (float)D);
@@ -791,12 +718,10 @@ struct ChainCtx {
   // langevin kernel, kernels.py:53-64
   __device__ void langevin(int i, Key key, const sgmcmc_step_coef& cf) {
     SG_TA(t_l);
-    xi_ready = LAT && ahead;                             // shadow() of the previous step prepared this one
-    if (!(LAT && ahead)) expand_step_keys(key); else look_slot = -1;   // shadow() already split the next carry
+    expand_step_keys(key);
     SG_TB(1, t_l);
     Key k2; k2.a = s.keys[2]; k2.b = s.keys[3];
     diffuse(1, i, cf, 4);
-    xi_ready = false;
     SG_TB(2, t_l);
     estimate(i, k2, false);
     plan_cached = false;
@@ -819,7 +744,7 @@ struct ChainCtx {
   }
 };
 
-template <int FAMILY, int CV, int NCH, bool EXT = false, bool LAT = false>
+template <int FAMILY, int CV, int NCH, bool EXT = false>
 __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel m, const VecRun run) {
   extern __shared__ __align__(16) float smem_raw[];
   const int W = blockDim.x >> 5;
@@ -852,7 +777,7 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
   }
   __syncthreads();
 
-  ChainCtx<FAMILY, CV, NCH, EXT, LAT> ctx(m, s);
+  ChainCtx<FAMILY, CV, NCH, EXT> ctx(m, s);
   Key carry{0u, 0u};
 
   if (EXT && run.sum_in) {                            // finish the previous estimate from the all-reduced sums
@@ -898,11 +823,8 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
       }
       else { Key nk; split2(carry, nk, sub); carry = nk; }      // samplers.py:49 / optimizer.py:46
       have_next = false;
-      ctx.next_slot = -1;
       if (run.step_keys == nullptr && sidx + 1 < run.K && !(EXT && m.diffusion == SGMCMC_DIFF_ADAM_OPT)) {
         ctx.look_slot = (sidx + 1) & 1; ctx.look_carry = carry; have_next = true;
-        // cluster launches: the next langevin step is prepared in the shadow of this step's cluster barrier
-        if (LAT && cs > 1 && m.diffusion != SGMCMC_DIFF_SGHMC) ctx.next_slot = (sidx + 1) & 1;
       }
       SG_TB(0, t_s);
       if (EXT && m.diffusion == SGMCMC_DIFF_ADAM_OPT) {
