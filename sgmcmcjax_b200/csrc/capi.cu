@@ -385,14 +385,24 @@ int fullgrad_tc(sgmcmc_handle* h, const float* thetas, int m, float* out, cudaSt
     k2::transpose_rows_kernel<<<blocks, 256, 0, s>>>(h->rows, n, ds, d, dn, h->k2_xt);
     CUDA_TRY(cudaGetLastError()); ++g_launches;
   }
-  // rows per pass: W (hi + lo) of one pass stays <= 1 GB; a multiple of 128 so that only the last pass is ragged
-  size_t nc_max = ((size_t)1 << 30) / ((size_t)8 * m);
-  nc_max = nc_max < 128 ? 128 : (nc_max & ~(size_t)127);
+  // Blocking.  The intermediate W = -sigmoid(Theta X~^T) (hi + lo: 8 bytes per (theta, row) pair) is produced by one kernel
+  // and consumed by the next; sized to stay in L2 between the two (SGMCMC_K2_W_MB, default 48 of the 126 MB) it never
+  // makes the HBM round trip that bounded round 1's 1 GB passes.  A block is mb parameter vectors x nc rows: nc = 1024 rows
+  // (8 row tiles) if that leaves mb >= 128, all rows of the theta block otherwise; both multiples of 128 so that only the
+  // last blocks are ragged.
+  const size_t w_budget = (size_t)std::max(1, env_int("SGMCMC_K2_W_MB", 48)) << 20;
+  size_t nc_max = 1024, mb_max = (w_budget / (8 * nc_max)) & ~(size_t)127;
+  if (mb_max < 128) mb_max = 128;
+  if (mb_max >= (size_t)m) {                       // every parameter vector in one block: spend the budget on rows
+    mb_max = ((size_t)m + 127) & ~(size_t)127;
+    nc_max = (w_budget / (8 * mb_max)) & ~(size_t)127;
+    if (nc_max < 128) nc_max = 128;
+  }
   if (nc_max > n) nc_max = (n + 127) & ~(size_t)127;
   const size_t nic_max = nc_max / kt::KC;
   const size_t ts_bytes = kt::align_up((size_t)2 * chunks * m * kt::KC * sizeof(float), 256);
   const size_t g_bytes = kt::align_up((size_t)m * P * sizeof(float), 256);
-  const size_t w_bytes = kt::align_up((size_t)2 * nic_max * m * kt::KC * sizeof(float), 256);
+  const size_t w_bytes = kt::align_up((size_t)2 * nic_max * mb_max * kt::KC * sizeof(float), 256);
   if (ts_bytes + g_bytes + w_bytes > h->k2_scratch_bytes) {
     if (h->k2_scratch) CUDA_TRY(cudaFree(h->k2_scratch));
     h->k2_scratch = nullptr; h->k2_scratch_bytes = 0;
@@ -414,18 +424,22 @@ int fullgrad_tc(sgmcmc_handle* h, const float* thetas, int m, float* out, cudaSt
   const size_t smem_b = k2::smem_b(dn);
   CUDA_TRY(cudaFuncSetAttribute(k2::k2_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2::SMEM_A));
   CUDA_TRY(cudaFuncSetAttribute(k2::k2_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-  const int MT = (m + kt::TILE - 1) / kt::TILE;
-  for (size_t i0 = 0; i0 < n; i0 += nc_max) {
-    const int nc = (int)std::min(nc_max, n - i0);
-    const int nic = (nc + kt::KC - 1) / kt::KC;
-    const long long tiles = (long long)MT * ((nc + kt::TILE - 1) / kt::TILE);
-    if ((rc = encode_rows16(&wmap, W, (size_t)2 * nic * m, kt::TILE)) != SGMCMC_OK) return rc;
-    k2::k2_scores_kernel<<<(int)std::min<long long>(tiles, h->num_sms), k2::THREADS, k2::SMEM_A, s>>>(tmap, xmap, m, (int)n, chunks, dp,
-                                                                                                    (int)i0, nc, W);
-    CUDA_TRY(cudaGetLastError()); ++g_launches;
-    int ksplit = std::max(1, std::min(nic, 2 * h->num_sms / MT));
-    k2::k2_accum_kernel<<<MT * ksplit, k2::THREADS, smem_b, s>>>(wmap, xtmap, m, P, d, dn, nic, (int)nic_all, (int)(i0 / kt::KC), ksplit, G);
-    CUDA_TRY(cudaGetLastError()); ++g_launches;
+  for (size_t m0 = 0; m0 < (size_t)m; m0 += mb_max) {
+    const int mb = (int)std::min(mb_max, (size_t)m - m0);
+    const int MT = (mb + kt::TILE - 1) / kt::TILE;
+    for (size_t i0 = 0; i0 < n; i0 += nc_max) {
+      const int nc = (int)std::min(nc_max, n - i0);
+      const int nic = (nc + kt::KC - 1) / kt::KC;
+      const long long tiles = (long long)MT * ((nc + kt::TILE - 1) / kt::TILE);
+      if ((rc = encode_rows16(&wmap, W, (size_t)2 * nic * mb, kt::TILE)) != SGMCMC_OK) return rc;
+      k2::k2_scores_kernel<<<(int)std::min<long long>(tiles, h->num_sms), k2::THREADS, k2::SMEM_A, s>>>(
+          tmap, xmap, m, (int)m0, mb, (int)n, chunks, dp, (int)i0, nc, W);
+      CUDA_TRY(cudaGetLastError()); ++g_launches;
+      int ksplit = std::max(1, std::min(nic, 2 * h->num_sms / MT));
+      k2::k2_accum_kernel<<<MT * ksplit, k2::THREADS, smem_b, s>>>(wmap, xtmap, mb, P, d, dn, nic, (int)nic_all, (int)(i0 / kt::KC), ksplit,
+                                                                  G + m0 * (size_t)P);
+      CUDA_TRY(cudaGetLastError()); ++g_launches;
+    }
   }
   k2::finish_kernel<<<std::min(blocks, (int)((size_t)m * P / 256 + 1)), 256, 0, s>>>(G, thetas, m, P, h->vm.prior2[0], out);
   CUDA_TRY(cudaGetLastError()); ++g_launches;

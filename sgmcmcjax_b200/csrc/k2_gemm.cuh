@@ -119,11 +119,11 @@ __global__ void finish_kernel(const float* __restrict__ G, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------ scores
-// tmap: Theta split as a [.., 16] matrix (rows (seg * chunks + c) * m + r); xmap: Xs likewise with n rows per block.
-// W[seg][ic][m][16] for the nic_local = ceil(nc / 16) row chunks of [i0, i0 + nc).
+// tmap: Theta split as a [.., 16] matrix (rows (seg * chunks + c) * m_all + r); xmap: Xs likewise with n rows per block.
+// This launch: parameter vectors [m0, m0 + m) x rows [i0, i0 + nc);  W[seg][ic][m][16] for the ceil(nc / 16) row chunks.
 __global__ void __launch_bounds__(THREADS, 1)
-k2_scores_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap xmap, int m, int n, int chunks,
-                 int dp, int i0, int nc, float* __restrict__ W) {
+k2_scores_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap xmap, int m_all, int m0, int m,
+                 int n, int chunks, int dp, int i0, int nc, float* __restrict__ W) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + (size_t)A_STAGES * A_STAGE_BYTES;
@@ -156,7 +156,7 @@ k2_scores_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
           mbar_arrive_expect_tx(&tail->full[stage], A_STAGE_BYTES);
 #pragma unroll
           for (int seg = 0; seg < 2; ++seg) {
-            tma_load_2d(sb + seg * CHUNK_BYTES, &tmap, 0, (seg * chunks + c) * m + mt * TILE, &tail->full[stage]);
+            tma_load_2d(sb + seg * CHUNK_BYTES, &tmap, 0, (seg * chunks + c) * m_all + m0 + mt * TILE, &tail->full[stage]);
             tma_load_2d(sb + (2 + seg) * CHUNK_BYTES, &xmap, 0, (seg * chunks + c) * n + i0 + it * TILE, &tail->full[stage]);
           }
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }

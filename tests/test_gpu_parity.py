@@ -522,6 +522,14 @@ def test_fullbatch_grad_tensor_core_path(cuda, n, d, m):
         ref = fam.grad_log_post([thetas[j]], data, n, np.float64)[0]
         close(got[j], ref, rtol=2e-5, what=f"K2 tensor-core row {j}")
     close(got[:5], simt, rtol=2e-5, what="K2 tensor-core vs SIMT")
+    # the same with a 1 MB budget for the intermediate: blocks of 128 parameter vectors x 1024 rows (the blocking that keeps
+    # W = -sigmoid(Theta X~^T) in L2 between the two contractions, exercised here with ragged last blocks in both directions)
+    os.environ["SGMCMC_K2_W_MB"] = "1"
+    try:
+        small = eng.fullbatch_grad(torch.from_numpy(thetas).cuda()).cpu().numpy()
+    finally:
+        del os.environ["SGMCMC_K2_W_MB"]
+    close(small, got, rtol=2e-5, what="K2 blocked (1 MB) vs default blocking")
 
 
 @pytest.mark.parametrize("name,dt,kw", [KERNELS[0], KERNELS[1], KERNELS[3], KERNELS[5], KERNELS[7], KERNELS[9]],
