@@ -385,12 +385,14 @@ int fullgrad_tc(sgmcmc_handle* h, const float* thetas, int m, float* out, cudaSt
     k2::transpose_rows_kernel<<<blocks, 256, 0, s>>>(h->rows, n, ds, d, dn, h->k2_xt);
     CUDA_TRY(cudaGetLastError()); ++g_launches;
   }
-  // Blocking.  The intermediate W = -sigmoid(Theta X~^T) (hi + lo: 8 bytes per (theta, row) pair) is produced by one kernel
-  // and consumed by the next; sized to stay in L2 between the two (SGMCMC_K2_W_MB, default 48 of the 126 MB) it never
-  // makes the HBM round trip that bounded round 1's 1 GB passes.  A block is mb parameter vectors x nc rows: nc = 1024 rows
-  // (8 row tiles) if that leaves mb >= 128, all rows of the theta block otherwise; both multiples of 128 so that only the
-  // last blocks are ragged.
-  const size_t w_budget = (size_t)std::max(1, env_int("SGMCMC_K2_W_MB", 48)) << 20;
+  // Blocking: a block is mb parameter vectors x nc rows whose intermediate W = -sigmoid(Theta X~^T) (hi + lo: 8 bytes per
+  // (theta, row) pair) fits SGMCMC_K2_W_MB.  Default 1 GB: all parameter vectors, as many rows as fit.  Small blocks whose W
+  // stays in L2 between the two kernels (no HBM round trip) were measured and LOSE: 48 MB blocks 485 ms, 96 MB 357 ms,
+  // 256 MB 250 ms against 199-206 ms at 1 GB for M = 5e4, N = 1e6 - two launches of 576-thread / 196 KB / 512-TMEM-column
+  // kernels per block cost ~30 us of launch, prologue and drain against ~25 us of work.  Only a persistent fused kernel
+  // would collect the L2 residency.  nc = 1024 rows (8 row tiles) if that leaves mb >= 128, all rows of the theta block
+  // otherwise; both multiples of 128 so that only the last blocks are ragged.
+  const size_t w_budget = (size_t)std::max(1, env_int("SGMCMC_K2_W_MB", 1024)) << 20;
   size_t nc_max = 1024, mb_max = (w_budget / (8 * nc_max)) & ~(size_t)127;
   if (mb_max < 128) mb_max = 128;
   if (mb_max >= (size_t)m) {                       // every parameter vector in one block: spend the budget on rows
