@@ -229,6 +229,83 @@ __device__ __forceinline__ void noise_pass(unsigned n, const float* xi, LD ld, S
   for (; e0 < n; e0 += bd) { const Elt v = ld(e0); const float z = xi[e0]; st(e0, v, z); }
 }
 
+// Pair versions: a thread takes the ADJACENT blocks 2p and 2p + 1, i.e. elements (2p, 2p + 1) and (2p + h, 2p + 1 + h), so
+// that every array is read and written 8 bytes at a time (half the load / store instructions and address arithmetic of
+// the scalar passes: these passes are bound by instruction issue, not by bandwidth).  Needs h even and 8-byte aligned
+// arrays (the caller checks); the blocks past the last full pair go through the scalar tail.
+//   ld2(e, t0, t1): elements e, e + 1;   f(e, t, xi) -> Out;   st2(e, o0, o1)
+struct Out { float x, a, b; };                   // new x, new first / second auxiliary value
+template <int U, class LD2, class F, class ST2, class LD, class ST>
+__device__ __forceinline__ void leaf_pass2(unsigned n, Key key, LD2 ld2, F f, ST2 st2, LD ld, ST st) {
+  const unsigned h = (n + 1u) >> 1;
+  const unsigned hf = n - h;
+  const unsigned np = hf >> 1;                   // full pairs of blocks
+  const unsigned bd = blockDim.x;
+  unsigned p0 = threadIdx.x;
+#pragma unroll 1
+  for (; p0 + (U - 1) * bd < np; p0 += U * bd) {
+    Elt a0[U], a1[U], b0[U], b1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const unsigned e = 2u * (p0 + u * bd); ld2(e, a0[u], a1[u]); ld2(e + h, b0[u], b1[u]); }
+    uint32_t w[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned e = 2u * (p0 + u * bd);
+      stream_block(key, e, n, w[u][0], w[u][2]);          // block e: elements e, e + h
+      stream_block(key, e + 1u, n, w[u][1], w[u][3]);     // block e + 1: elements e + 1, e + 1 + h
+    }
+    float z[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) z[u][k] = bits_to_normal(w[u][k]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned e = 2u * (p0 + u * bd);
+      st2(e, f(e, a0[u], z[u][0]), f(e + 1u, a1[u], z[u][1]));
+      st2(e + h, f(e + h, b0[u], z[u][2]), f(e + h + 1u, b1[u], z[u][3]));
+    }
+  }
+#pragma unroll 1
+  for (; p0 < np; p0 += bd) {
+    const unsigned e = 2u * p0;
+    Elt a0, a1, b0, b1;
+    ld2(e, a0, a1); ld2(e + h, b0, b1);
+    uint32_t w0, w1, w2, w3;
+    stream_block(key, e, n, w0, w2);
+    stream_block(key, e + 1u, n, w1, w3);
+    st2(e, f(e, a0, bits_to_normal(w0)), f(e + 1u, a1, bits_to_normal(w1)));
+    st2(e + h, f(e + h, b0, bits_to_normal(w2)), f(e + h + 1u, b1, bits_to_normal(w3)));
+  }
+#pragma unroll 1
+  for (unsigned m0 = 2u * np + threadIdx.x; m0 < h; m0 += bd) {   // blocks past the last full pair (scalar)
+    const bool two = m0 + h < n;
+    const Elt a = ld(m0);
+    const Elt b = two ? ld(m0 + h) : Elt{};
+    uint32_t w0, w1;
+    stream_block(key, m0, n, w0, w1);
+    st(m0, a, bits_to_normal(w0));
+    if (two) st(m0 + h, b, bits_to_normal(w1));
+  }
+}
+// ... and without noise: elements (2q, 2q + 1)
+template <int U, class LD2, class F, class ST2, class LD, class ST>
+__device__ __forceinline__ void plain_pass2(unsigned n, LD2 ld2, F f, ST2 st2, LD ld, ST st) {
+  const unsigned nq = n >> 1, bd = blockDim.x;
+  unsigned q0 = threadIdx.x;
+#pragma unroll 1
+  for (; q0 + (2 * U - 1) * bd < nq; q0 += 2 * U * bd) {
+    Elt t0[2 * U], t1[2 * U];
+#pragma unroll
+    for (int u = 0; u < 2 * U; ++u) ld2(2u * (q0 + u * bd), t0[u], t1[u]);
+#pragma unroll
+    for (int u = 0; u < 2 * U; ++u) { const unsigned e = 2u * (q0 + u * bd); st2(e, f(e, t0[u]), f(e + 1u, t1[u])); }
+  }
+#pragma unroll 1
+  for (; q0 < nq; q0 += bd) { const unsigned e = 2u * q0; Elt t0, t1; ld2(e, t0, t1); st2(e, f(e, t0), f(e + 1u, t1)); }
+  if ((n & 1u) && threadIdx.x == 0) { const Elt t = ld(n - 1u); st(n - 1u, t); }
+}
+
 // Producer side: the threads [t0, t0 + nt) of the CTA fill dst[0, n) with normal(key, (n,)).
 __device__ __forceinline__ void produce_leaf_noise(unsigned n, Key key, float* dst, unsigned t, unsigned nt) {
   const unsigned h = (n + 1u) >> 1;
@@ -750,61 +827,108 @@ struct BigCtx {
         if (smp) SG_GLOBAL_PTR(smp);
         if (MODE == 2) { SG_GLOBAL_PTR(fb); SG_GLOBAL_PTR(center); }
       }
-      // loaders: pure loads of x, the gradient buffer (+ CV terms) and optionally the auxiliaries
-      auto ld_xg = [&](unsigned e) { Elt t{}; t.x = x[e]; ld_grad<MODE>(t, g, e, off + e); return t; };
-      auto ld_xvg = [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; ld_grad<MODE>(t, g, e, off + e); return t; };
-      auto ld_xvvg = [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; t.b = v2[e]; ld_grad<MODE>(t, g, e, off + e); return t; };
-      auto emit = [&](unsigned e, float xn) { x[e] = xn; if (zg) g[e] = 0.f; if (smp) __stcs(smp + e, xn); };
+      // 8-byte path (leaf_pass2 / plain_pass2): every array 8-byte aligned and the half-split offset h even
+      const unsigned hh2 = (n + 1u) >> 1;
+      uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g);
+      if (v) al |= reinterpret_cast<uintptr_t>(v);
+      if (v2) al |= reinterpret_cast<uintptr_t>(v2);
+      if (smp) al |= reinterpret_cast<uintptr_t>(smp);
+      if (MODE == 2 || MODE == 4) al |= reinterpret_cast<uintptr_t>(fb + off) | reinterpret_cast<uintptr_t>(center + off);
+      const bool vec2 = (al & 7) == 0 && (hh2 & 1u) == 0 && !use_noise;
+      // loaders: pure loads of x, the gradient buffer (+ CV terms) and optionally the auxiliaries; HV / HV2: with v / v2
+      auto ld1 = [&](unsigned e, bool hv, bool hv2, bool hg) {
+        Elt t{}; t.x = x[e];
+        if (hv) t.a = v[e];
+        if (hv2) t.b = v2[e];
+        if (hg) ld_grad<MODE>(t, g, e, off + e);
+        return t;
+      };
+      auto ld2v = [&](unsigned e, Elt& t0, Elt& t1, bool hv, bool hv2, bool hg) {
+        t0 = Elt{}; t1 = Elt{};
+        const float2 xx = *reinterpret_cast<const float2*>(x + e); t0.x = xx.x; t1.x = xx.y;
+        if (hv) { const float2 a = *reinterpret_cast<const float2*>(v + e); t0.a = a.x; t1.a = a.y; }
+        if (hv2) { const float2 b = *reinterpret_cast<const float2*>(v2 + e); t0.b = b.x; t1.b = b.y; }
+        if (hg) {
+          if (MODE >= 3) { t0.g = compact_raw(off + e); t1.g = compact_raw(off + e + 1u); }
+          else { const float2 gg = __ldcg(reinterpret_cast<const float2*>(g + e)); t0.g = gg.x; t1.g = gg.y; }
+          if (MODE == 2 || MODE == 4) {
+            const float2 f2 = *reinterpret_cast<const float2*>(fb + off + e), c2 = *reinterpret_cast<const float2*>(center + off + e);
+            t0.fb = f2.x; t1.fb = f2.y; t0.cen = c2.x; t1.cen = c2.y;
+          }
+        }
+      };
+      // stores of the new x (+ sample), auxiliaries, and the zero that re-arms the gradient buffer
+      auto st1 = [&](unsigned e, const Out& o, bool sv, bool sv2, bool z, bool sm) {
+        x[e] = o.x;
+        if (sv) v[e] = o.a;
+        if (sv2) v2[e] = o.b;
+        if (z && zg) g[e] = 0.f;
+        if (sm && smp) __stcs(smp + e, o.x);
+      };
+      auto st2v = [&](unsigned e, const Out& o0, const Out& o1, bool sv, bool sv2, bool z, bool sm) {
+        *reinterpret_cast<float2*>(x + e) = make_float2(o0.x, o1.x);
+        if (sv) *reinterpret_cast<float2*>(v + e) = make_float2(o0.a, o1.a);
+        if (sv2) *reinterpret_cast<float2*>(v2 + e) = make_float2(o0.b, o1.b);
+        if (z && zg) *reinterpret_cast<float2*>(g + e) = make_float2(0.f, 0.f);
+        if (sm && smp) __stcs(reinterpret_cast<float2*>(smp + e), make_float2(o0.x, o1.x));
+      };
       const float* xi_buf = noise + off;
-      // st(e, t, xi) for every element with its N(0,1) draw: from the look-ahead buffer, or generated in place
-      auto noisy = [&](Key key, auto ld, auto st) {
-        if (use_noise) noise_pass<U>(n, xi_buf, ld, st); else leaf_pass<U>(n, key, ld, st);
+      // one noisy pass: f(e, t, xi) -> Out for every element with its N(0,1) draw (look-ahead buffer, or generated in
+      // place); HV / HV2: the diffusion carries one / two auxiliary arrays, HG: the pass consumes the gradient
+      auto noisy = [&](Key key, auto f, bool hv, bool hv2, bool hg, bool sm) {
+        auto ld = [&](unsigned e) { return ld1(e, hv, hv2, hg); };
+        auto st = [&](unsigned e, const Elt& t, float xi) { st1(e, f(e, t, xi), hv, hv2, hg, sm); };
+        if (use_noise) { noise_pass<U>(n, xi_buf, ld, st); return; }
+        if (vec2) {
+          leaf_pass2<(U > 1 ? U / 2 : 1)>(n, key, [&](unsigned e, Elt& t0, Elt& t1) { ld2v(e, t0, t1, hv, hv2, hg); }, f,
+                                          [&](unsigned e, const Out& o0, const Out& o1) { st2v(e, o0, o1, hv, hv2, hg, sm); }, ld, st);
+          return;
+        }
+        leaf_pass<U>(n, key, ld, st);
       };
       switch (m.diffusion) {
         case SGMCMC_DIFF_SGLD:
-          noisy(lk, ld_xg, [&](unsigned e, const Elt& t, float xi) { emit(e, fmaf(cfv.ca, xi, fmaf(cfv.h, gval<MODE>(t, gs, prior), t.x))); });
+          noisy(lk, [&](unsigned, const Elt& t, float xi) {
+            return Out{fmaf(cfv.ca, xi, fmaf(cfv.h, gval<MODE>(t, gs, prior), t.x)), 0.f, 0.f};
+          }, false, false, true, true);
           break;
         case SGMCMC_DIFF_PSGLD: {
           const float alpha = m.hyper[0], eps = m.hyper[1];
-          noisy(lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
+          noisy(lk, [&](unsigned, const Elt& t, float xi) {
             const float gg = gval<MODE>(t, gs, prior);
             const float vv = alpha * t.a + (1.0f - alpha) * (gg * gg);
             const float G = fast_rcp(fast_sqrt(vv) + eps);
-            v[e] = vv;
-            emit(e, t.x + cfv.hh * G * gg + fast_sqrt(cfv.h * G) * xi);
-          });
+            return Out{t.x + cfv.hh * G * gg + fast_sqrt(cfv.h * G) * xi, vv, 0.f};
+          }, true, false, true, true);
           break;
         }
         case SGMCMC_DIFF_SGLDADAM: {
           const float b1 = m.hyper[0], b2 = m.hyper[1], eps = m.hyper[2];
-          noisy(lk, ld_xvvg, [&](unsigned e, const Elt& t, float xi) {
+          noisy(lk, [&](unsigned, const Elt& t, float xi) {
             const float gg = gval<MODE>(t, gs, prior);
             const float mm = b1 * t.a + (1.0f - b1) * gg;
             const float vv = b2 * t.b + (1.0f - b2) * (gg * gg);
             const float mh = mm * fast_rcp(cfv.ca), vh = vv * fast_rcp(cfv.cb);
             const float a = cfv.h * fast_rcp(fast_sqrt(vh) + eps);
-            v[e] = mm; v2[e] = vv;
-            emit(e, t.x + a * 0.5f * mh + fast_sqrt(a) * xi);
-          });
+            return Out{t.x + a * 0.5f * mh + fast_sqrt(a) * xi, mm, vv};
+          }, true, true, true, true);
           break;
         }
         case SGMCMC_DIFF_SGHMC: {
           const float alpha = m.hyper[0];
-          noisy(lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
-            v[e] = t.a + cfv.h * gval<MODE>(t, gs, prior) - alpha * t.a + cfv.ca * xi;
-            emit(e, t.x + t.a);
-          });
+          noisy(lk, [&](unsigned, const Elt& t, float xi) {
+            return Out{t.x + t.a, t.a + cfv.h * gval<MODE>(t, gs, prior) - alpha * t.a + cfv.ca * xi, 0.f};
+          }, true, false, true, true);
           break;
         }
         case SGMCMC_DIFF_BAOAB:
-          noisy(lk, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
+          noisy(lk, [&](unsigned, const Elt& t, float xi) {
             float ve = fmaf(cfv.hh, gval<MODE>(t, gs, prior), t.a);
             float xe = t.x + ve * cfv.h * 0.5f;
             ve = cfv.ca * ve + cfv.cb * xi;
             xe = xe + ve * cfv.h * 0.5f;
-            v[e] = ve;
-            emit(e, xe);
-          });
+            return Out{xe, ve, 0.f};
+          }, true, false, true, true);
           break;
         case SGMCMC_DIFF_SGNHT: {
           Key kn = lk, sub = lk;
@@ -812,13 +936,12 @@ struct BigCtx {
           const bool first = (i == 0);
           if (first) split2(lk, kn, sub);               // diffusions.py:268-278
           float ss = 0.f;
-          noisy(kn, ld_xvg, [&](unsigned e, const Elt& t, float xi) {
+          noisy(kn, [&](unsigned e, const Elt& t, float xi) {
             float ve = first ? cfv.cb * normal_at(sub, e, n) : t.a;
             ve = ve - alpha * ve + cfv.h * gval<MODE>(t, gs, prior) + cfv.ca * xi;
-            v[e] = ve;
-            emit(e, t.x + ve);
             ss = fmaf(ve, ve, ss);
-          });
+            return Out{t.x + ve, ve, 0.f};
+          }, true, false, true, true);
           const float nrm = sqrtf(big_block_sum(ss, s.red));
           if (threadIdx.x == 0) s.alpha[leaf] = alpha + (nrm * nrm) / (float)n - cfv.h;
           break;
@@ -826,24 +949,30 @@ struct BigCtx {
         case SGMCMC_DIFF_BADODAB: {
           float alpha = s.alpha[leaf];
           float ss = 0.f;
-          plain_pass<U>(n, ld_xvg, [&](unsigned e, const Elt& t) {
-            const float ve = fmaf(cfv.hh, gval<MODE>(t, gs, prior), t.a);
-            v[e] = ve; x[e] = fmaf(cfv.hh, ve, t.x); if (zg) g[e] = 0.f;
-            ss = fmaf(ve, ve, ss);
-          });
+          {
+            auto f = [&](unsigned, const Elt& t) {
+              const float ve = fmaf(cfv.hh, gval<MODE>(t, gs, prior), t.a);
+              ss = fmaf(ve, ve, ss);
+              return Out{fmaf(cfv.hh, ve, t.x), ve, 0.f};
+            };
+            auto ld = [&](unsigned e) { return ld1(e, true, false, true); };
+            auto st = [&](unsigned e, const Elt& t) { st1(e, f(e, t), true, false, true, false); };
+            if (vec2 || ((al & 7) == 0 && !use_noise && (n & 1u) == 0))
+              plain_pass2<U>(n, [&](unsigned e, Elt& t0, Elt& t1) { ld2v(e, t0, t1, true, false, true); }, f,
+                             [&](unsigned e, const Out& o0, const Out& o1) { st2v(e, o0, o1, true, false, true, false); }, ld, st);
+            else
+              plain_pass<U>(n, ld, st);
+          }
           alpha = alpha + cfv.hh * (sqrtf(big_block_sum(ss, s.red)) - (float)n);
           const float c1 = (float)exp((double)(-alpha * cfv.h));     // correctly rounded, see vec_sampler.cuh
           const float c2 = (alpha == 0.0f) ? cfv.ca : sqrtf(fabsf((1.0f - c1 * c1) / (2.0f * alpha)));
           __syncthreads();
           float ss2 = 0.f;
-          noisy(lk, [&](unsigned e) { Elt t{}; t.x = x[e]; t.a = v[e]; return t; },
-                       [&](unsigned e, const Elt& t, float xi) {
-                         const float ve = c1 * t.a + c2 * xi;
-                         v[e] = ve; ss2 = fmaf(ve, ve, ss2);
-                         const float xn = fmaf(cfv.hh, ve, t.x);      // second half step of x with the new v
-                         x[e] = xn;
-                         if (smp) __stcs(smp + e, xn);
-                       });
+          noisy(lk, [&](unsigned, const Elt& t, float xi) {
+            const float ve = c1 * t.a + c2 * xi;
+            ss2 = fmaf(ve, ve, ss2);
+            return Out{fmaf(cfv.hh, ve, t.x), ve, 0.f};           // second half step of x with the new v
+          }, true, false, false, true);
           alpha = alpha + cfv.hh * (sqrtf(big_block_sum(ss2, s.red)) - (float)n);
           __syncthreads();
           if (threadIdx.x == 0) s.alpha[leaf] = alpha;
