@@ -26,6 +26,7 @@
 //       K2, the full-batch bypass) always use the dense buffer.
 //   MLP (models/bayesian_NN/NN_model.py:31-58): see mlp_grad.cuh.
 #pragma once
+#include <cstdlib>
 #include "prng.cuh"
 #include "vec_sampler.cuh"   // Key helpers, FULL, MAXL, VecRun layout reuse
 
@@ -76,7 +77,12 @@ struct BigModel {
 
 // threads per CTA of big_sampler_kernel<FAMILY> for this model
 template <int FAMILY> inline int big_threads(const BigModel& m) {
-  if (FAMILY == SGMCMC_FAMILY_PMF) return m.pmf_compact ? 512 : 256;
+  if (FAMILY == SGMCMC_FAMILY_PMF) {
+    if (m.pmf_compact) return 512;
+    const char* v = std::getenv("SGMCMC_PMF_THREADS");          // experiments: 128 / 256 / 384 / 512 (128 registers each)
+    const int t = v ? std::atoi(v) : 0;
+    return (t >= 64 && t <= 512 && t % 32 == 0) ? t : 256;
+  }
   return BigThreads<FAMILY>::value;
 }
 
