@@ -45,6 +45,7 @@ struct sgmcmc_handle {
   void* data1 = nullptr;       // owned (big families)
   int P = 0, DS = 0, nch = 1;
   float* rows = nullptr;       // owned: [n_data][DS]
+  float* mu = nullptr;         // owned: [DS] column means of the centred table (gaussian_mean)
   float* cv_center = nullptr;  // owned: [P]
   float* cv_grad = nullptr;    // owned: [P]
   float* partial = nullptr;    // owned scratch for sgmcmc_fullbatch_grad
@@ -79,6 +80,25 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, const int* __restr
       if (family == SGMCMC_FAMILY_LOGREG && y[r] != 0) v = -v;
     }
     rows[t] = v;
+  }
+}
+
+// gaussian_mean: column sums of x[n][D] in double (grid-stride over rows, one atomic per block and column)
+__global__ void column_sum_kernel(const float* __restrict__ x, size_t n, int D, double* __restrict__ sums) {
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double a = 0.0;
+    for (size_t r = blockIdx.x; r < n; r += gridDim.x) a += (double)x[r * D + d];
+    atomicAdd(&sums[d], a);
+  }
+}
+__global__ void column_mean_kernel(const double* __restrict__ sums, size_t n, int D, int DS, float* __restrict__ mu) {
+  for (int d = threadIdx.x; d < DS; d += blockDim.x) mu[d] = d < D ? (float)(sums[d] / (double)n) : 0.f;
+}
+__global__ void center_rows_kernel(float* __restrict__ rows, size_t n, int D, int DS, const float* __restrict__ mu) {
+  const size_t total = n * (size_t)DS;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int d = (int)(t % DS);
+    if (d < D) rows[t] -= mu[d];
   }
 }
 
@@ -132,7 +152,8 @@ __global__ void fullgrad_finish_kernel(const VecModel m, const float* __restrict
     const int leaf = e / m.leaf_dim, d = e - leaf * m.leaf_dim;
     float S = 0.f;
     for (int sp = 0; sp < splits; ++sp) S += partial[((size_t)mi * splits + sp) * m.DS + d];
-    out[(size_t)mi * m.P + e] = grad_from_sum<FAMILY>(m, leaf, d, S, thetas[(size_t)mi * m.P + e], 1.0f, (float)m.own_n);
+    out[(size_t)mi * m.P + e] = grad_from_sum<FAMILY>(m, leaf, d, S, thetas[(size_t)mi * m.P + e], 1.0f, (float)m.own_n,
+                                                      (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN && m.mu) ? m.mu[d] : 0.f);
   }
 }
 
@@ -569,6 +590,7 @@ int sgmcmc_create(const sgmcmc_config* cfg, sgmcmc_handle** out) {
 int sgmcmc_destroy(sgmcmc_handle* h) {
   if (!h) return SGMCMC_OK;
   if (h->rows) cudaFree(h->rows);
+  if (h->mu) cudaFree(h->mu);
   if (h->data0) cudaFree(h->data0);
   if (h->data1) cudaFree(h->data1);
   if (h->cv_center) cudaFree(h->cv_center);
@@ -636,6 +658,25 @@ int sgmcmc_set_data(sgmcmc_handle* h, const void* xv, const void* y, void* strea
   sg::pack_rows_kernel<<<blocks, 256, 0, s>>>(x, (const int*)y, h->rows, nrows, h->cfg.data_dim, h->DS, h->cfg.family);
   CUDA_TRY(cudaGetLastError()); ++g_launches;
   h->vm.rows = h->rows;
+  h->vm.mu = nullptr;
+  if (h->cfg.family == SGMCMC_FAMILY_GAUSSIAN_MEAN && h->vm.own_n == h->vm.n_data) {
+    // centre the rows by their column means (vec_sampler.cuh VecModel::mu): a data mean far from 0 would otherwise cancel
+    // in fp32 when the gradient is formed from the row SUM.  Row-sharded tables keep mu = 0 (every rank must use one shift).
+    if (!h->mu) CUDA_TRY(cudaMalloc(&h->mu, (size_t)h->DS * sizeof(float)));
+    double* sums = nullptr;
+    CUDA_TRY(cudaMalloc(&sums, (size_t)h->cfg.data_dim * sizeof(double)));
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)h->cfg.data_dim * sizeof(double), s);
+    if (e == cudaSuccess) {
+      sg::column_sum_kernel<<<(int)std::min<size_t>(nrows, (size_t)h->num_sms * 8), 128, 0, s>>>(x, nrows, h->cfg.data_dim, sums);
+      sg::column_mean_kernel<<<1, 128, 0, s>>>(sums, nrows, h->cfg.data_dim, h->DS, h->mu);
+      sg::center_rows_kernel<<<blocks, 256, 0, s>>>(h->rows, nrows, h->cfg.data_dim, h->DS, h->mu);
+      e = cudaGetLastError(); g_launches += 3;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(sums);
+    CUDA_TRY(e);
+    h->vm.mu = h->mu;
+  }
   h->has_data = true;
   if (h->k2_xs) { cudaFree(h->k2_xs); h->k2_xs = nullptr; }      // operand copies of the previous table
   if (h->k2_xt) { cudaFree(h->k2_xt); h->k2_xt = nullptr; }

@@ -47,6 +47,9 @@ struct VecModel {
   float prior2[MAXL];      // gaussian_mean: 2 c_l ; logreg: [0] = prior precision
   float hyper[4];
   const float* rows;       // [own_n][DS]: rows own_lo .. own_lo + own_n - 1 of the table (data-sharded mode: a slice)
+  const float* mu;         // gaussian_mean: [DS] column means the stored rows were centred by (nullptr: not centred).  The
+                           //   gradient lik2 (sum x - B theta) is formed as lik2 (sum (x - mu) - B (theta - mu)): without the
+                           //   shift, data whose mean is far from 0 cancels in fp32 at ~B |x| 2^-24 instead of ~sqrt(B) |x| 2^-24
   unsigned own_lo, own_n;  // own_lo = 0, own_n = n_data unless the rows are sharded over ranks
   const float* cv_center;  // [P]  (CV only)
   const float* cv_grad;    // [P]  full-batch gradient at cv_center
@@ -82,6 +85,7 @@ constexpr int SHARD_UPDATE2 = 1, SHARD_STEP = 2;
 // shared-memory carve-up (dynamic): all arrays padded to DSP = max(P, DS) rounded to 4
 struct Smem {
   float *theta, *aux1, *aux2, *grad, *center, *fb, *S, *part;
+  float* mu;          // [DS] column means of the centred row table (gaussian_mean), zeros otherwise
   float* recv;        // [2][cs][DS + 4]: folded partial sums (+ log-likelihood value term) PUSHED here by every CTA of the cluster
   float* alpha;       // [MAXL]
   float* red;         // [32] block-reduction scratch
@@ -98,6 +102,7 @@ __device__ __forceinline__ Smem carve(float* base, int PP, int DS, int W, int cs
   s.fb = base;               base += PP;
   s.S = base;                base += DS + 4;     // [DS] sums, [DS] = log-likelihood value term (optimiser)
   s.part = base;             base += W * DS;
+  s.mu = base;               base += DS;
   s.recv = base;             base += cs > 1 ? 2 * cs * (DS + 4) : 0;
   s.alpha = base;            base += MAXL;
   s.red = base;              base += 32;
@@ -110,7 +115,7 @@ constexpr int SMEM_KEY_WORDS = 2 * (4 + 2 * MAXL);
 constexpr int KEY_PLAN = 4 + 2 * MAXL, KEY_NEXT = KEY_PLAN + 4;
 static_assert(KEY_NEXT + 8 <= SMEM_KEY_WORDS, "key slots");
 __host__ __device__ inline size_t vec_smem_bytes(int PP, int DS, int W, int cs) {
-  return sizeof(float) * (size_t)(6 * PP + (DS + 4) + W * DS + (cs > 1 ? 2 * cs * (DS + 4) : 0) + MAXL + 32) +
+  return sizeof(float) * (size_t)(6 * PP + (DS + 4) + W * DS + DS + (cs > 1 ? 2 * cs * (DS + 4) : 0) + MAXL + 32) +
          sizeof(uint32_t) * SMEM_KEY_WORDS;
 }
 
@@ -421,11 +426,12 @@ __device__ __forceinline__ void fold_parts(const Smem& s, int DS, int& buf, bool
 
 // grad_log_post at theta from the folded row sum S (util.py:43-44).
 //   rows_in_S = number of rows summed (as float), scale = Ndata / rows_in_S
+//   mu_d = column mean the rows were centred by (gaussian_mean; 0 if not centred): S_d sums x - mu
 template <int FAMILY>
 __device__ __forceinline__ float grad_from_sum(const VecModel& m, int leaf, int d, float S_d, float theta_e,
-                                               float scale, float rows_in_S) {
+                                               float scale, float rows_in_S, float mu_d = 0.f) {
   if (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN)
-    return scale * (m.lik2[leaf] * (S_d - rows_in_S * theta_e)) - m.prior2[leaf] * theta_e;
+    return scale * (m.lik2[leaf] * (S_d - rows_in_S * (theta_e - mu_d))) - m.prior2[leaf] * theta_e;
   return scale * S_d - m.prior2[0] * theta_e;
 }
 
@@ -460,7 +466,7 @@ struct ChainCtx {
     const float rows = (float)m.own_n;
     for (int e = threadIdx.x; e < m.P; e += blockDim.x) {
       const int leaf = e / m.leaf_dim, d = e - leaf * m.leaf_dim;
-      dst[e] = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.theta[e], 1.0f, rows);
+      dst[e] = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.theta[e], 1.0f, rows, s.mu[d]);
     }
     __syncthreads();
   }
@@ -518,15 +524,17 @@ struct ChainCtx {
     const float B = (float)m.batch;
     float lik = 0.f, pri = 0.f;
     if (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN) {
-      for (int leaf = 0; leaf < m.n_leaves; ++leaf) {      // sum_i |x_i - th|^2 = sum |x|^2 - 2 th.S + B |th|^2
-        float a = 0.f, b = 0.f;
+      // with x' = x - mu (the stored rows), u = th - mu:  sum_i |x_i - th|^2 = sum |x'|^2 - 2 u.S' + B |u|^2
+      for (int leaf = 0; leaf < m.n_leaves; ++leaf) {
+        float a = 0.f, b = 0.f, c = 0.f;
         for (int d = threadIdx.x; d < m.leaf_dim; d += blockDim.x) {
-          const float t = s.theta[leaf * m.leaf_dim + d];
-          a = fmaf(t, s.S[d], a); b = fmaf(t, t, b);
+          const float t = s.theta[leaf * m.leaf_dim + d], u = t - s.mu[d];
+          a = fmaf(u, s.S[d], a); b = fmaf(u, u, b); c = fmaf(t, t, c);
         }
-        const float tS = block_sum(a, s.red);
-        const float tt = block_sum(b, s.red);
-        lik -= 0.5f * m.lik2[leaf] * (lps - 2.0f * tS + B * tt);
+        const float uS = block_sum(a, s.red);
+        const float uu = block_sum(b, s.red);
+        const float tt = block_sum(c, s.red);
+        lik -= 0.5f * m.lik2[leaf] * (lps - 2.0f * uS + B * uu);
         pri -= 0.5f * m.prior2[leaf] * tt;
       }
     } else {
@@ -558,11 +566,11 @@ struct ChainCtx {
       const int leaf = e / m.leaf_dim, d = e - leaf * m.leaf_dim;
       float g;
       if (!CV) {
-        g = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.theta[e], m.scale, rows);
+        g = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.theta[e], m.scale, rows, s.mu[d]);
       } else if (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN) {
         // (c + g) - gc, gradient_estimation.py:72
-        const float gt = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.theta[e], m.scale, rows);
-        const float gc = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.center[e], m.scale, rows);
+        const float gt = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.theta[e], m.scale, rows, s.mu[d]);
+        const float gc = grad_from_sum<FAMILY>(m, leaf, d, s.S[d], s.center[e], m.scale, rows, s.mu[d]);
         g = (s.fb[e] + gt) - gc;
       } else {
         // S already holds sum (w - w_c) x~ : c + (g - gc) without the fp32 cancellation
@@ -775,6 +783,8 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
       a = run.mode == 0 ? st.alpha[(size_t)c * m.n_leaves + threadIdx.x] : m.hyper[0];
     s.alpha[threadIdx.x] = a;
   }
+  for (int d = threadIdx.x; d < m.DS; d += blockDim.x)
+    s.mu[d] = (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN && m.mu) ? m.mu[d] : 0.f;
   __syncthreads();
 
   ChainCtx<FAMILY, CV, NCH, EXT> ctx(m, s);

@@ -744,3 +744,26 @@ def test_gen_data_matches_reference_key_tree(cuda):
     p = P.uniform(P.PRNGKey(6), (3000,))
     import torch
     assert np.array_equal(R.bernoulli_rows(k, torch.from_numpy(p)).cpu().numpy(), OG.bernoulli_rows(k, p))
+
+
+def test_gaussian_mean_far_from_zero_does_not_cancel(cuda):
+    """Data whose mean is 1000 standard deviations from 0: the gradient lik2 (sum x - B theta) is formed from the row SUM,
+    so without the column-mean shift of the row table (VecModel::mu) it cancels at ~B |x| 2^-24 in fp32.  Against the fp64
+    evaluation of util.py:43-44 on the same minibatch, and one sampler step against the oracle."""
+    from sgmcmcjax_b200 import kernels as NK
+    from sgmcmcjax_b200.models import gaussian_mean as G
+
+    n, d, batch = 10_000, 16, 1000
+    X = (np.float32(1000.0) + P.normal(P.PRNGKey(21), (n, d))).astype(np.float32)
+    th0 = np.full(d, 1000.1, np.float32)
+    fam = M.GaussianMean()
+    init_fn, kernel, get_params = NK.build_sgld_kernel(1e-7, G.loglikelihood, G.logprior, (X,), batch)
+    sub = P.split(P.PRNGKey(3))[1]
+    st = init_fn(sub, th0)
+    idx = P.choice_indices(sub, n, batch)
+    ref = fam.grad_log_post([th0], (X[idx],), n, np.float64)[0]
+    got = to_np(st.param_grad)
+    assert np.abs(got - ref).max() / np.abs(ref).max() <= 1e-5, np.abs(got - ref).max() / np.abs(ref).max()
+    fb = init_fn.engine.fullbatch_grad(__import__("torch").from_numpy(th0[None]).cuda()).cpu().numpy()[0]
+    ref_fb = fam.grad_log_post([th0], (X,), n, np.float64)[0]
+    assert np.abs(fb - ref_fb).max() / np.abs(ref_fb).max() <= 1e-5
