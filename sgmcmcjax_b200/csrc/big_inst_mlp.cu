@@ -9,10 +9,10 @@ template int big_resident_ctas<SGMCMC_FAMILY_MLP>(const BigModel&, size_t, int);
 
 // phase timers of this translation unit's kernel (tools/phase_timing.py)
 #if defined(SG_PHASE_TIMING) && !defined(SG_PHASE_TIMING_VEC)
-extern "C" int sgmcmc_debug_phase_cycles(unsigned long long* out16, int reset) {
+extern "C" int sgmcmc_debug_phase_cycles(unsigned long long* out32, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out16, sg::g_phase_cycles, sizeof(unsigned long long) * 16);
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(sg::g_phase_cycles, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(out32, sg::g_phase_cycles, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(sg::g_phase_cycles, z, sizeof(z)); }
   return 0;
 }
 #endif

@@ -36,7 +36,9 @@ constexpr int MLP_ROWS = 128;      // largest sub-batch (MMA M of the forward co
 #define SG_MLP_ISSUER_WARP 0
 #endif
 constexpr int MLP_THREADS = 512;   // gradient worker threads (warps 0..15); the CTA has 8 more noise-producer warps
+constexpr int MLP_STAGER_ROWS = (MLP_THREADS - 32) / 8;   // forward GEMM: rows one pass of the 480 operand-staging threads covers
 constexpr int MLP_KC = 32;         // forward K chunk (floats): one 128-byte swizzled row
+constexpr int MLP_W2S = 128;       // row stride of the staged, zero-padded copy of W_2 (>= any layer-1 width)
 constexpr size_t MLP_SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
 __host__ __device__ inline int mlp_stride(int w) { return w | 1; }   // odd row stride: conflict-free row-per-lane access
@@ -126,6 +128,15 @@ using namespace ksdtc;
 
 // barrier of the 512 gradient worker threads (the noise-producer warps are elsewhere during a likelihood pass)
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// Stage hand-over to the MMA-issuing thread (thread 0): the 15 other worker warps only ARRIVE on the stage's named barrier
+// (2 + stage) and go on to their next loads; warp 0 syncs on it and issues.  With a full barrier here every chunk cost all
+// 512 threads the ~1.4 us thread 0 needs to issue its 12 tcgen05.mma (phase timers: 34 of the 95 us of the forward GEMM).
+// One barrier per ring stage: a worker cannot arrive for chunk c + 2 before the MMAs of chunk c have retired, i.e. before
+// warp 0 has passed this barrier for chunk c, so instances never overlap.
+__device__ __forceinline__ void stage_handover(int stage, bool issuer_warp) {
+  if (issuer_warp) asm volatile("bar.sync %0, 512;" ::"r"(2 + stage) : "memory");
+  else asm volatile("bar.arrive %0, 512;" ::"r"(2 + stage) : "memory");
+}
 
 // K-major, 128-byte swizzle: rows of 32 floats, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t desc_k_sw128(uint32_t smem_addr) {
@@ -214,10 +225,19 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     const float* W1 = th + m.leaf_off[0];
     // fast path (s0 % 4 == 0, W1 at least 8-byte aligned) as its own instantiation: merged with the general path, ptxas
     // if-converts the two and leaves predicated-off spill stores that still wait for the staged loads
-    if ((s0 & 3) == 0 && (reinterpret_cast<uintptr_t>(W1) & 7) == 0) layer1_forward_impl<true>(m, ms, region, th, nb, rows, Z, zs);
-    else layer1_forward_impl<false>(m, ms, region, th, nb, rows, Z, zs);
+    const bool fast = (s0 & 3) == 0 && (reinterpret_cast<uintptr_t>(W1) & 7) == 0;
+    if (mlp_n16(m.dims[2]) <= 4 * MLP_STAGER_ROWS - MLP_ROWS) {
+      if (fast) layer1_forward_impl<true, 4>(m, ms, region, th, nb, rows, Z, zs);
+      else layer1_forward_impl<false, 4>(m, ms, region, th, nb, rows, Z, zs);
+    } else {
+      if (fast) layer1_forward_impl<true, 5>(m, ms, region, th, nb, rows, Z, zs);
+      else layer1_forward_impl<false, 5>(m, ms, region, th, nb, rows, Z, zs);
+    }
   }
-  template <bool FAST>
+  // Warp 0 only issues the MMAs; warps 1..15 (480 "stagers") move the operands.  Stager t handles 16-byte chunk t & 7 of
+  // rows (t >> 3) + 60 j, j < NI, of the stack [X rows 0..127 | W1 rows 0..s1n): NI = 4 covers s1n <= 112 (the 784-100-10
+  // network: 240 rows x 8 chunks = 480 x 4 exactly), NI = 5 the widths up to 128.
+  template <bool FAST, int NI>
   __device__ __noinline__ static void layer1_forward_impl(const BigModel& m, MlpSmem& ms, uint8_t* region, const float* th, int nb,
                                         int rows, float* Z, int zs) {
     using namespace mlptc;
@@ -235,15 +255,20 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     const int s0p8 = (s0 + 7) & ~7;
     const uint32_t idesc = idesc_tf32(s1n, false);
     const uint32_t tmem = ms.tmem_base;
-#if SG_MLP_ISSUER_WARP
-    if (tid >= MLP_THREADS) {
-      // MMA issuer (one thread of the extra warp): chunk c is in stage c & 1 once all 512 workers have arrived on
-      // ready[c & 1]; 12 MMAs per chunk and the commit that frees the stage - off the workers' critical path
-      if (tid == MLP_THREADS) {
-        uint32_t rp[2] = {ms.rparity[0], ms.rparity[1]};
-        for (int c = 0; c < n_chunks; ++c) {
-          const int st = c & 1;
-          mbar_wait(&ms.ready[st], rp[st]); rp[st] ^= 1;
+    uint32_t par[2] = {ms.parity[0], ms.parity[1]};
+    int uses[2] = {0, 0};
+
+    if (tid < 32) {
+      // MMA issuer: chunk c is in stage c & 1 once the stagers have arrived on the stage's named barrier; 12 MMAs per
+      // chunk, and the commit that frees the stage again
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+        const int st = c & 1;
+        SG_TA(ti);
+        if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }   // (already retired: the stagers waited for it)
+        stage_handover(st, true);
+        SG_TB(15, ti);
+        if (tid == 0) {
           tc_fence_after();
           uint8_t* sb = region + (size_t)st * stage_bytes;
           uint8_t* whi = sb + 2 * MLP_ROWS * 128;
@@ -251,127 +276,105 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           const uint64_t dxh = desc_k_sw128(smem_u32(sb)), dxl = desc_k_sw128(smem_u32(sb + MLP_ROWS * 128));
           const uint64_t dwh = desc_k_sw128(smem_u32(whi)), dwl = desc_k_sw128(smem_u32(whi + (size_t)s1n * 128));
           for (int sl = 0; sl < slices; ++sl) {
-            const uint64_t adv = (uint64_t)(sl * 2);
+            const uint64_t adv = (uint64_t)(sl * 2);                           // 32 bytes of K per tf32 MMA
             umma_tf32(tmem, dxl + adv, dwh + adv, idesc, (c | sl) ? 1u : 0u);
             umma_tf32(tmem, dxh + adv, dwl + adv, idesc, 1u);
             umma_tf32(tmem, dxh + adv, dwh + adv, idesc, 1u);
           }
           tc_commit(&ms.bar[st]);
         }
-        ms.rparity[0] = rp[0]; ms.rparity[1] = rp[1];
+        SG_TB(13, ti);
+        __syncwarp();
+        ++uses[st];
       }
-      return;
-    }
-#endif
-    uint32_t par[2] = {ms.parity[0], ms.parity[1]};
-
-    // this thread's items: rows tid >> 3 and (tid >> 3) + 64 of X and of W1 (if in range); 16-byte chunk tid & 7
-    const int ch = tid & 7;
-    const int r0 = tid >> 3, r1 = r0 + 64;
-    const float* xsrc0 = r0 < nb ? X + (size_t)ms.idx[r0] * s0 : nullptr;
-    const float* xsrc1 = r1 < nb ? X + (size_t)ms.idx[r1] * s0 : nullptr;
-    const float* wsrc0 = r0 < s1 ? W1 + (size_t)r0 * s0 : nullptr;
-    const float* wsrc1 = r1 < s1 ? W1 + (size_t)r1 * s0 : nullptr;
-    const bool w0_in = r0 < s1n, w1_in = r1 < s1n;
-    const uint32_t off0 = (uint32_t)r0 * 128u + (uint32_t)((ch ^ (r0 & 7)) << 4);
-    const uint32_t off1 = (uint32_t)r1 * 128u + (uint32_t)((ch ^ (r1 & 7)) << 4);
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // Fast path (s0 % 4 == 0, W1 at least 8-byte aligned): every 16-byte chunk is wholly inside or outside a row, so
-    // the loads are unconditional (clamped address, result masked) and issue back to back; a branch between two
-    // loads would serialise them on the memory latency.
-    constexpr bool fast = FAST;
-    const float* xp0 = xsrc0 ? xsrc0 : X;
-    const float* xp1 = xsrc1 ? xsrc1 : X;
-    const float* wp0 = wsrc0 ? wsrc0 : W1;
-    const float* wp1 = wsrc1 ? wsrc1 : W1;
-    auto fetch = [&](int c, float4& xv0, float4& xv1, float4& wv0, float4& wv1) {
-      const int k = c * MLP_KC + ch * 4;
-      if (fast) {
-        const int kk = min(k, s0 - 4);
-        xv0 = __ldg(reinterpret_cast<const float4*>(xp0 + kk));
-        xv1 = __ldg(reinterpret_cast<const float4*>(xp1 + kk));
-#if SG_MLP_W_LDCG   // experiment: explicit ld.global.cg (L2) instead of generic loads for the W1 operand
-        const float2 a0 = __ldcg(reinterpret_cast<const float2*>(wp0 + kk)), a1 = __ldcg(reinterpret_cast<const float2*>(wp0 + kk + 2));
-        const float2 b0 = __ldcg(reinterpret_cast<const float2*>(wp1 + kk)), b1 = __ldcg(reinterpret_cast<const float2*>(wp1 + kk + 2));
-#else
-        const float2 a0 = *reinterpret_cast<const float2*>(wp0 + kk), a1 = *reinterpret_cast<const float2*>(wp0 + kk + 2);
-        const float2 b0 = *reinterpret_cast<const float2*>(wp1 + kk), b1 = *reinterpret_cast<const float2*>(wp1 + kk + 2);
-#endif
-        wv0 = make_float4(a0.x, a0.y, a1.x, a1.y);      // NO use of the loaded values here: masking happens in step(),
-        wv1 = make_float4(b0.x, b0.y, b1.x, b1.y);      // a use right after the load would stall the thread on it
-        return;
-      }
-      const int valid = s0 - k;
-      xv0 = xsrc0 ? load4(xsrc0 + k, valid, x16, x16, true) : zero4;
-      xv1 = xsrc1 ? load4(xsrc1 + k, valid, x16, x16, true) : zero4;
-      wv0 = wsrc0 ? load4(wsrc0 + k, valid, w16, w8, false) : zero4;
-      wv1 = wsrc1 ? load4(wsrc1 + k, valid, w16, w8, false) : zero4;
-    };
-    int uses[2] = {0, 0};
-    // one pipeline step: registers of chunk c -> stage c & 1, refill the registers with chunk c + 2, issue the MMAs
-    auto step = [&](int c, float4& xv0, float4& xv1, float4& wv0, float4& wv1) {
-      const int st = c & 1;
-      uint8_t* sb = region + (size_t)st * stage_bytes;
-      uint8_t* xhi = sb;
-      uint8_t* xlo = sb + MLP_ROWS * 128;
-      uint8_t* whi = sb + 2 * MLP_ROWS * 128;
-      uint8_t* wlo = whi + (size_t)s1n * 128;
-      SG_TA(tt);
-      if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }   // MMAs of chunk c - 2 retired
-      SG_TB(9, tt);
-      if (fast) {                                                            // out-of-range rows / columns read as zero
-        const bool in = c * MLP_KC + ch * 4 < s0;
-        if (!(in && xsrc0)) xv0 = zero4;
-        if (!(in && xsrc1)) xv1 = zero4;
-        if (!(in && wsrc0)) wv0 = zero4;
-        if (!(in && wsrc1)) wv1 = zero4;
-      }
-      float4 hi, lo;
-      split4(xv0, hi, lo); *reinterpret_cast<float4*>(xhi + off0) = hi; *reinterpret_cast<float4*>(xlo + off0) = lo;
-      split4(xv1, hi, lo); *reinterpret_cast<float4*>(xhi + off1) = hi; *reinterpret_cast<float4*>(xlo + off1) = lo;
-      if (w0_in) { split4(wv0, hi, lo); *reinterpret_cast<float4*>(whi + off0) = hi; *reinterpret_cast<float4*>(wlo + off0) = lo; }
-      if (w1_in) { split4(wv1, hi, lo); *reinterpret_cast<float4*>(whi + off1) = hi; *reinterpret_cast<float4*>(wlo + off1) = lo; }
-      SG_TB(10, tt);
-      fence_proxy_async();                      // BEFORE the next loads are issued: the fence would wait for them too
-      SG_TB(11, tt);
-#if SG_MLP_ISSUER_WARP
-      tc_fence_before();
-      mbar_arrive(&ms.ready[st]);               // no barrier among the workers: the issuer warp takes it from here
-      SG_TB(12, tt);
-      if (c + 2 < n_chunks) fetch(c + 2, xv0, xv1, wv0, wv1);               // two chunks of loads stay in flight
-      SG_TB(14, tt);
-      if (false) {
-#else
-      mlptc::worker_sync();
-      SG_TB(12, tt);
-      if (c + 2 < n_chunks) fetch(c + 2, xv0, xv1, wv0, wv1);               // two chunks of loads stay in flight
-      SG_TB(14, tt);
-      if (tid == 0) {
-#endif
-        tc_fence_after();
-        const int slices = min(MLP_KC, s0p8 - c * MLP_KC) / 8;
-        const uint64_t dxh = desc_k_sw128(smem_u32(xhi)), dxl = desc_k_sw128(smem_u32(xlo));
-        const uint64_t dwh = desc_k_sw128(smem_u32(whi)), dwl = desc_k_sw128(smem_u32(wlo));
-        for (int s = 0; s < slices; ++s) {
-          const uint64_t adv = (uint64_t)(s * 2);                            // 32 bytes of K per tf32 MMA
-          umma_tf32(tmem, dxl + adv, dwh + adv, idesc, (c | s) ? 1u : 0u);
-          umma_tf32(tmem, dxh + adv, dwl + adv, idesc, 1u);
-          umma_tf32(tmem, dxh + adv, dwh + adv, idesc, 1u);
+    } else {
+      const int tw = tid - 32;
+      const int ch = tw & 7, rb = tw >> 3;
+      const float* src[NI];                 // row start (a valid address even when the row is padding)
+      uint32_t dhi[NI], dlo[NI];            // byte offsets of the hi / lo copies inside a stage
+      bool real[NI], put[NI];
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int R = rb + MLP_STAGER_ROWS * j;
+        if (R < MLP_ROWS) {
+          real[j] = R < nb;
+          src[j] = real[j] ? X + (size_t)ms.idx[R] * s0 : X;
+          put[j] = true;
+          dhi[j] = (uint32_t)R * 128u + (uint32_t)((ch ^ (R & 7)) << 4);
+          dlo[j] = dhi[j] + MLP_ROWS * 128u;
+        } else {
+          const int r = R - MLP_ROWS;
+          real[j] = r < s1;
+          src[j] = real[j] ? W1 + (size_t)r * s0 : W1;
+          put[j] = r < s1n;
+          dhi[j] = 2u * MLP_ROWS * 128u + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
+          dlo[j] = dhi[j] + (uint32_t)s1n * 128u;
         }
-        tc_commit(&ms.bar[st]);
       }
-      SG_TB(13, tt);
-      ++uses[st];
-    };
-    {
-      float4 ax0, ax1, aw0, aw1, bx0, bx1, bw0, bw1;
-      fetch(0, ax0, ax1, aw0, aw1);
-      if (n_chunks > 1) fetch(1, bx0, bx1, bw0, bw1);
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      // Fast path (s0 % 4 == 0, W1 at least 8-byte aligned): every 16-byte chunk is wholly inside or outside a row, so
+      // the loads are unconditional (clamped address, result masked in step()) and issue back to back; a branch between
+      // two loads, or a use of a loaded value, would serialise them on the memory latency.
+      auto fetch = [&](int c, float4 (&v)[NI]) {
+        const int k = c * MLP_KC + ch * 4;
+        if (FAST) {
+          const int kk = min(k, s0 - 4);
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            if (MLP_STAGER_ROWS * j + MLP_STAGER_ROWS <= MLP_ROWS) {            // always a row of X: 16-byte aligned, read-only
+              v[j] = __ldg(reinterpret_cast<const float4*>(src[j] + kk));
+            } else {
+#if SG_MLP_W_LDCG   // experiment: explicit ld.global.cg (L2) instead of generic loads for the W1 operand
+              const float2 a0 = __ldcg(reinterpret_cast<const float2*>(src[j] + kk)), a1 = __ldcg(reinterpret_cast<const float2*>(src[j] + kk + 2));
+#else
+              const float2 a0 = *reinterpret_cast<const float2*>(src[j] + kk), a1 = *reinterpret_cast<const float2*>(src[j] + kk + 2);
+#endif
+              v[j] = make_float4(a0.x, a0.y, a1.x, a1.y);
+            }
+          }
+          return;
+        }
+        const int valid = s0 - k;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const bool is_x = rb + MLP_STAGER_ROWS * j < MLP_ROWS;
+          v[j] = real[j] ? load4(src[j] + k, valid, is_x ? x16 : w16, is_x ? x16 : w8, false) : zero4;
+        }
+      };
+      // one pipeline step: registers of chunk c -> stage c & 1, hand the stage to warp 0, refill the registers with chunk c + 2
+      auto step = [&](int c, float4 (&v)[NI]) {
+        const int st = c & 1;
+        uint8_t* sb = region + (size_t)st * stage_bytes;
+        SG_TA(tt);
+        if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }   // MMAs of chunk c - 2 retired
+        SG_TBT(9, tt, 32);
+        const bool in = c * MLP_KC + ch * 4 < s0;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          if (!put[j]) continue;
+          float4 x = v[j];
+          if (FAST && !(in && real[j])) x = zero4;                               // out-of-range rows / columns read as zero
+          float4 hi, lo;
+          split4(x, hi, lo);
+          *reinterpret_cast<float4*>(sb + dhi[j]) = hi;
+          *reinterpret_cast<float4*>(sb + dlo[j]) = lo;
+        }
+        SG_TBT(10, tt, 32);
+        fence_proxy_async();                      // BEFORE the next loads are issued: the fence would wait for them too
+        SG_TBT(11, tt, 32);
+        stage_handover(st, false);
+        SG_TBT(12, tt, 32);
+        if (c + 2 < n_chunks) fetch(c + 2, v);                                 // two chunks of loads stay in flight
+        SG_TBT(14, tt, 32);
+        ++uses[st];
+      };
+      float4 a[NI], b[NI];
+      fetch(0, a);
+      if (n_chunks > 1) fetch(1, b);
 #pragma unroll 1
       for (int c = 0; c < n_chunks; c += 2) {
-        step(c, ax0, ax1, aw0, aw1);
-        if (c + 1 < n_chunks) step(c + 1, bx0, bx1, bw0, bw1);
+        step(c, a);
+        if (c + 1 < n_chunks) step(c + 1, b);
       }
     }
     for (int st = 0; st < 2; ++st)
@@ -502,7 +505,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
         if (false) {
 #else
-        mlptc::worker_sync();
+        mlptc::stage_handover(st, tid < 32);
         if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
         if (tid == 0) {
 #endif
@@ -600,17 +603,38 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     auto dzbuf = [&](int k) { return fbase + plan.dz_off(k); };
     auto dzstr = [&](int k) { return mlp_stride(plan.dz_w(k)); };
 
+    // The labels of the sub-batch (Y rows: a dependent gather from HBM) are requested before the forward GEMM and parked in
+    // the output layer's dZ buffer after it, so that the output layer finds them in shared memory.
+    float* const ybuf = dzbuf(0);
+    const int ybs = dzstr(0), wL = sz[L];
+    float ypre[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int o = tid + t * MLP_THREADS;
+      ypre[t] = o < nb * wL ? __ldg(Y + (size_t)ms.idx[o / wL] * wL + o % wL) : 0.f;
+    }
     { SG_T0(); layer1_forward(m, ms, region, th, nb, R, act(1), astr(1)); SG_T1(1); }
     SG_T0();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int o = tid + t * MLP_THREADS;
+      if (o < nb * wL) ybuf[(o / wL) * ybs + o % wL] = ypre[t];
+    }
+    for (int o = tid + 4 * MLP_THREADS; o < nb * wL; o += MLP_THREADS) ybuf[(o / wL) * ybs + o % wL] = __ldg(Y + (size_t)ms.idx[o / wL] * wL + o % wL);
     // W_2 (sz[2] x sz[1] floats, 4 KB for 784-100-10) is read by every thread of the layer-2 forward and of the dZ_1
-    // back-propagation: from global memory those loops are bound by L2 latency (measured 43 us of the 76 us "small
-    // layers" phase in the quad dZ_1 loop alone).  Stage it once per sub-batch in the part of xs the bias-gradient
-    // scratch (first 8 KB) leaves free; xs is idle until layer1_backward streams X.
+    // back-propagation: from global memory those loops are bound by L2 latency.  Stage it once per sub-batch, rows padded
+    // with zeros to MLP_W2S = 128 columns (so the loops over its columns need no bounds checks: a bounds check in front
+    // of every load becomes a branch, and a load behind a branch is not hoisted - the loop then runs at one memory
+    // latency per multiply-add), in the part of xs the bias-gradient scratch (first 8 KB) leaves free; xs is idle until
+    // layer1_backward streams X.
     float* w2s = nullptr;
-    if (L >= 2 && (size_t)sz[2] * sz[1] * sizeof(float) + 8192 <= plan.xs_bytes) {
+    if (L >= 2 && (size_t)sz[2] * MLP_W2S * sizeof(float) + 8192 <= plan.xs_bytes) {
       w2s = reinterpret_cast<float*>(xs + 8192);
       const float* W2g = th + m.leaf_off[2];
-      for (int o = tid; o < sz[2] * sz[1]; o += MLP_THREADS) w2s[o] = W2g[o];
+      for (int o = tid; o < sz[2] * MLP_W2S; o += MLP_THREADS) {
+        const int n = o / MLP_W2S, j = o % MLP_W2S;
+        w2s[o] = j < sz[1] ? W2g[n * sz[1] + j] : 0.f;
+      }
     }
 
     // =================================================================== softmax + small layers forward
@@ -618,26 +642,70 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       float* A = act(l);
       const int as = astr(l), w = sz[l];
       SG_T0();
-      if (tid < R) {                                    // a_l = softmax(z_l), one thread per row
-        float mx = -INFINITY;
-        for (int c = 0; c < w; ++c) mx = fmaxf(mx, A[tid * as + c]);
-        float sum = 0.f;
-        for (int c = 0; c < w; ++c) { const float e = expf(A[tid * as + c] - mx); A[tid * as + c] = e; sum += e; }
-        const float inv = 1.0f / sum;
-        for (int c = 0; c < w; ++c) A[tid * as + c] *= inv;
+      {                                                 // a_l = softmax(z_l): four threads per row, columns q, q + 4, ...
+        const int b = tid >> 2, q = tid & 3;
+        if (b < R) {                                    // warp-uniform: R is a multiple of 8
+          float* row = A + b * as;
+          float mx = -INFINITY;
+          for (int c = q; c < w; c += 4) mx = fmaxf(mx, row[c]);
+          mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 2));
+          float sum = 0.f;
+          for (int c = q; c < w; c += 4) { const float e = expf(row[c] - mx); row[c] = e; sum += e; }
+          sum += __shfl_xor_sync(FULL, sum, 1);
+          sum += __shfl_xor_sync(FULL, sum, 2);
+          const float inv = 1.0f / sum;
+          for (int c = q; c < w; c += 4) row[c] *= inv;
+        }
       }
       mlptc::worker_sync();
       SG_T1(4);
       float* Zn = act(l + 1);
       const int zs = astr(l + 1), wn = sz[l + 1];
-      const float* Wn = (l == 1 && w2s) ? w2s : th + m.leaf_off[2 * l];       // staged by the time of the barrier above
       const float* bn = th + m.leaf_off[2 * l + 1];
-      for (int o = tid; o < R * wn; o += MLP_THREADS) {            // z_{l+1}[b][n] = a_l[b] . W[n] + b[n]
-        const int b = o % R, n = o / R;
-        float accv = 0.f;
-        const float* wr = Wn + (size_t)n * w;
-        for (int k = 0; k < w; ++k) accv = fmaf(A[b * as + k], wr[k], accv);
-        Zn[b * zs + n] = accv + bn[n];
+      if (l == 1 && w2s) {
+        // z_2[b][n] = a_1[b] . W_2[n] + b_2[n]: row b = tid & 127, four outputs n = (tid >> 7) + 4 t at a time (the W_2 rows
+        // are warp-uniform: broadcast 16-byte reads of the staged copy)
+        const int b = tid & 127, ng = tid >> 7;
+        if (b < R) {
+          const float* arow = A + b * as;
+          for (int n0 = ng; n0 < wn; n0 += 16) {
+            const float* wr[4];
+            float accv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int n = min(n0 + 4 * t, wn - 1);
+              wr[t] = w2s + n * MLP_W2S;
+              accv[t] = bn[n];
+            }
+            int k = 0;
+            for (; k + 4 <= w; k += 4) {
+              const float a0 = arow[k], a1 = arow[k + 1], a2 = arow[k + 2], a3 = arow[k + 3];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float4 wv = *reinterpret_cast<const float4*>(wr[t] + k);
+                accv[t] = fmaf(a0, wv.x, accv[t]); accv[t] = fmaf(a1, wv.y, accv[t]);
+                accv[t] = fmaf(a2, wv.z, accv[t]); accv[t] = fmaf(a3, wv.w, accv[t]);
+              }
+            }
+            for (; k < w; ++k) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) accv[t] = fmaf(arow[k], wr[t][k], accv[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (n0 + 4 * t < wn) Zn[b * zs + n0 + 4 * t] = accv[t];
+          }
+        }
+      } else {
+        const float* Wn = th + m.leaf_off[2 * l];
+        for (int o = tid; o < R * wn; o += MLP_THREADS) {            // z_{l+1}[b][n] = a_l[b] . W[n] + b[n]
+          const int b = o % R, n = o / R;
+          float accv = 0.f;
+          const float* wr = Wn + (size_t)n * w;
+          for (int k = 0; k < w; ++k) accv = fmaf(A[b * as + k], wr[k], accv);
+          Zn[b * zs + n] = accv + bn[n];
+        }
       }
       mlptc::worker_sync();
       SG_T1(5);
@@ -652,19 +720,19 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       const float* Z = act(L);
       if (tid < R) {
         if (tid < nb) {
-          const float* yr = Y + (size_t)ms.idx[tid] * w;
+          const float* yr = dz + tid * dzs;            // the labels parked here after the forward GEMM; overwritten by dZ_L
           float mx = -INFINITY, ys = 0.f;
-          for (int c = 0; c < w; ++c) { mx = fmaxf(mx, Z[tid * zs + c]); ys += __ldg(yr + c); }
+          for (int c = 0; c < w; ++c) { mx = fmaxf(mx, Z[tid * zs + c]); ys += yr[c]; }
           float sum = 0.f;
           for (int c = 0; c < w; ++c) sum += expf(Z[tid * zs + c] - mx);
           const float inv = ys / sum;
-          for (int c = 0; c < w; ++c) dz[tid * dzs + c] = __ldg(yr + c) - inv * expf(Z[tid * zs + c] - mx);
           if (lp) {                                    // loglik = sum_c y_c log_softmax(z)_c  (NN_model.py:48-50)
             const float lse = mx + logf(sum);
             float v = 0.f;
-            for (int c = 0; c < w; ++c) v = fmaf(__ldg(yr + c), Z[tid * zs + c] - lse, v);
+            for (int c = 0; c < w; ++c) v = fmaf(yr[c], Z[tid * zs + c] - lse, v);
             atomicAdd(lp, v);
           }
+          for (int c = 0; c < w; ++c) dz[tid * dzs + c] = yr[c] - inv * expf(Z[tid * zs + c] - mx);
         } else {
           for (int c = 0; c < w; ++c) dz[tid * dzs + c] = 0.f;      // padded rows contribute nothing
         }
@@ -689,16 +757,28 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       float* gW = g + m.leaf_off[2 * (l - 1)];
       float* gb = g + m.leaf_off[2 * (l - 1) + 1];
       SG_T0();
-      for (int o = tid; o < w * wp; o += MLP_THREADS) {             // dW_l[n][k] = sum_b dz[b][n] a_{l-1}[b][k]
-        const int k = o % wp, n = o / wp;
-        float accv = 0.f;
-        for (int b = 0; b < nb; ++b) accv = fmaf(dz[b * dzs + n], A[b * as + k], accv);
-        gW[o] += sign * accv;
+      // dW_l[n][k] = sum_b dz[b][n] a_{l-1}[b][k]: two rows n per item (independent accumulation chains), the old values
+      // requested before the loop; the bias sums go to the threads at the far end, which have the fewest items
+      const int npairs = (w + 1) >> 1;
+      for (int o = tid; o < npairs * wp; o += MLP_THREADS) {
+        const int k = o % wp, n0 = 2 * (o / wp), n1 = min(n0 + 1, w - 1);
+        const float old0 = gW[n0 * wp + k], old1 = gW[n1 * wp + k];
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+        for (int b = 0; b < nb; ++b) {
+          const float a = A[b * as + k];
+          acc0 = fmaf(dz[b * dzs + n0], a, acc0);
+          acc1 = fmaf(dz[b * dzs + n1], a, acc1);
+        }
+        gW[n0 * wp + k] = fmaf(sign, acc0, old0);
+        if (n1 != n0) gW[n1 * wp + k] = fmaf(sign, acc1, old1);
       }
-      for (int n = tid; n < w; n += MLP_THREADS) {
+      for (int n = MLP_THREADS - 1 - tid; n < w; n += MLP_THREADS) {
+        const float old0 = gb[n];
         float accv = 0.f;
+#pragma unroll 4
         for (int b = 0; b < nb; ++b) accv += dz[b * dzs + n];
-        gb[n] += sign * accv;
+        gb[n] = fmaf(sign, accv, old0);
       }
       SG_T1(7);
       if (l > 2) {
@@ -720,49 +800,114 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         mlptc::worker_sync();
         dz = dn; dzs = dns; cur ^= 1;
       } else {
-        // l == 2: dZ_1 of row b by a quad of threads (columns j = q, q + 4, ...), written straight into the
-        // tensor-core operand (hi / lo); bias gradient by fixed-order shuffles + a per-warp fold.
+        // l == 2: dZ_1 of row b by a quad of threads, written straight into the tensor-core operand (hi / lo); bias
+        // gradient by fixed-order shuffles + a per-warp fold.
         const int b = tid >> 2, q = tid & 3;
         const bool live = b < nb;
         const int warp = tid >> 5, lane = tid & 31;
-        // dA[b][j] = sum_n dz[b][n] W_2[n][j] for this thread's columns j = q + 4 i: one sweep over n, 32 accumulators
-        float da[32];
+        SG_TA(tq);
+        if (w2s) {
+          // thread q of the quad owns the 16-byte column chunks q, q + 4, ...: columns j = 16 t + 4 q + e.  All 128 columns
+          // of the padded W_2 copy are swept (zeros beyond s1), so no load sits behind a bounds check.
+          // dA[b][j] = sum_n dz[b][n] W_2[n][j]: one sweep over n, 32 accumulators
+          float da[8][4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) da[i] = 0.f;
-        if (live) {
-#pragma unroll 1
-          for (int n = 0; n < w; ++n) {
-            const float dzn = dz[b * dzs + n];
-            const float* wrow = Wl + (size_t)n * wp + q;
+          for (int t = 0; t < 8; ++t) da[t][0] = da[t][1] = da[t][2] = da[t][3] = 0.f;
+          if (live) {
+#pragma unroll 2
+            for (int n = 0; n < w; ++n) {
+              const float dzn = dz[b * dzs + n];
+              const float4* wrow = reinterpret_cast<const float4*>(w2s + n * MLP_W2S) + q;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (4 * i < s1n) da[i] = fmaf(dzn, 4 * i + q < wp ? wrow[4 * i] : 0.f, da[i]);
+              for (int t = 0; t < 8; ++t) {
+                const float4 wv = wrow[4 * t];
+                da[t][0] = fmaf(dzn, wv.x, da[t][0]); da[t][1] = fmaf(dzn, wv.y, da[t][1]);
+                da[t][2] = fmaf(dzn, wv.z, da[t][2]); da[t][3] = fmaf(dzn, wv.w, da[t][3]);
+              }
+            }
           }
-        }
-        float dotv = 0.f;
+          SG_TB(16, tq);
+          // (reads of a_1 beyond its row stay inside the activation buffers; they are discarded by the select)
+          const float* arow = A + (live ? b : 0) * as;
+          float dotv = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (4 * i < s1n) dotv = fmaf((live && 4 * i + q < wp) ? A[b * as + 4 * i + q] : 0.f, da[i], dotv);
-        dotv += __shfl_xor_sync(FULL, dotv, 1);
-        dotv += __shfl_xor_sync(FULL, dotv, 2);
+          for (int t = 0; t < 8; ++t)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int j = q + 4 * i;
-          if (4 * i < s1n) {                                       // warp-uniform
-            float v = (live && j < wp) ? A[b * as + j] * (da[i] - dotv) : 0.f;
-            if (b < R) put_dz1(bhi, blo, b, j, v);
-            v += __shfl_xor_sync(FULL, v, 4);
-            v += __shfl_xor_sync(FULL, v, 8);
-            v += __shfl_xor_sync(FULL, v, 16);
-            if (lane < 4) red[warp * 128 + j] = v;
+            for (int e = 0; e < 4; ++e) {
+              const int j = 16 * t + 4 * q + e;
+              const float av = arow[j];
+              dotv = fmaf(j < wp ? av : 0.f, da[t][e], dotv);
+            }
+          dotv += __shfl_xor_sync(FULL, dotv, 1);
+          dotv += __shfl_xor_sync(FULL, dotv, 2);
+          SG_TB(17, tq);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int j0 = 16 * t + 4 * q;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float av = arow[j0 + e];
+              v[e] = (live && j0 + e < wp) ? av * (da[t][e] - dotv) : 0.f;
+            }
+            if (b < R) {                                           // columns in [s1n, 128) land in the operand's padding
+              const uint32_t off = (uint32_t)(b >> 3) * 4096u + (uint32_t)(j0 >> 5) * 1024u + mlptc::mn_chunk_off(b & 7, (j0 & 31) >> 2);
+              float4 hi, lo;
+              mlptc::split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+              *reinterpret_cast<float4*>(bhi + off) = hi;
+              *reinterpret_cast<float4*>(blo + off) = lo;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[e] += __shfl_xor_sync(FULL, v[e], 4);
+              v[e] += __shfl_xor_sync(FULL, v[e], 8);
+              v[e] += __shfl_xor_sync(FULL, v[e], 16);
+            }
+            if (lane < 4) *reinterpret_cast<float4*>(red + warp * 128 + j0) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+          SG_TB(18, tq);
+        } else {
+          // W_2 too large to stage: columns j = q, q + 4, ... of the global copy
+          float da[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) da[i] = 0.f;
+          if (live) {
+#pragma unroll 1
+            for (int n = 0; n < w; ++n) {
+              const float dzn = dz[b * dzs + n];
+              const float* wrow = Wl + (size_t)n * wp + q;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (4 * i < s1n) da[i] = fmaf(dzn, 4 * i + q < wp ? wrow[4 * i] : 0.f, da[i]);
+            }
+          }
+          float dotv = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (4 * i < s1n) dotv = fmaf((live && 4 * i + q < wp) ? A[b * as + 4 * i + q] : 0.f, da[i], dotv);
+          dotv += __shfl_xor_sync(FULL, dotv, 1);
+          dotv += __shfl_xor_sync(FULL, dotv, 2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = q + 4 * i;
+            if (4 * i < s1n) {                                       // warp-uniform
+              float v = (live && j < wp) ? A[b * as + j] * (da[i] - dotv) : 0.f;
+              if (b < R) put_dz1(bhi, blo, b, j, v);
+              v += __shfl_xor_sync(FULL, v, 4);
+              v += __shfl_xor_sync(FULL, v, 8);
+              v += __shfl_xor_sync(FULL, v, 16);
+              if (lane < 4) red[warp * 128 + j] = v;
+            }
           }
         }
         mlptc::worker_sync();
+        SG_TB(19, tq);
         for (int n = tid; n < s1; n += MLP_THREADS) {
           float accv = 0.f;
           for (int w16 = 0; w16 < 16; ++w16) accv += red[w16 * 128 + n];
           gb1[n] += sign * accv;
         }
+        SG_TB(20, tq);
         SG_T1(8);
       }
     }

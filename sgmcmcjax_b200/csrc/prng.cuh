@@ -19,8 +19,10 @@ static __device__ unsigned long long g_phase_cycles[32];   // per translation un
 #define SG_T0() const long long sg_t0__ = clock64()
 #define SG_T1(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_phase_cycles[slot], (unsigned long long)(clock64() - sg_t0__)); } while (0)
 #define SG_TA(var) long long var = clock64()
-#define SG_TB(slot, var) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long n__ = clock64(); atomicAdd(&g_phase_cycles[slot], (unsigned long long)(n__ - var)); var = n__; } } while (0)
+#define SG_TBT(slot, var, t) do { if (blockIdx.x == 0 && threadIdx.x == (t)) { const long long n__ = clock64(); atomicAdd(&g_phase_cycles[slot], (unsigned long long)(n__ - var)); var = n__; } } while (0)
+#define SG_TB(slot, var) SG_TBT(slot, var, 0)
 #else
+#define SG_TBT(slot, var, t) do {} while (0)
 #define SG_T0() do {} while (0)
 #define SG_T1(slot) do {} while (0)
 #define SG_TA(var) do {} while (0)
