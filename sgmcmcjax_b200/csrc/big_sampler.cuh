@@ -51,10 +51,7 @@ template <int FAMILY> struct BigThreads { static constexpr int value = SG_BIG_TH
 #ifndef SG_MLP_PRODUCER_WARPS
 #define SG_MLP_PRODUCER_WARPS 0
 #endif
-#ifndef SG_MLP_ISSUER_WARP
-#define SG_MLP_ISSUER_WARP 0
-#endif
-template <> struct BigThreads<SGMCMC_FAMILY_MLP> { static constexpr int value = 512 + 32 * (SG_MLP_PRODUCER_WARPS + SG_MLP_ISSUER_WARP); static constexpr int min_blocks = 1; };
+template <> struct BigThreads<SGMCMC_FAMILY_MLP> { static constexpr int value = 512 + 32 * SG_MLP_PRODUCER_WARPS; static constexpr int min_blocks = 1; };
 
 struct BigModel {
   int family, estimator, diffusion, flags;

@@ -30,11 +30,6 @@ constexpr int MLP_ROWS = 128;      // largest sub-batch (MMA M of the forward co
 #ifndef SG_MLP_W_LDCG
 #define SG_MLP_W_LDCG 0
 #endif
-// SG_MLP_ISSUER_WARP: a 17th warp issues every tcgen05.mma of the two layer-1 GEMMs; the 512 workers hand a filled stage
-// over with an mbarrier arrive instead of a block barrier followed by thread 0 issuing 12 MMAs while 511 threads wait
-#ifndef SG_MLP_ISSUER_WARP
-#define SG_MLP_ISSUER_WARP 0
-#endif
 constexpr int MLP_THREADS = 512;   // gradient worker threads (warps 0..15); the CTA has 8 more noise-producer warps
 constexpr int MLP_STAGER_ROWS = (MLP_THREADS - 32) / 8;   // forward GEMM: rows one pass of the 480 operand-staging threads covers
 constexpr int MLP_KC = 32;         // forward K chunk (floats): one 128-byte swizzled row
@@ -45,10 +40,8 @@ __host__ __device__ inline int mlp_stride(int w) { return w | 1; }   // odd row 
 __host__ __device__ inline int mlp_n16(int w) { return (w + 15) & ~15; }
 
 struct MlpSmem {
-  uint64_t bar[2];             // stage-free barriers (tcgen05.commit arrives)
-  uint64_t ready[2];           // stage-filled barriers: one arrival per worker thread (SG_MLP_ISSUER_WARP)
-  uint32_t parity[2];          // next phase parity of bar[], carried from one GEMM to the next (worker side)
-  uint32_t rparity[2];         // next phase parity of ready[] (issuer side)
+  uint64_t bar[4];             // stage-free barriers (tcgen05.commit arrives): forward ring 2 stages, backward ring 2 or 4
+  uint32_t parity[4];          // next phase parity of bar[], carried from one GEMM to the next
   uint32_t tmem_base;
   uint32_t pad;
   int idx[MLP_ROWS];
@@ -199,10 +192,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
   __device__ static void cta_init(const BigModel& m, void* fam_smem) {
     MlpSmem& ms = *reinterpret_cast<MlpSmem*>(fam_smem);
     if (threadIdx.x == 0) {
-      mlptc::mbar_init(&ms.bar[0], 1); mlptc::mbar_init(&ms.bar[1], 1);
-      mlptc::mbar_init(&ms.ready[0], MLP_THREADS); mlptc::mbar_init(&ms.ready[1], MLP_THREADS);
-      ms.parity[0] = ms.parity[1] = 0;
-      ms.rparity[0] = ms.rparity[1] = 0;
+      for (int i = 0; i < 4; ++i) { mlptc::mbar_init(&ms.bar[i], 1); ms.parity[i] = 0; }
       mlptc::fence_barrier_init();
     }
     if (threadIdx.x < 32) { mlptc::tmem_alloc(&ms.tmem_base, (uint32_t)mlp_plan(m.dims, m.batch).tmem_cols); mlptc::tmem_relinquish(); }
@@ -414,8 +404,8 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
   }
 
   // gW1[n][k] += sign * sum_b dZ1[b][n] X[b][k]   (dZ1 hi / lo already staged in `region`)
-  __device__ __noinline__ static void layer1_backward(const BigModel& m, MlpSmem& ms, uint8_t* region, uint8_t* xs, float sign,
-                                         int nb, int rows, float* gW, bool overwrite) {
+  __device__ __noinline__ static void layer1_backward(const BigModel& m, MlpSmem& ms, uint8_t* region, uint8_t* xs, uint8_t* spare,
+                                         float sign, int nb, int rows, float* gW, bool overwrite) {
     using namespace mlptc;
     const int s0 = m.dims[1], s1 = m.dims[2];
     const int s1n = mlp_n16(s1);
@@ -429,41 +419,13 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     const uint32_t tmem = ms.tmem_base;
     const uint8_t* bhi = region;
     const uint8_t* blo = region + (size_t)(rows / 8) * 4096;
-    const size_t stage_bytes = 2 * 8 * 256 * sizeof(float);      // [hi 8 KB | lo 8 KB]
-#if SG_MLP_ISSUER_WARP
-    if (tid >= MLP_THREADS) {
-      if (tid == MLP_THREADS) {                                   // MMA issuer, as in layer1_forward
-        uint32_t rp[2] = {ms.rparity[0], ms.rparity[1]};
-        for (int t0 = 0; t0 < n_tiles; t0 += tiles_per_pass) {
-          const int pass_tiles = min(tiles_per_pass, n_tiles - t0);
-          const int npp = (pass_tiles + 1) >> 1;
-          const int units = G * npp;
-          for (int u = 0; u < units; ++u) {
-            const int st = u & 1;
-            mbar_wait(&ms.ready[st], rp[st]); rp[st] ^= 1;
-            tc_fence_after();
-            const uint8_t* sb = xs + (size_t)st * stage_bytes;
-            const int g = u / npp, p = u - g * npp;
-            const uint64_t dbh = desc_mn_sw128_32b(smem_u32(bhi) + (uint32_t)g * 4096u, 1024u, 512u);
-            const uint64_t dbl = desc_mn_sw128_32b(smem_u32(blo) + (uint32_t)g * 4096u, 1024u, 512u);
-            for (int t = 0; t < 2; ++t) {
-              if (2 * p + t >= pass_tiles) break;
-              const uint64_t dah = desc_mn_sw128_32b(smem_u32(sb) + (uint32_t)t * 4096u, 1024u, 512u);
-              const uint64_t dal = desc_mn_sw128_32b(smem_u32(sb) + 8192u + (uint32_t)t * 4096u, 1024u, 512u);
-              const uint32_t acc = tmem + (uint32_t)((2 * p + t) * s1n);
-              umma_tf32(acc, dal, dbh, idesc, g ? 1u : 0u);
-              umma_tf32(acc, dah, dbl, idesc, 1u);
-              umma_tf32(acc, dah, dbh, idesc, 1u);
-            }
-            tc_commit(&ms.bar[st]);
-          }
-        }
-        ms.rparity[0] = rp[0]; ms.rparity[1] = rp[1];
-      }
-      return;
-    }
-#endif
-    uint32_t par[2] = {ms.parity[0], ms.parity[1]};
+    constexpr uint32_t stage_bytes = 2 * 8 * 256 * sizeof(float);      // [hi 8 KB | lo 8 KB]
+    // Stage ring: the two stages of xs, plus two more in `spare` (the activation buffers, dead by now) when they fit.
+    // One unit's chain - wait for the stage, st.shared, fence, hand-over, 6 MMAs, commit - is ~3 us of latencies; the
+    // depth of the ring is how many of them overlap.
+    const int nst = spare ? 4 : 2;
+    auto stage_ptr = [&](int st) { return st < 2 ? xs + (size_t)st * stage_bytes : spare + (size_t)(st - 2) * stage_bytes; };
+    uint32_t par = ms.parity[0] | ms.parity[1] << 1 | ms.parity[2] << 2 | ms.parity[3] << 3;   // bit st: next phase parity of bar[st]
 
     // loader mapping for one unit = 8 batch rows x 256 columns: row tid >> 6, 16-byte chunk tid & 63
     const int lr = tid >> 6, c4 = tid & 63;
@@ -484,12 +446,12 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b < nb && k < s0) xv = load4(X + (size_t)ms.idx[b] * s0 + k, s0 - k, x16, x16, true);
       };
-      int uses[2] = {0, 0};
+      uint32_t used = 0;                                          // bit st: stage st has MMAs in flight
       // one pipeline step: registers of unit u -> stage u & 1, refill them with unit u + 4, issue the MMAs
       auto step = [&](int u, float4& xv) {
-        const int st = u & 1;
-        uint8_t* sb = xs + (size_t)st * stage_bytes;
-        if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }
+        const int st = u & (nst - 1);
+        uint8_t* sb = stage_ptr(st);
+        if (used >> st & 1) { mbar_wait(&ms.bar[st], par >> st & 1); par ^= 1u << st; }
         if (x16) {
           const int g = u / npp, p = u - g * npp;
           if (!(g * 8 + lr < nb && (t0 + 2 * p) * 128 + c4 * 4 < s0)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -499,16 +461,9 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         *reinterpret_cast<float4*>(sb + soff) = hi;
         *reinterpret_cast<float4*>(sb + 8192 + soff) = lo;
         fence_proxy_async();                                   // before the next load is issued (the fence would wait for it)
-#if SG_MLP_ISSUER_WARP
-        tc_fence_before();
-        mbar_arrive(&ms.ready[st]);
-        if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
-        if (false) {
-#else
         mlptc::stage_handover(st, tid < 32);
         if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
         if (tid == 0) {
-#endif
           tc_fence_after();
           const int g = u / npp, p = u - g * npp;
           const uint64_t dbh = desc_mn_sw128_32b(smem_u32(bhi) + (uint32_t)g * 4096u, 1024u, 512u);
@@ -524,7 +479,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           }
           tc_commit(&ms.bar[st]);
         }
-        ++uses[st];
+        used |= 1u << st;
       };
       {
         float4 x0, x1, x2, x3;
@@ -540,8 +495,8 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           if (u + 3 < units) step(u + 3, x3);
         }
       }
-      for (int st = 0; st < 2; ++st)
-        if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }
+      for (int st = 0; st < 4; ++st)
+        if (used >> st & 1) { mbar_wait(&ms.bar[st], par >> st & 1); par ^= 1u << st; }
       tc_fence_after();
       // epilogue: warp group (warp >> 2) owns tile t0 + (warp >> 2); lane = input column k, TMEM column = unit n
       {
@@ -574,7 +529,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       tc_fence_before();
       mlptc::worker_sync();                                            // TMEM tiles are free for the next pass
     }
-    if (tid == 0) { ms.parity[0] = par[0]; ms.parity[1] = par[1]; }
+    if (tid == 0) { ms.parity[0] = par & 1; ms.parity[1] = par >> 1 & 1; ms.parity[2] = par >> 2 & 1; ms.parity[3] = par >> 3 & 1; }
     mlptc::worker_sync();
   }
 
@@ -590,13 +545,6 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     const int R = plan.rows;
     uint8_t* region = base;
     uint8_t* xs = base + plan.region_bytes;
-#if SG_MLP_ISSUER_WARP
-    if (tid >= MLP_THREADS) {                         // the issuer warp only takes part in the two tensor-core phases
-      layer1_forward(m, ms, region, th, nb, R, nullptr, 0);
-      layer1_backward(m, ms, region, xs, sign, nb, R, g + m.leaf_off[0], overwrite);
-      return;
-    }
-#endif
     float* fbase = reinterpret_cast<float*>(xs + plan.xs_bytes);
     auto act = [&](int l) { return fbase + plan.act_off(l); };
     auto astr = [&](int l) { return mlp_stride(sz[l]); };
@@ -926,13 +874,16 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     mlptc::worker_sync();
 
     SG_T1(2);
-    { SG_T0(); layer1_backward(m, ms, region, xs, sign, nb, R, g + m.leaf_off[0], overwrite); SG_T1(3); }
+    // the fp32 activation / dZ buffers are dead from here on: two more X stages for layer1_backward if they hold them
+    uint8_t* spare = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fbase) + 1023) & ~(uintptr_t)1023);
+    if (spare + 2 * (2 * 8 * 256 * sizeof(float)) > base + plan.total_bytes - 1024) spare = nullptr;
+    { SG_T0(); layer1_backward(m, ms, region, xs, spare, sign, nb, R, g + m.leaf_off[0], overwrite); SG_T1(3); }
   }
 
   __device__ static void lik_pass(const BigModel& m, void* fam_smem, const float* theta, const float* center,
                                   bool sequential, const RandintPlan& plan, unsigned seq_base, unsigned count, float* g,
                                   bool fresh, const NoiseJob& job, float* lp = nullptr, bool /*compact*/ = false) {
-    if (!SG_MLP_ISSUER_WARP && threadIdx.x >= MLP_THREADS) {
+    if (threadIdx.x >= MLP_THREADS) {
       // noise-producer warps: the Gaussian draws of the NEXT diffusion update (its key tree is data independent,
       // diffusion_util.py:66), generated while the worker warps run the GEMM phase; the caller's __syncthreads() after
       // the pass publishes them
@@ -949,16 +900,6 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(&ms + 1) + 1023) & ~(uintptr_t)1023);
     const unsigned rows = (unsigned)mlp_plan(m.dims, m.batch).rows;
     const unsigned h = (count + 1u) >> 1;
-#if SG_MLP_ISSUER_WARP
-    if (threadIdx.x >= MLP_THREADS) {                 // issuer warp: same sub-batch sequence, tensor-core phases only
-      for (unsigned base_row = 0; base_row < count; base_row += rows) {
-        const int nb = (int)min(rows, count - base_row);
-        sub_batch(m, ms, base, theta, 1.0f, nb, g, fresh && base_row == 0, nullptr);
-        if (center) sub_batch(m, ms, base, center, -1.0f, nb, g, false, nullptr);
-      }
-      return;
-    }
-#endif
     for (unsigned base_row = 0; base_row < count; base_row += rows) {
       const int nb = (int)min(rows, count - base_row);
       mlptc::worker_sync();
