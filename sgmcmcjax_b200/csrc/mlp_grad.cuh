@@ -451,7 +451,9 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       auto step = [&](int u, float4& xv) {
         const int st = u & (nst - 1);
         uint8_t* sb = stage_ptr(st);
+        SG_TA(tb);
         if (used >> st & 1) { mbar_wait(&ms.bar[st], par >> st & 1); par ^= 1u << st; }
+        SG_TB(21, tb);
         if (x16) {
           const int g = u / npp, p = u - g * npp;
           if (!(g * 8 + lr < nb && (t0 + 2 * p) * 128 + c4 * 4 < s0)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -460,9 +462,13 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         split4(xv, hi, lo);
         *reinterpret_cast<float4*>(sb + soff) = hi;
         *reinterpret_cast<float4*>(sb + 8192 + soff) = lo;
+        SG_TB(22, tb);
         fence_proxy_async();                                   // before the next load is issued (the fence would wait for it)
+        SG_TB(23, tb);
         mlptc::stage_handover(st, tid < 32);
+        SG_TB(24, tb);
         if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
+        SG_TB(25, tb);
         if (tid == 0) {
           tc_fence_after();
           const int g = u / npp, p = u - g * npp;
@@ -479,6 +485,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           }
           tc_commit(&ms.bar[st]);
         }
+        SG_TB(26, tb);
         used |= 1u << st;
       };
       {
@@ -495,9 +502,11 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           if (u + 3 < units) step(u + 3, x3);
         }
       }
+      SG_TA(te);
       for (int st = 0; st < 4; ++st)
         if (used >> st & 1) { mbar_wait(&ms.bar[st], par >> st & 1); par ^= 1u << st; }
       tc_fence_after();
+      SG_TB(27, te);
       // epilogue: warp group (warp >> 2) owns tile t0 + (warp >> 2); lane = input column k, TMEM column = unit n
       {
         const int warp = tid >> 5, lane = tid & 31;
@@ -526,8 +535,10 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           }
         }
       }
+      SG_TB(28, te);
       tc_fence_before();
       mlptc::worker_sync();                                            // TMEM tiles are free for the next pass
+      SG_TB(29, te);
     }
     if (tid == 0) { ms.parity[0] = par & 1; ms.parity[1] = par >> 1 & 1; ms.parity[2] = par >> 2 & 1; ms.parity[3] = par >> 3 & 1; }
     mlptc::worker_sync();

@@ -17,7 +17,10 @@ names = ["diffuse passes", "layer-1 forward GEMM", "small layers (softmax, layer
          "  fwd stager: wait stage free (MMA c-2)", "  fwd stager: mask + split + st.shared (incl. wait for the loads)",
          "  fwd stager: fence.proxy.async", "  fwd stager: barrier arrive", "  fwd issuer: MMA issue + commit",
          "  fwd stager: issue loads c+2", "  fwd issuer: wait for the stage",
-         "  dZ1 quad: dA sweep", "  dZ1 quad: softmax dot", "  dZ1 quad: operand stores + db1 shuffles", "  dZ1 quad: barrier", "  dZ1 quad: db1 fold"]
+         "  dZ1 quad: dA sweep", "  dZ1 quad: softmax dot", "  dZ1 quad: operand stores + db1 shuffles", "  dZ1 quad: barrier", "  dZ1 quad: db1 fold",
+         "  bwd thread 0: wait stage free", "  bwd thread 0: mask + split + st.shared (incl. wait for the load)", "  bwd thread 0: fence.proxy.async",
+         "  bwd thread 0: hand-over barrier", "  bwd thread 0: issue load u+4", "  bwd thread 0: MMA issue + commit",
+         "  bwd: wait for the last MMAs", "  bwd: epilogue (TMEM -> gW1)", "  bwd: barrier after the epilogue"]
 steps = 3 * 4
 for n, v in zip(names, buf):
     print(f"{n:40s} {v / steps / 1.965e3:8.1f} us per chain-step (block 0)")
