@@ -30,6 +30,9 @@ constexpr int MLP_ROWS = 128;      // largest sub-batch (MMA M of the forward co
 #ifndef SG_MLP_W_LDCG
 #define SG_MLP_W_LDCG 0
 #endif
+#ifndef SG_MLP_FWD_DEPTH
+#define SG_MLP_FWD_DEPTH 1         // chunks of operand loads a stager thread keeps in flight in the forward GEMM (1 or 2)
+#endif
 constexpr int MLP_THREADS = 512;   // gradient worker threads (warps 0..15); the CTA has 8 more noise-producer warps
 constexpr int MLP_STAGER_ROWS = (MLP_THREADS - 32) / 8;   // forward GEMM: rows one pass of the 480 operand-staging threads covers
 constexpr int MLP_KC = 32;         // forward K chunk (floats): one 128-byte swizzled row
@@ -281,24 +284,24 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       const int tw = tid - 32;
       const int ch = tw & 7, rb = tw >> 3;
       const float* src[NI];                 // row start (a valid address even when the row is padding)
-      uint32_t dhi[NI], dlo[NI];            // byte offsets of the hi / lo copies inside a stage
-      bool real[NI], put[NI];
+      uint32_t dhi[NI];                     // byte offset of the hi copy inside a stage (the lo copy: lo_delta(j) further)
+      uint32_t flags = 0;                   // bit 2j: the row exists (else it reads as zero); bit 2j + 1: it is stored at all
+      auto is_x = [&](int j) { return rb + MLP_STAGER_ROWS * j < MLP_ROWS; };
+      auto lo_delta = [&](int j) { return is_x(j) ? (uint32_t)MLP_ROWS * 128u : (uint32_t)s1n * 128u; };
 #pragma unroll
       for (int j = 0; j < NI; ++j) {
         const int R = rb + MLP_STAGER_ROWS * j;
         if (R < MLP_ROWS) {
-          real[j] = R < nb;
-          src[j] = real[j] ? X + (size_t)ms.idx[R] * s0 : X;
-          put[j] = true;
+          const bool real = R < nb;
+          src[j] = real ? X + (size_t)ms.idx[R] * s0 : X;
+          flags |= (real ? 1u : 0u) << (2 * j) | 2u << (2 * j);
           dhi[j] = (uint32_t)R * 128u + (uint32_t)((ch ^ (R & 7)) << 4);
-          dlo[j] = dhi[j] + MLP_ROWS * 128u;
         } else {
           const int r = R - MLP_ROWS;
-          real[j] = r < s1;
-          src[j] = real[j] ? W1 + (size_t)r * s0 : W1;
-          put[j] = r < s1n;
+          const bool real = r < s1;
+          src[j] = real ? W1 + (size_t)r * s0 : W1;
+          flags |= (real ? 1u : 0u) << (2 * j) | (r < s1n ? 2u : 0u) << (2 * j);
           dhi[j] = 2u * MLP_ROWS * 128u + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
-          dlo[j] = dhi[j] + (uint32_t)s1n * 128u;
         }
       }
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -327,8 +330,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         const int valid = s0 - k;
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
-          const bool is_x = rb + MLP_STAGER_ROWS * j < MLP_ROWS;
-          v[j] = real[j] ? load4(src[j] + k, valid, is_x ? x16 : w16, is_x ? x16 : w8, false) : zero4;
+          v[j] = (flags >> (2 * j) & 1) ? load4(src[j] + k, valid, is_x(j) ? x16 : w16, is_x(j) ? x16 : w8, false) : zero4;
         }
       };
       // one pipeline step: registers of chunk c -> stage c & 1, hand the stage to warp 0, refill the registers with chunk c + 2
@@ -341,23 +343,28 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         const bool in = c * MLP_KC + ch * 4 < s0;
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
-          if (!put[j]) continue;
+          if (!(flags >> (2 * j) & 2)) continue;
           float4 x = v[j];
-          if (FAST && !(in && real[j])) x = zero4;                               // out-of-range rows / columns read as zero
+          if (FAST && !(in && (flags >> (2 * j) & 1))) x = zero4;                // out-of-range rows / columns read as zero
           float4 hi, lo;
           split4(x, hi, lo);
           *reinterpret_cast<float4*>(sb + dhi[j]) = hi;
-          *reinterpret_cast<float4*>(sb + dlo[j]) = lo;
+          *reinterpret_cast<float4*>(sb + dhi[j] + lo_delta(j)) = lo;
         }
         SG_TBT(10, tt, 32);
         fence_proxy_async();                      // BEFORE the next loads are issued: the fence would wait for them too
         SG_TBT(11, tt, 32);
         stage_handover(st, false);
         SG_TBT(12, tt, 32);
+#if SG_MLP_FWD_DEPTH == 2
         if (c + 2 < n_chunks) fetch(c + 2, v);                                 // two chunks of loads stay in flight
+#else
+        if (c + 1 < n_chunks) fetch(c + 1, v);                                 // the next chunk's loads fly during the hand-over + wait
+#endif
         SG_TBT(14, tt, 32);
         ++uses[st];
       };
+#if SG_MLP_FWD_DEPTH == 2
       float4 a[NI], b[NI];
       fetch(0, a);
       if (n_chunks > 1) fetch(1, b);
@@ -366,6 +373,18 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         step(c, a);
         if (c + 1 < n_chunks) step(c + 1, b);
       }
+#else
+      // ONE chunk of loads in flight per thread: with two (32 registers of prefetched values) the compiler spills the
+      // values it has just loaded - the spill store waits for the load, and the "prefetch" runs at one memory latency per
+      // chunk (ncu source view: 7 % of the kernel's stall samples on STL instructions right behind the loads)
+      float4 a[NI];
+      fetch(0, a);
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; c += 2) {
+        step(c, a);
+        if (c + 1 < n_chunks) step(c + 1, a);
+      }
+#endif
     }
     for (int st = 0; st < 2; ++st)
       if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }
@@ -404,14 +423,23 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
   }
 
   // gW1[n][k] += sign * sum_b dZ1[b][n] X[b][k]   (dZ1 hi / lo already staged in `region`)
-  __device__ __noinline__ static void layer1_backward(const BigModel& m, MlpSmem& ms, uint8_t* region, uint8_t* xs, uint8_t* spare,
+  __device__ __forceinline__ static void layer1_backward(const BigModel& m, MlpSmem& ms, uint8_t* region, uint8_t* xs, uint8_t* spare,
+                                         float sign, int nb, int rows, float* gW, bool overwrite) {
+    // the 16-byte-aligned table (s0 % 4 == 0) as its own instantiation, for the reason given in layer1_forward: merged
+    // with the element-wise general path the prefetched float4 lives in local memory, and the store that puts it there
+    // waits for the load (ncu source view: STL.64 right behind LDG.E.128, 2.5 % of the kernel's stall samples)
+    if ((m.dims[1] & 3) == 0) layer1_backward_impl<true>(m, ms, region, xs, spare, sign, nb, rows, gW, overwrite);
+    else layer1_backward_impl<false>(m, ms, region, xs, spare, sign, nb, rows, gW, overwrite);
+  }
+  template <bool X16>
+  __device__ __noinline__ static void layer1_backward_impl(const BigModel& m, MlpSmem& ms, uint8_t* region, uint8_t* xs, uint8_t* spare,
                                          float sign, int nb, int rows, float* gW, bool overwrite) {
     using namespace mlptc;
     const int s0 = m.dims[1], s1 = m.dims[2];
     const int s1n = mlp_n16(s1);
     const int tid = threadIdx.x;
     const float* X = reinterpret_cast<const float*>(m.data0);
-    const bool x16 = (s0 & 3) == 0;
+    constexpr bool x16 = X16;
     const int G = (nb + 7) >> 3;                                  // K groups of 8 batch rows
     const int n_tiles = (s0 + 127) >> 7;                          // M tiles of 128 input columns
     const int tiles_per_pass = 4;                                 // 4 s1n <= 512 TMEM columns
