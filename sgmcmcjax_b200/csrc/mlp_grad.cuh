@@ -36,6 +36,7 @@ constexpr int MLP_ROWS = 128;      // largest sub-batch (MMA M of the forward co
 constexpr int MLP_THREADS = 512;   // gradient worker threads (warps 0..15); the CTA has 8 more noise-producer warps
 constexpr int MLP_STAGER_ROWS = (MLP_THREADS - 32) / 8;   // forward GEMM: rows one pass of the 480 operand-staging threads covers
 constexpr int MLP_KC = 32;         // forward K chunk (floats): one 128-byte swizzled row
+constexpr int MLP_BWD_TILE = 120;  // backward GEMM: input columns per M tile (of 128 lanes): 2 tiles x 8 rows = 480 16-byte slots
 constexpr int MLP_W2S = 128;       // row stride of the staged, zero-padded copy of W_2 (>= any layer-1 width)
 constexpr size_t MLP_SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
@@ -441,7 +442,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     const float* X = reinterpret_cast<const float*>(m.data0);
     constexpr bool x16 = X16;
     const int G = (nb + 7) >> 3;                                  // K groups of 8 batch rows
-    const int n_tiles = (s0 + 127) >> 7;                          // M tiles of 128 input columns
+    const int n_tiles = (s0 + MLP_BWD_TILE - 1) / MLP_BWD_TILE;   // M tiles of 120 input columns (see the stager mapping)
     const int tiles_per_pass = 4;                                 // 4 s1n <= 512 TMEM columns
     const uint32_t idesc = idesc_tf32(s1n, true);
     const uint32_t tmem = ms.tmem_base;
@@ -455,68 +456,88 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
     auto stage_ptr = [&](int st) { return st < 2 ? xs + (size_t)st * stage_bytes : spare + (size_t)(st - 2) * stage_bytes; };
     uint32_t par = ms.parity[0] | ms.parity[1] << 1 | ms.parity[2] << 2 | ms.parity[3] << 3;   // bit st: next phase parity of bar[st]
 
-    // loader mapping for one unit = 8 batch rows x 256 columns: row tid >> 6, 16-byte chunk tid & 63
-    const int lr = tid >> 6, c4 = tid & 63;
-    const uint32_t soff = (uint32_t)(c4 >> 3) * 1024u + mn_chunk_off(lr, c4 & 7);
+    // Warp 0 only issues the MMAs (as in layer1_forward); the 480 threads of warps 1..15 stage X.  So that they divide a
+    // unit evenly, an M tile holds MLP_BWD_TILE = 120 input columns (lanes 120..127 of its accumulators are never read):
+    // one unit = 8 batch rows x 2 tiles x 30 sixteen-byte chunks = 480 slots, one per stager.
+    const int tw = tid >= 32 ? tid - 32 : 0;
+    const int lr = tw / 60, c60 = tw - lr * 60;
+    const int tl = c60 / 30, cl = c60 - tl * 30;               // tile of the pair, chunk inside the tile
+    const uint32_t soff = (uint32_t)(tl * 4 + (cl >> 3)) * 1024u + mn_chunk_off(lr, cl & 7);
+    {                                                             // the never-written chunks 30, 31 of every tile row: zero
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int st = 0; st < nst; ++st)
+        for (int o = tid; o < (int)(stage_bytes / 16); o += MLP_THREADS) reinterpret_cast<float4*>(stage_ptr(st))[o] = z;
+      fence_proxy_async();
+      mlptc::worker_sync();
+    }
 
     for (int t0 = 0; t0 < n_tiles; t0 += tiles_per_pass) {
       const int pass_tiles = min(tiles_per_pass, n_tiles - t0);
       const int npp = (pass_tiles + 1) >> 1;                      // tile pairs in this pass
       const int units = G * npp;
-      auto fetch = [&](int u, float4& xv) {
-        const int g = u / npp, p = u - g * npp;
-        const int b = g * 8 + lr;
-        const int k = (t0 + 2 * p) * 128 + c4 * 4;
-        if (x16) {                                             // unconditional load, clamped address; masked in step()
-          xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)ms.idx[min(b, nb - 1)] * s0 + min(k, s0 - 4)));
-          return;
-        }
-        xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < nb && k < s0) xv = load4(X + (size_t)ms.idx[b] * s0 + k, s0 - k, x16, x16, true);
-      };
       uint32_t used = 0;                                          // bit st: stage st has MMAs in flight
-      // one pipeline step: registers of unit u -> stage u & 1, refill them with unit u + 4, issue the MMAs
-      auto step = [&](int u, float4& xv) {
-        const int st = u & (nst - 1);
-        uint8_t* sb = stage_ptr(st);
-        SG_TA(tb);
-        if (used >> st & 1) { mbar_wait(&ms.bar[st], par >> st & 1); par ^= 1u << st; }
-        SG_TB(21, tb);
-        if (x16) {
-          const int g = u / npp, p = u - g * npp;
-          if (!(g * 8 + lr < nb && (t0 + 2 * p) * 128 + c4 * 4 < s0)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float4 hi, lo;
-        split4(xv, hi, lo);
-        *reinterpret_cast<float4*>(sb + soff) = hi;
-        *reinterpret_cast<float4*>(sb + 8192 + soff) = lo;
-        SG_TB(22, tb);
-        fence_proxy_async();                                   // before the next load is issued (the fence would wait for it)
-        SG_TB(23, tb);
-        mlptc::stage_handover(st, tid < 32);
-        SG_TB(24, tb);
-        if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
-        SG_TB(25, tb);
-        if (tid == 0) {
-          tc_fence_after();
-          const int g = u / npp, p = u - g * npp;
-          const uint64_t dbh = desc_mn_sw128_32b(smem_u32(bhi) + (uint32_t)g * 4096u, 1024u, 512u);
-          const uint64_t dbl = desc_mn_sw128_32b(smem_u32(blo) + (uint32_t)g * 4096u, 1024u, 512u);
-          for (int t = 0; t < 2; ++t) {
-            if (2 * p + t >= pass_tiles) break;
-            const uint64_t dah = desc_mn_sw128_32b(smem_u32(sb) + (uint32_t)t * 4096u, 1024u, 512u);
-            const uint64_t dal = desc_mn_sw128_32b(smem_u32(sb) + 8192u + (uint32_t)t * 4096u, 1024u, 512u);
-            const uint32_t acc = tmem + (uint32_t)((2 * p + t) * s1n);
-            umma_tf32(acc, dal, dbh, idesc, g ? 1u : 0u);
-            umma_tf32(acc, dah, dbl, idesc, 1u);
-            umma_tf32(acc, dah, dbh, idesc, 1u);
+      if (tid < 32) {
+#pragma unroll 1
+        for (int u = 0; u < units; ++u) {
+          const int st = u & (nst - 1);
+          const uint8_t* sb = stage_ptr(st);
+          if (used >> st & 1) { mbar_wait(&ms.bar[st], par >> st & 1); par ^= 1u << st; }   // (retired: the stagers waited for it)
+          stage_handover(st, true);
+          if (tid == 0) {
+            tc_fence_after();
+            const int g = u / npp, p = u - g * npp;
+            const uint64_t dbh = desc_mn_sw128_32b(smem_u32(bhi) + (uint32_t)g * 4096u, 1024u, 512u);
+            const uint64_t dbl = desc_mn_sw128_32b(smem_u32(blo) + (uint32_t)g * 4096u, 1024u, 512u);
+            for (int t = 0; t < 2; ++t) {
+              if (2 * p + t >= pass_tiles) break;
+              const uint64_t dah = desc_mn_sw128_32b(smem_u32(sb) + (uint32_t)t * 4096u, 1024u, 512u);
+              const uint64_t dal = desc_mn_sw128_32b(smem_u32(sb) + 8192u + (uint32_t)t * 4096u, 1024u, 512u);
+              const uint32_t acc = tmem + (uint32_t)((2 * p + t) * s1n);
+              umma_tf32(acc, dal, dbh, idesc, g ? 1u : 0u);
+              umma_tf32(acc, dah, dbl, idesc, 1u);
+              umma_tf32(acc, dah, dbh, idesc, 1u);
+            }
+            tc_commit(&ms.bar[st]);
           }
-          tc_commit(&ms.bar[st]);
+          __syncwarp();
+          used |= 1u << st;
         }
-        SG_TB(26, tb);
-        used |= 1u << st;
-      };
-      {
+      } else {
+        auto fetch = [&](int u, float4& xv) {
+          const int g = u / npp, p = u - g * npp;
+          const int b = g * 8 + lr;
+          const int k = (t0 + 2 * p + tl) * MLP_BWD_TILE + cl * 4;
+          if (x16) {                                             // unconditional load, clamped address; masked in step()
+            xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)ms.idx[min(b, nb - 1)] * s0 + min(k, s0 - 4)));
+            return;
+          }
+          xv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (b < nb && k < s0) xv = load4(X + (size_t)ms.idx[b] * s0 + k, s0 - k, x16, x16, true);
+        };
+        // one pipeline step: registers of unit u -> its ring stage, hand the stage to warp 0, refill them with unit u + 4
+        auto step = [&](int u, float4& xv) {
+          const int st = u & (nst - 1);
+          uint8_t* sb = stage_ptr(st);
+          SG_TA(tb);
+          if (used >> st & 1) { mbar_wait(&ms.bar[st], par >> st & 1); par ^= 1u << st; }
+          SG_TBT(21, tb, 32);
+          if (x16) {
+            const int g = u / npp, p = u - g * npp;
+            if (!(g * 8 + lr < nb && (t0 + 2 * p + tl) * MLP_BWD_TILE + cl * 4 < s0)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          float4 hi, lo;
+          split4(xv, hi, lo);
+          *reinterpret_cast<float4*>(sb + soff) = hi;
+          *reinterpret_cast<float4*>(sb + 8192 + soff) = lo;
+          SG_TBT(22, tb, 32);
+          fence_proxy_async();                                   // before the next load is issued (the fence would wait for it)
+          SG_TBT(23, tb, 32);
+          stage_handover(st, false);
+          SG_TBT(24, tb, 32);
+          if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
+          SG_TBT(25, tb, 32);
+          used |= 1u << st;
+        };
         float4 x0, x1, x2, x3;
         fetch(0, x0);
         if (units > 1) fetch(1, x1);
@@ -539,7 +560,8 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       {
         const int warp = tid >> 5, lane = tid & 31;
         const int tq = warp >> 2;
-        const int k = (t0 + tq) * 128 + (warp & 3) * 32 + lane;
+        const int kl = (warp & 3) * 32 + lane;
+        const int k = kl < MLP_BWD_TILE ? (t0 + tq) * MLP_BWD_TILE + kl : s0;
         if (tq < pass_tiles) {
           const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tq * s1n);
           for (int n0 = 0; n0 < s1n; n0 += 16) {
