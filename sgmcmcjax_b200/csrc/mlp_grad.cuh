@@ -30,8 +30,8 @@ constexpr int MLP_ROWS = 128;      // largest sub-batch (MMA M of the forward co
 #ifndef SG_MLP_W_LDCG
 #define SG_MLP_W_LDCG 0
 #endif
-#ifndef SG_MLP_FWD_DEPTH
-#define SG_MLP_FWD_DEPTH 1         // chunks of operand loads a stager thread keeps in flight in the forward GEMM (1 or 2)
+#ifndef SG_MLP_FWD_DEEP_ITEMS
+#define SG_MLP_FWD_DEEP_ITEMS 0    // forward GEMM: how many of a stager's 4-5 items are prefetched TWO chunks ahead (the rest: one); 1 and 2 spill
 #endif
 constexpr int MLP_THREADS = 512;   // gradient worker threads (warps 0..15); the CTA has 8 more noise-producer warps
 constexpr int MLP_STAGER_ROWS = (MLP_THREADS - 32) / 8;   // forward GEMM: rows one pass of the 480 operand-staging threads covers
@@ -309,12 +309,13 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       // Fast path (s0 % 4 == 0, W1 at least 8-byte aligned): every 16-byte chunk is wholly inside or outside a row, so
       // the loads are unconditional (clamped address, result masked in step()) and issue back to back; a branch between
       // two loads, or a use of a loaded value, would serialise them on the memory latency.
-      auto fetch = [&](int c, float4 (&v)[NI]) {
+      auto fetch = [&](int c, float4 (&v)[NI], int j0, int j1) {                 // items j0 <= j < j1 of chunk c
         const int k = c * MLP_KC + ch * 4;
         if (FAST) {
           const int kk = min(k, s0 - 4);
 #pragma unroll
           for (int j = 0; j < NI; ++j) {
+            if (j < j0 || j >= j1) continue;
             if (MLP_STAGER_ROWS * j + MLP_STAGER_ROWS <= MLP_ROWS) {            // always a row of X: 16-byte aligned, read-only
               v[j] = __ldg(reinterpret_cast<const float4*>(src[j] + kk));
             } else {
@@ -331,11 +332,18 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         const int valid = s0 - k;
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
+          if (j < j0 || j >= j1) continue;
           v[j] = (flags >> (2 * j) & 1) ? load4(src[j] + k, valid, is_x(j) ? x16 : w16, is_x(j) ? x16 : w8, false) : zero4;
         }
       };
-      // one pipeline step: registers of chunk c -> stage c & 1, hand the stage to warp 0, refill the registers with chunk c + 2
-      auto step = [&](int c, float4 (&v)[NI]) {
+      // Prefetch depth: ONE chunk of loads in flight per thread.  With two (32 registers of prefetched values) the compiler
+      // spills the values it has just loaded - the spill store waits for the load, and the "prefetch" runs at one memory
+      // latency per chunk (ncu source view: 7 % of the kernel's stall samples on STL right behind the loads).  Keeping only
+      // the first ND items (gathered rows of X: HBM latency) two chunks ahead still spills one float4 per deep item at the
+      // 128-register cap of a 512-thread CTA (checked in the SASS for ND = 1, 2), so ND = 0.
+      constexpr int ND = SG_MLP_FWD_DEEP_ITEMS;
+      // one pipeline step: registers of chunk c -> stage c & 1, hand the stage to warp 0, refill the registers
+      auto step = [&](int c, float4 (&vd)[NI], float4 (&vs)[NI]) {
         const int st = c & 1;
         uint8_t* sb = region + (size_t)st * stage_bytes;
         SG_TA(tt);
@@ -345,7 +353,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
           if (!(flags >> (2 * j) & 2)) continue;
-          float4 x = v[j];
+          float4 x = j < ND ? vd[j] : vs[j];
           if (FAST && !(in && (flags >> (2 * j) & 1))) x = zero4;                // out-of-range rows / columns read as zero
           float4 hi, lo;
           split4(x, hi, lo);
@@ -357,35 +365,20 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         SG_TBT(11, tt, 32);
         stage_handover(st, false);
         SG_TBT(12, tt, 32);
-#if SG_MLP_FWD_DEPTH == 2
-        if (c + 2 < n_chunks) fetch(c + 2, v);                                 // two chunks of loads stay in flight
-#else
-        if (c + 1 < n_chunks) fetch(c + 1, v);                                 // the next chunk's loads fly during the hand-over + wait
-#endif
+        if (c + 2 < n_chunks) fetch(c + 2, vd, 0, ND);
+        if (c + 1 < n_chunks) fetch(c + 1, vs, ND, NI);
         SG_TBT(14, tt, 32);
         ++uses[st];
       };
-#if SG_MLP_FWD_DEPTH == 2
-      float4 a[NI], b[NI];
-      fetch(0, a);
-      if (n_chunks > 1) fetch(1, b);
+      float4 a[NI], b[NI], w[NI];
+      fetch(0, a, 0, ND);
+      fetch(0, w, ND, NI);
+      if (n_chunks > 1) fetch(1, b, 0, ND);
 #pragma unroll 1
       for (int c = 0; c < n_chunks; c += 2) {
-        step(c, a);
-        if (c + 1 < n_chunks) step(c + 1, b);
+        step(c, a, w);
+        if (c + 1 < n_chunks) step(c + 1, b, w);
       }
-#else
-      // ONE chunk of loads in flight per thread: with two (32 registers of prefetched values) the compiler spills the
-      // values it has just loaded - the spill store waits for the load, and the "prefetch" runs at one memory latency per
-      // chunk (ncu source view: 7 % of the kernel's stall samples on STL instructions right behind the loads)
-      float4 a[NI];
-      fetch(0, a);
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; c += 2) {
-        step(c, a);
-        if (c + 1 < n_chunks) step(c + 1, a);
-      }
-#endif
     }
     for (int st = 0; st < 2; ++st)
       if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }
@@ -485,7 +478,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           stage_handover(st, true);
           if (tid == 0) {
             tc_fence_after();
-            const int g = u / npp, p = u - g * npp;
+            const int g = npp == 2 ? u >> 1 : u, p = npp == 2 ? u & 1 : 0;       // npp <= 2: tiles_per_pass == 4
             const uint64_t dbh = desc_mn_sw128_32b(smem_u32(bhi) + (uint32_t)g * 4096u, 1024u, 512u);
             const uint64_t dbl = desc_mn_sw128_32b(smem_u32(blo) + (uint32_t)g * 4096u, 1024u, 512u);
             for (int t = 0; t < 2; ++t) {
@@ -503,27 +496,32 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           used |= 1u << st;
         }
       } else {
-        auto fetch = [&](int u, float4& xv) {
-          const int g = u / npp, p = u - g * npp;
-          const int b = g * 8 + lr;
-          const int k = (t0 + 2 * p + tl) * MLP_BWD_TILE + cl * 4;
+        // unit u = (K group g, tile pair p); npp <= 2 because tiles_per_pass == 4
+        auto group_of = [&](int u) { return npp == 2 ? u >> 1 : u; };
+        auto pair_of = [&](int u) { return npp == 2 ? u & 1 : 0; };
+        // table row of this thread's slot in unit u (read ahead of the load that needs it: ms.idx sits behind a generic
+        // pointer, and the gather waited for it - 3 % of the kernel's stall samples on the LDG)
+        auto row_of = [&](int u) { return ms.idx[min(group_of(u) * 8 + lr, nb - 1)]; };
+        auto fetch = [&](int u, int row, float4& xv) {
+          const int b = group_of(u) * 8 + lr;
+          const int k = (t0 + 2 * pair_of(u) + tl) * MLP_BWD_TILE + cl * 4;
           if (x16) {                                             // unconditional load, clamped address; masked in step()
-            xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)ms.idx[min(b, nb - 1)] * s0 + min(k, s0 - 4)));
+            xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)row * s0 + min(k, s0 - 4)));
             return;
           }
           xv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (b < nb && k < s0) xv = load4(X + (size_t)ms.idx[b] * s0 + k, s0 - k, x16, x16, true);
+          if (b < nb && k < s0) xv = load4(X + (size_t)row * s0 + k, s0 - k, x16, x16, true);
         };
         // one pipeline step: registers of unit u -> its ring stage, hand the stage to warp 0, refill them with unit u + 4
         auto step = [&](int u, float4& xv) {
           const int st = u & (nst - 1);
           uint8_t* sb = stage_ptr(st);
+          const int next_row = u + 4 < units ? row_of(u + 4) : 0;
           SG_TA(tb);
           if (used >> st & 1) { mbar_wait(&ms.bar[st], par >> st & 1); par ^= 1u << st; }
           SG_TBT(21, tb, 32);
           if (x16) {
-            const int g = u / npp, p = u - g * npp;
-            if (!(g * 8 + lr < nb && (t0 + 2 * p + tl) * MLP_BWD_TILE + cl * 4 < s0)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!(group_of(u) * 8 + lr < nb && (t0 + 2 * pair_of(u) + tl) * MLP_BWD_TILE + cl * 4 < s0)) xv = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           float4 hi, lo;
           split4(xv, hi, lo);
@@ -534,15 +532,15 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           SG_TBT(23, tb, 32);
           stage_handover(st, false);
           SG_TBT(24, tb, 32);
-          if (u + 4 < units) fetch(u + 4, xv);                   // four units of loads stay in flight
+          if (u + 4 < units) fetch(u + 4, next_row, xv);         // four units of loads stay in flight
           SG_TBT(25, tb, 32);
           used |= 1u << st;
         };
         float4 x0, x1, x2, x3;
-        fetch(0, x0);
-        if (units > 1) fetch(1, x1);
-        if (units > 2) fetch(2, x2);
-        if (units > 3) fetch(3, x3);
+        fetch(0, row_of(0), x0);
+        if (units > 1) fetch(1, row_of(1), x1);
+        if (units > 2) fetch(2, row_of(2), x2);
+        if (units > 3) fetch(3, row_of(3), x3);
 #pragma unroll 1
         for (int u = 0; u < units; u += 4) {
           step(u, x0);
