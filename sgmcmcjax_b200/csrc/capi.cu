@@ -984,12 +984,32 @@ int sgmcmc_ksd_imq_tc(const float* x, const float* g, int32_t n, int32_t d, int3
   if (cr != CUDA_SUCCESS) return fail(SGMCMC_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)cr));
 
   const long long T = (n + kt::TILE - 1) / kt::TILE;
-  const long long total = T * (T + 1) / 2;
+  // SGMCMC_KSD_CLUSTER=2: clusters of two CTAs sharing the row-side operand by TMA multicast (ksd_tc.cuh).  Parity-green and
+  // 25 % less L2 -> SM operand traffic, but measured 1.4 % SLOWER (4.91 vs 4.84 ms at N = 50k): the kernel is bound by the
+  // MMA -> epilogue hand-over of its single accumulator set, not by the operand stream; one CTA per tile stays the default.
+  const char* cl_env = getenv("SGMCMC_KSD_CLUSTER");
+  const int cl = cl_env && atoi(cl_env) == 2 ? 2 : 1;
+  const long long total = cl == 1 ? T * (T + 1) / 2 : kt::pair_start(T, T);
   const long long n_local = total > part ? (total - part + nparts - 1) / nparts : 0;
   if (n_local == 0) return SGMCMC_OK;
-  CUDA_TRY(cudaFuncSetAttribute(kt::ksd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt::SMEM_BYTES));
-  const int grid = (int)std::min<long long>(n_local, sms);
-  kt::ksd_tc_kernel<<<grid, kt::NUM_THREADS, kt::SMEM_BYTES, s>>>(zmap, rt, n, d, dp, part, nparts, partial_sum);
+  if (cl == 1) {
+    CUDA_TRY(cudaFuncSetAttribute(kt::ksd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt::SMEM_BYTES));
+    const int grid = (int)std::min<long long>(n_local, sms);
+    kt::ksd_tc_kernel<1><<<grid, kt::NUM_THREADS, kt::SMEM_BYTES, s>>>(zmap, rt, n, d, dp, part, nparts, partial_sum);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(kt::ksd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kt::SMEM_BYTES));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * std::min<long long>(n_local, sms / 2)));
+    cfg.blockDim = dim3(kt::NUM_THREADS);
+    cfg.dynamicSmemBytes = kt::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kt::ksd_tc_kernel<2>, zmap, (const float4*)rt, n, d, dp, (int)part, (int)nparts, partial_sum));
+  }
   CUDA_TRY(cudaGetLastError()); ++g_launches;
   return SGMCMC_OK;
 }

@@ -92,6 +92,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// the same box delivered to the same shared-memory offsets (and signalled on the same mbarrier offset) of every CTA in
+// cta_mask of this cluster
+__device__ __forceinline__ void tma_load_2d_multicast(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -107,6 +119,11 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one arrival on the mbarrier at this offset in EVERY CTA of cta_mask, when the MMAs issued so far have retired
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate, M = 128, N = 128, K = 8.
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -256,6 +273,24 @@ __device__ __forceinline__ void tile_of(long long t, int T, int& I, int& J) {
   J = i + (int)(t - start(i));
 }
 
+// Cluster items: the two CTAs of a cluster take the tiles (I, J) and (I, J + 1) of one tile ROW at a time, so that the
+// row-side operand is fetched once and multicast to both.  Row I has ceil((T - I) / 2) items; item g -> (I, first J).
+__host__ __device__ __forceinline__ long long pair_start(long long I, long long T) {   // items in rows 0 .. I-1
+  const long long m = T + 1;                                     // sum_{i<I} floor((m - i) / 2)
+  const long long odd = (m & 1) ? (I + 1) >> 1 : I >> 1;          // how many of the (m - i) are odd
+  return (I * m - I * (I - 1) / 2 - odd) / 2;
+}
+__device__ __forceinline__ void pair_of(long long g, int T, int& I, int& J) {
+  const double tt = (double)T + 1.0;
+  int i = (int)(tt - sqrt(fmax(tt * tt - 4.0 * (double)g, 0.0)));
+  if (i < 0) i = 0;
+  if (i > T - 1) i = T - 1;
+  while (i > 0 && pair_start(i, T) > g) --i;
+  while (i < T - 1 && pair_start(i + 1, T) <= g) ++i;
+  I = i;
+  J = i + 2 * (int)(g - pair_start(i, T));
+}
+
 __device__ __forceinline__ float imq_k0_tc(float dd, float gg, float gd, float dim) {
   const float b = 1.0f + dd;
   float r;                                      // b >= 1: the denormal guard of rsqrtf() (3 more instructions) is dead weight
@@ -277,6 +312,13 @@ static __constant__ int16_t PROD[6][3] = {
 };
 __device__ __forceinline__ int col_slot(int seg) { return ((seg & 1) << 1) | (seg >> 1); }   // xh 0, gh 1, xl 2, gl 3
 
+// CL = 1 (default): one CTA per tile.  CL = 2 (opt-in, launched as clusters of two CTAs): the operand stream from L2 is
+// large (458 KB per 128 x 128 tile: ncu 35.4 GB per N = 50k call at 7.3 TB/s, tensor pipe 56 % busy), so the two CTAs of a
+// cluster work on neighbouring tiles of one tile row in lockstep and share its row-side chunks: each CTA fetches two of the
+// four row-side segments and TMA-multicasts them into both CTAs' stage (344 KB per tile).  A stage is refilled only when
+// BOTH CTAs have consumed it: the MMA issuers commit to the `empty` barrier of both CTAs (arrival count 2).  Measured: same
+// result, 4.91 vs 4.84 ms - the stream was not the limit.
+template <int CL>
 static __global__ void __launch_bounds__(NUM_THREADS, 1)
 ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict__ rt, int n, int d, int dp,
               int part, int nparts, double* __restrict__ out) {
@@ -286,13 +328,23 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int T = (n + TILE - 1) / TILE;
-  const long long total = (long long)T * (T + 1) / 2;
-  // tiles of this partition: g = part + nparts * u, u = 0 .. n_local-1; this CTA takes u = blockIdx.x + k * gridDim.x
+  const long long total = CL == 1 ? (long long)T * (T + 1) / 2 : pair_start(T, T);
+  // items (tiles / tile pairs) of this partition: g = part + nparts * u, u = 0 .. n_local-1; this CTA (cluster) takes
+  // u = first + k * stride
   const long long n_local = total > part ? (total - part + nparts - 1) / nparts : 0;
   const int n_chunks = (dp + KC - 1) / KC;
+  const uint32_t crank = CL == 1 ? 0u : cluster_ctarank();
+  const long long first = blockIdx.x / CL, stride = gridDim.x / CL;
+  // item g -> this CTA's tile (I, J); `live` false: the odd tile out at the end of a row (a weight-0 repeat of its neighbour)
+  auto item = [&](long long g, int& I, int& J, bool& live) {
+    if (CL == 1) { tile_of(g, T, I, J); live = true; return; }
+    pair_of(g, T, I, J);
+    live = J + (int)crank < T;
+    if (live) J += (int)crank;
+  };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], CL); }
     mbar_init(&tail->tmem_full, 1);
     mbar_init(&tail->tmem_empty, 16);      // one arrival per epilogue warp
     fence_barrier_init();
@@ -301,6 +353,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
   if (warp == 0 && lane == 0) tma_prefetch_desc(&zmap);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
@@ -308,9 +361,10 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (long long u = blockIdx.x; u < n_local; u += gridDim.x) {
+      for (long long u = first; u < n_local; u += stride) {
         int I, J;
-        tile_of(part + (long long)nparts * u, T, I, J);
+        bool live;
+        item(part + (long long)nparts * u, I, J, live);
         for (int c = 0; c < n_chunks; ++c) {
           mbar_wait(&tail->empty[stage], phase ^ 1);
           uint8_t* sbase = smem + (size_t)stage * STAGE_BYTES;
@@ -318,7 +372,9 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
 #pragma unroll
           for (int seg = 0; seg < 4; ++seg) {
             const int blk_row = (seg * n_chunks + c) * n;          // first row of block (segment, chunk) in the [.., KC] view
-            tma_load_2d(sbase + seg * CHUNK_BYTES, &zmap, 0, blk_row + I * TILE, &tail->full[stage]);
+            if (CL == 1) tma_load_2d(sbase + seg * CHUNK_BYTES, &zmap, 0, blk_row + I * TILE, &tail->full[stage]);
+            else if ((uint32_t)(seg >> 1) == crank)
+              tma_load_2d_multicast(sbase + seg * CHUNK_BYTES, &zmap, 0, blk_row + I * TILE, &tail->full[stage], (uint16_t)3);
             tma_load_2d(sbase + (4 + col_slot(seg)) * CHUNK_BYTES, &zmap, 0, blk_row + J * TILE, &tail->full[stage]);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -329,7 +385,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
     // ===== MMA issuer (one lane) =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc_phase = 0;
-      for (long long u = blockIdx.x; u < n_local; u += gridDim.x) {
+      for (long long u = first; u < n_local; u += stride) {
         mbar_wait(&tail->tmem_empty, acc_phase ^ 1);
         tc_fence_after();
         uint32_t started = 0;                                  // bit a set once accumulator a holds data
@@ -351,7 +407,8 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
               started |= 1u << a;
             }
           }
-          tc_commit(&tail->empty[stage]);                      // frees the smem stage when these MMAs retire
+          if (CL == 1) tc_commit(&tail->empty[stage]);         // frees the smem stage when these MMAs retire
+          else tc_commit_multicast(&tail->empty[stage], (uint16_t)3);   // ... in both CTAs: either may refill both
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(&tail->tmem_full);                           // accumulators complete
@@ -368,9 +425,10 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
     double acc = 0.0;
     uint32_t acc_phase = 0;
     int buf = 0;
-    for (long long u = blockIdx.x; u < n_local; u += gridDim.x) {
+    for (long long u = first; u < n_local; u += stride) {
       int I, J;
-      tile_of(part + (long long)nparts * u, T, I, J);
+      bool live;
+      item(part + (long long)nparts * u, I, J, live);
       const int gi = I * TILE + row_in_tile;
       const int gjc = J * TILE + et;
       if (et < TILE) tail->colterm[buf][et] = gjc < n ? rt[gjc] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -422,7 +480,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tmem_empty);           // accumulators may be overwritten
-      acc += (double)tsum * (I == J ? 1.0 : 2.0);
+      acc += (double)tsum * (!live ? 0.0 : I == J ? 1.0 : 2.0);
       acc_phase ^= 1;
       buf ^= 1;
     }
@@ -433,6 +491,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 

@@ -708,6 +708,25 @@ def test_ksd_tc_tile_partitions_sum_to_whole(cuda):
     assert abs(whole - simt) <= 2e-4 * abs(ref)
 
 
+@pytest.mark.parametrize("n,d", [(1, 3), (129, 100), (333, 7), (1000, 100), (1100, 100), (700, 260)])
+def test_ksd_tc_cluster_multicast_variant(cuda, monkeypatch, n, d):
+    """The opt-in two-CTA-cluster kernel (row-side operand by TMA multicast, csrc/ksd_tc.cuh): same sums as one CTA per tile,
+    odd and even tile-row lengths (the odd tile out is a weight-0 repeat), and its item partitions still sum to the whole."""
+    from sgmcmcjax_b200 import ksd as NKSD
+
+    X, G = ksd_case(n, d, "logreg")
+    monkeypatch.setenv("SGMCMC_KSD_CLUSTER", "1")
+    base = float(NKSD.imq_KSD_tiles(X, G, 0, 1).cpu()[0])
+    monkeypatch.setenv("SGMCMC_KSD_CLUSTER", "2")
+    whole = float(NKSD.imq_KSD_tiles(X, G, 0, 1).cpu()[0])
+    assert abs(whole - base) <= 1e-9 * abs(base), (whole, base)
+    for nparts in (2, 5):
+        parts = sum(float(NKSD.imq_KSD_tiles(X, G, p, nparts).cpu()[0]) for p in range(nparts))
+        assert abs(whole - parts) <= 1e-9 * abs(whole)
+    ref = OK.imq_ksd_literal(X, G)
+    assert abs(float(NKSD.imq_KSD(X, G, method="tc")) - ref) <= 1e-4 * abs(ref)
+
+
 def test_ksd_row_blocks_sum_to_whole_and_golden(cuda):
     from sgmcmcjax_b200 import ksd as NKSD
 
