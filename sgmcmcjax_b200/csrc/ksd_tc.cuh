@@ -22,7 +22,7 @@
 // Per 128 x 128 tile and K-chunk of 16 columns, TMA brings the 4 row-side and 4 column-side
 // segment chunks into one 64 KB smem stage (64-byte swizzle, K-major); 12 segment products
 // (3 for x.x, 3 for g.g, 6 for the cross term), issued as 6 N = 256 MMAs on adjacent column-side
-// segments, accumulate into four 128-column fp32 accumulators in TMEM.  Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc),
+// segments, accumulate into three 128-column fp32 accumulators in TMEM (the two cross products share one).  Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc),
 // 2..17 = epilogue (tcgen05.ld -> IMQ formula -> fp64 partial sums; four warps per TMEM lane quarter, 32 columns each).
 #pragma once
 #include <cuda.h>
@@ -39,7 +39,7 @@ constexpr int STAGES = 3;
 constexpr int CHUNK_BYTES = TILE * KC * 4;           // 8 KB per (segment, side) chunk
 constexpr int STAGE_BYTES = 8 * CHUNK_BYTES;         // 64 KB
 constexpr int NUM_THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue (4 per TMEM lane quarter)
-constexpr int TMEM_COLS = 512;     // 4 accumulators x 128 columns
+constexpr int TMEM_COLS = 512;     // 3 accumulators x 128 columns (allocations are powers of two)
 constexpr int UMMA_K = 8;          // tf32: 32 bytes of K per instruction
 
 struct SmemTail {                  // after the stage buffers
@@ -304,11 +304,15 @@ __device__ __forceinline__ float imq_k0_tc(float dd, float gg, float gd, float d
 // MMA multiplies a row-side segment with TWO adjacent column-side segments and writes two adjacent TMEM
 // accumulators: half the MMA instructions, and the A operand is read from shared memory once per 256 columns
 // (12 KB of operand traffic per 128 tensor cycles instead of 8 KB per 64, the 128 B/clk shared-memory port).
-//   TMEM columns: [0,128) x_I.x_J   [128,256) x_I.g_J   [256,384) g_I.x_J   [384,512) g_I.g_J
+//   TMEM columns: [0,128) x_I.x_J   [128,256) x_I.g_J + g_I.x_J   [256,384) g_I.g_J
+// Only the SUM of the two cross products enters the formula, so the g_I pair lands one accumulator to the right of the x_I
+// pair and both add into the middle one: three accumulators for the epilogue to read instead of four (TMEM reads, at
+// 64 B/clk, are the bulk of the epilogue; round 2).  The one MMA per tile that would have to overwrite [256,384) while
+// adding into [128,256) is issued as two N = 128 halves (see the issuer).
 // table: (TMEM column of the pair, row-side segment 0 xh 1 xl 2 gh 3 gl, column-side pair 0 = [xh|gh], 1 = [xl|gl])
 static __constant__ int16_t PROD[6][3] = {
     {0, 0, 0}, {0, 0, 1}, {0, 1, 0},          // x_I . [x_J | g_J]  (3xTF32: hi.hi, hi.lo, lo.hi)
-    {256, 2, 0}, {256, 2, 1}, {256, 3, 0}     // g_I . [x_J | g_J]
+    {128, 2, 0}, {128, 2, 1}, {128, 3, 0}     // g_I . [x_J | g_J]
 };
 __device__ __forceinline__ int col_slot(int seg) { return ((seg & 1) << 1) | (seg >> 1); }   // xh 0, gh 1, xl 2, gl 3
 
@@ -388,7 +392,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       for (long long u = first; u < n_local; u += stride) {
         mbar_wait(&tail->tmem_empty, acc_phase ^ 1);
         tc_fence_after();
-        uint32_t started = 0;                                  // bit a set once accumulator a holds data
+        uint32_t started = 0;                                  // bit 0 / 1: the x_I / g_I pair has written its accumulators
         for (int c = 0; c < n_chunks; ++c) {
           mbar_wait(&tail->full[stage], phase);
           tc_fence_after();
@@ -397,13 +401,21 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
           const int slices = valid / UMMA_K;
 #pragma unroll
           for (int p = 0; p < 6; ++p) {
-            const int a = PROD[p][0] >> 8;                         // 0: columns [0,256), 1: columns [256,512)
+            const int a = p >= 3;                                  // 0: x_I pair, columns [0,256); 1: g_I pair, columns [128,384)
             const uint64_t da = make_desc_sw64(sbase + PROD[p][1] * CHUNK_BYTES);
             const uint64_t db = make_desc_sw64(sbase + (4 + 2 * PROD[p][2]) * CHUNK_BYTES);
             for (int k = 0; k < slices; ++k) {
               // advancing K inside the swizzle atom = +32 bytes on the start address (>>4 => +2)
-              umma_tf32(tmem_base + PROD[p][0], da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_TF32_128x256,
-                        (started >> a) & 1u);
+              if (a == 1 && !(started & 2u)) {
+                // first g_I product of the tile: ADD g_I.x_J into the cross accumulator (the x_I pair, p < 3, has written
+                // it), OVERWRITE the g_I.g_J accumulator - two N = 128 MMAs on the two halves of the column-side pair
+                const uint64_t db2 = make_desc_sw64(sbase + (4 + 2 * PROD[p][2] + 1) * CHUNK_BYTES);
+                umma_tf32(tmem_base + 128, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_TF32_128x128, 1u);
+                umma_tf32(tmem_base + 256, da + (uint64_t)(k * 2), db2 + (uint64_t)(k * 2), IDESC_TF32_128x128, 0u);
+              } else {
+                umma_tf32(tmem_base + PROD[p][0], da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC_TF32_128x256,
+                          a == 1 ? 1u : (started & 1u));
+              }
               started |= 1u << a;
             }
           }
@@ -449,11 +461,10 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
       const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cb = cgrp * 32; cb < cgrp * 32 + 32; cb += 8) {
-        uint32_t p1[8], p2[8], p3[8], p4[8];
+        uint32_t p1[8], p2[8], p3[8];
         tmem_ld8(tl + cb, p1);                  // x_I.x_J
-        tmem_ld8(tl + 3 * TILE + cb, p2);       // g_I.g_J
-        tmem_ld8(tl + TILE + cb, p3);           // x_I.g_J
-        tmem_ld8(tl + 2 * TILE + cb, p4);       // g_I.x_J
+        tmem_ld8(tl + 2 * TILE + cb, p2);       // g_I.g_J
+        tmem_ld8(tl + TILE + cb, p3);           // x_I.g_J + g_I.x_J
         tmem_ld_wait();
         if (interior) {
 #pragma unroll
@@ -461,7 +472,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
             const float4 cj = colterm(cb + e);
             const float dd = fmaf(-2.0f, __uint_as_float(p1[e]), ri.x + cj.x);
             const float gg = __uint_as_float(p2[e]) + (ri.z + cj.z);
-            const float gd = (ri.y + cj.y) - (__uint_as_float(p3[e]) + __uint_as_float(p4[e]));
+            const float gd = (ri.y + cj.y) - __uint_as_float(p3[e]);
             tsum += imq_k0_tc(dd, gg, gd, dim);
           }
         } else {
@@ -470,7 +481,7 @@ ksd_tc_kernel(const __grid_constant__ CUtensorMap zmap, const float4* __restrict
             const float4 cj = colterm(cb + e);
             float dd = fmaf(-2.0f, __uint_as_float(p1[e]), ri.x + cj.x);
             float gg = __uint_as_float(p2[e]) + (ri.z + cj.z);
-            float gd = (ri.y + cj.y) - (__uint_as_float(p3[e]) + __uint_as_float(p4[e]));
+            float gd = (ri.y + cj.y) - __uint_as_float(p3[e]);
             if (diag_tile && cb + e == row_in_tile) { dd = 0.f; gd = 0.f; gg = ri.w; }   // i == j: exact
             const float k0 = imq_k0_tc(dd, gg, gd, dim);
             tsum += (gi < n && cb + e < jmax) ? k0 : 0.f;
