@@ -22,7 +22,7 @@
 //       one slot of r floats per touched row, filled by the row's owner in a fixed order - no float atomics, no dense
 //       P-vector that is zeroed, scattered into and read back every step; the diffusion pass looks the slot up).
 //       Deterministic, and it removes 2 of the 7 state accesses per element - but measured slower (capi.cu), because the
-//       kernel is bound by instruction issue in the RNG, not by traffic.  Full passes over all N ratings (SVRG refresh,
+//       kernel is bound by its dependent RNG chains at 16 warps per SM, not by traffic (DESIGN.md, K1-big, round-2 correction).  Full passes over all N ratings (SVRG refresh,
 //       K2, the full-batch bypass) always use the dense buffer.
 //   MLP (models/bayesian_NN/NN_model.py:31-58): see mlp_grad.cuh.
 #pragma once
@@ -234,7 +234,7 @@ __device__ __forceinline__ void noise_pass(unsigned n, const float* xi, LD ld, S
 
 // Pair versions: a thread takes the ADJACENT blocks 2p and 2p + 1, i.e. elements (2p, 2p + 1) and (2p + h, 2p + 1 + h), so
 // that every array is read and written 8 bytes at a time (half the load / store instructions and address arithmetic of
-// the scalar passes: these passes are bound by instruction issue, not by bandwidth).  Needs h even and 8-byte aligned
+// the scalar passes: these passes are bound by their instruction streams, not by bandwidth).  Needs h even and 8-byte aligned
 // arrays (the caller checks); the blocks past the last full pair go through the scalar tail.
 //   ld2(e, t0, t1): elements e, e + 1;   f(e, t, xi) -> Out;   st2(e, o0, o1)
 struct Out { float x, a, b; };                   // new x, new first / second auxiliary value
