@@ -37,6 +37,15 @@ constexpr int MLP_THREADS = 512;   // gradient worker threads (warps 0..15); the
 constexpr int MLP_STAGER_ROWS = (MLP_THREADS - 32) / 8;   // forward GEMM: rows one pass of the 480 operand-staging threads covers
 constexpr int MLP_KC = 32;         // forward K chunk (floats): one 128-byte swizzled row
 constexpr int MLP_BWD_TILE = 120;  // backward GEMM: input columns per M tile (of 128 lanes): 2 tiles x 8 rows = 480 16-byte slots
+// SG_MLP_ISSUER_FENCE = 1: the generic -> async proxy fence that makes a filled stage visible to tcgen05.mma is executed ONCE,
+// by the issuing thread, after the hand-over barrier (whose release / acquire makes the stagers' st.shared visible to it;
+// the proxy fence is cumulative over what the thread has observed).  The stagers then never execute it: as SASS it is
+// MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the MEMBAR waits for every load / cp.async the thread still has in flight -
+// i.e. it serialised the operand prefetch with the stage fill.  0: every stager fences its own writes (round 1 .. 2b).
+#ifndef SG_MLP_ISSUER_FENCE
+#define SG_MLP_ISSUER_FENCE 1
+#endif
+constexpr int MLP_RING_DEPTH = 2;   // forward GEMM: chunks of operand loads in flight in the cp.async ring
 constexpr int MLP_W2S = 128;       // row stride of the staged, zero-padded copy of W_2 (>= any layer-1 width)
 constexpr size_t MLP_SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
@@ -135,6 +144,21 @@ __device__ __forceinline__ void stage_handover(int stage, bool issuer_warp) {
   else asm volatile("bar.arrive %0, 512;" ::"r"(2 + stage) : "memory");
 }
 
+// Per-thread asynchronous copies global -> shared (LDGSTS); src_bytes < the copy size zero-fills the rest.
+__device__ __forceinline__ void cp_async16(uint32_t sdst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t sdst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sdst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 // K-major, 128-byte swizzle: rows of 32 floats, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t desc_k_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -214,26 +238,35 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
   // ---------------------------------------------------------------------------------------------------
   // Z1 = X W1^T + b1 into act1 (fp32, [rows][zs]); rows >= nb come out as b1.
   __device__ __forceinline__ static void layer1_forward(const BigModel& m, MlpSmem& ms, uint8_t* region, const float* th, int nb,
-                                        int rows, float* Z, int zs) {
+                                        int rows, float* Z, int zs, uint8_t* raw, size_t raw_bytes) {
     const int s0 = m.dims[1];
     const float* W1 = th + m.leaf_off[0];
     // fast path (s0 % 4 == 0, W1 at least 8-byte aligned) as its own instantiation: merged with the general path, ptxas
     // if-converts the two and leaves predicated-off spill stores that still wait for the staged loads
     const bool fast = (s0 & 3) == 0 && (reinterpret_cast<uintptr_t>(W1) & 7) == 0;
-    if (mlp_n16(m.dims[2]) <= 4 * MLP_STAGER_ROWS - MLP_ROWS) {
-      if (fast) layer1_forward_impl<true, 4>(m, ms, region, th, nb, rows, Z, zs);
-      else layer1_forward_impl<false, 4>(m, ms, region, th, nb, rows, Z, zs);
+    const bool ni4 = mlp_n16(m.dims[2]) <= 4 * MLP_STAGER_ROWS - MLP_ROWS;
+    // ... and with room for the raw operand ring (`raw`: shared memory that is idle during this GEMM), the prefetch goes
+    // through per-thread cp.async slots there instead of registers (layer1_forward_impl)
+    const bool ring = fast && raw_bytes >= (size_t)MLP_RING_DEPTH * (ni4 ? 4 : 5) * (MLP_THREADS - 32) * 16;
+    if (ni4) {
+      if (ring) layer1_forward_impl<true, 4, true>(m, ms, region, th, nb, rows, Z, zs, raw);
+      else if (fast) layer1_forward_impl<true, 4, false>(m, ms, region, th, nb, rows, Z, zs, raw);
+      else layer1_forward_impl<false, 4, false>(m, ms, region, th, nb, rows, Z, zs, raw);
     } else {
-      if (fast) layer1_forward_impl<true, 5>(m, ms, region, th, nb, rows, Z, zs);
-      else layer1_forward_impl<false, 5>(m, ms, region, th, nb, rows, Z, zs);
+      if (ring) layer1_forward_impl<true, 5, true>(m, ms, region, th, nb, rows, Z, zs, raw);
+      else if (fast) layer1_forward_impl<true, 5, false>(m, ms, region, th, nb, rows, Z, zs, raw);
+      else layer1_forward_impl<false, 5, false>(m, ms, region, th, nb, rows, Z, zs, raw);
     }
   }
   // Warp 0 only issues the MMAs; warps 1..15 (480 "stagers") move the operands.  Stager t handles 16-byte chunk t & 7 of
   // rows (t >> 3) + 60 j, j < NI, of the stack [X rows 0..127 | W1 rows 0..s1n): NI = 4 covers s1n <= 112 (the 784-100-10
   // network: 240 rows x 8 chunks = 480 x 4 exactly), NI = 5 the widths up to 128.
-  template <bool FAST, int NI>
+  // RING: the operand prefetch does not live in registers (one chunk of them was all that fitted, and its load latency
+  // showed in every chunk) but in per-thread slots of a shared-memory ring filled by cp.async: MLP_RING_DEPTH chunks in
+  // flight, read back by the thread that requested them (no barrier needed), then split into the tensor-core stages.
+  template <bool FAST, int NI, bool RING>
   __device__ __noinline__ static void layer1_forward_impl(const BigModel& m, MlpSmem& ms, uint8_t* region, const float* th, int nb,
-                                        int rows, float* Z, int zs) {
+                                        int rows, float* Z, int zs, uint8_t* raw) {
     using namespace mlptc;
     const int s0 = m.dims[1], s1 = m.dims[2];
     const int s1n = mlp_n16(s1);
@@ -263,6 +296,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
         stage_handover(st, true);
         SG_TB(15, ti);
         if (tid == 0) {
+          if (SG_MLP_ISSUER_FENCE) fence_proxy_async();
           tc_fence_after();
           uint8_t* sb = region + (size_t)st * stage_bytes;
           uint8_t* whi = sb + 2 * MLP_ROWS * 128;
@@ -305,79 +339,129 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           dhi[j] = 2u * MLP_ROWS * 128u + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
         }
       }
-      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      // Fast path (s0 % 4 == 0, W1 at least 8-byte aligned): every 16-byte chunk is wholly inside or outside a row, so
-      // the loads are unconditional (clamped address, result masked in step()) and issue back to back; a branch between
-      // two loads, or a use of a loaded value, would serialise them on the memory latency.
-      auto fetch = [&](int c, float4 (&v)[NI], int j0, int j1) {                 // items j0 <= j < j1 of chunk c
-        const int k = c * MLP_KC + ch * 4;
-        if (FAST) {
-          const int kk = min(k, s0 - 4);
+      if (RING) {
+        constexpr int D = MLP_RING_DEPTH;
+        constexpr uint32_t SLOT = (MLP_THREADS - 32) * 16;               // one item of every stager
+        const uint32_t raw_a = smem_u32(raw) + (uint32_t)tw * 16u;
+        // request chunk c into ring slot c % D (always one commit group per call, so the group count stays uniform)
+        auto request = [&](int c) {
+          if (c < n_chunks) {
+            const int k = c * MLP_KC + ch * 4;
+            const int kk = min(k, s0 - 4);
+            const bool in = k < s0;
 #pragma unroll
-          for (int j = 0; j < NI; ++j) {
-            if (j < j0 || j >= j1) continue;
-            if (MLP_STAGER_ROWS * j + MLP_STAGER_ROWS <= MLP_ROWS) {            // always a row of X: 16-byte aligned, read-only
-              v[j] = __ldg(reinterpret_cast<const float4*>(src[j] + kk));
-            } else {
-#if SG_MLP_W_LDCG   // experiment: explicit ld.global.cg (L2) instead of generic loads for the W1 operand
-              const float2 a0 = __ldcg(reinterpret_cast<const float2*>(src[j] + kk)), a1 = __ldcg(reinterpret_cast<const float2*>(src[j] + kk + 2));
-#else
-              const float2 a0 = *reinterpret_cast<const float2*>(src[j] + kk), a1 = *reinterpret_cast<const float2*>(src[j] + kk + 2);
-#endif
-              v[j] = make_float4(a0.x, a0.y, a1.x, a1.y);
+            for (int j = 0; j < NI; ++j) {
+              const uint32_t dst = raw_a + (uint32_t)((c % D) * NI + j) * SLOT;
+              const uint32_t ok = (in && (flags >> (2 * j) & 1)) ? 1u : 0u;  // rows / columns out of range arrive as zeros
+              if (MLP_STAGER_ROWS * j + MLP_STAGER_ROWS <= MLP_ROWS) {      // always a row of X: 16-byte aligned
+                cp_async16(dst, src[j] + kk, 16u * ok);
+              } else {                                                      // W1 rows are only 8-byte aligned
+                cp_async8(dst, src[j] + kk, 8u * ok);
+                cp_async8(dst + 8u, src[j] + kk + 2, 8u * ok);
+              }
             }
           }
-          return;
-        }
-        const int valid = s0 - k;
+          cp_async_commit();
+        };
 #pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          if (j < j0 || j >= j1) continue;
-          v[j] = (flags >> (2 * j) & 1) ? load4(src[j] + k, valid, is_x(j) ? x16 : w16, is_x(j) ? x16 : w8, false) : zero4;
-        }
-      };
-      // Prefetch depth: ONE chunk of loads in flight per thread.  With two (32 registers of prefetched values) the compiler
-      // spills the values it has just loaded - the spill store waits for the load, and the "prefetch" runs at one memory
-      // latency per chunk (ncu source view: 7 % of the kernel's stall samples on STL right behind the loads).  Keeping only
-      // the first ND items (gathered rows of X: HBM latency) two chunks ahead still spills one float4 per deep item at the
-      // 128-register cap of a 512-thread CTA (checked in the SASS for ND = 1, 2), so ND = 0.
-      constexpr int ND = SG_MLP_FWD_DEEP_ITEMS;
-      // one pipeline step: registers of chunk c -> stage c & 1, hand the stage to warp 0, refill the registers
-      auto step = [&](int c, float4 (&vd)[NI], float4 (&vs)[NI]) {
-        const int st = c & 1;
-        uint8_t* sb = region + (size_t)st * stage_bytes;
-        SG_TA(tt);
-        if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }   // MMAs of chunk c - 2 retired
-        SG_TBT(9, tt, 32);
-        const bool in = c * MLP_KC + ch * 4 < s0;
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          if (!(flags >> (2 * j) & 2)) continue;
-          float4 x = j < ND ? vd[j] : vs[j];
-          if (FAST && !(in && (flags >> (2 * j) & 1))) x = zero4;                // out-of-range rows / columns read as zero
-          float4 hi, lo;
-          split4(x, hi, lo);
-          *reinterpret_cast<float4*>(sb + dhi[j]) = hi;
-          *reinterpret_cast<float4*>(sb + dhi[j] + lo_delta(j)) = lo;
-        }
-        SG_TBT(10, tt, 32);
-        fence_proxy_async();                      // BEFORE the next loads are issued: the fence would wait for them too
-        SG_TBT(11, tt, 32);
-        stage_handover(st, false);
-        SG_TBT(12, tt, 32);
-        if (c + 2 < n_chunks) fetch(c + 2, vd, 0, ND);
-        if (c + 1 < n_chunks) fetch(c + 1, vs, ND, NI);
-        SG_TBT(14, tt, 32);
-        ++uses[st];
-      };
-      float4 a[NI], b[NI], w[NI];
-      fetch(0, a, 0, ND);
-      fetch(0, w, ND, NI);
-      if (n_chunks > 1) fetch(1, b, 0, ND);
+        for (int c = 0; c < D; ++c) request(c);
 #pragma unroll 1
-      for (int c = 0; c < n_chunks; c += 2) {
-        step(c, a, w);
-        if (c + 1 < n_chunks) step(c + 1, b, w);
+        for (int c = 0; c < n_chunks; ++c) {
+          const int st = c & 1;
+          uint8_t* sb = region + (size_t)st * stage_bytes;
+          if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }   // MMAs of chunk c - 2 retired
+          cp_async_wait<D - 1>();                                                // chunk c has landed in this thread's slots
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            if (!(flags >> (2 * j) & 2)) continue;
+            const float4 x = lds128(raw_a + (uint32_t)((c % D) * NI + j) * SLOT);
+            float4 hi, lo;
+            split4(x, hi, lo);
+            *reinterpret_cast<float4*>(sb + dhi[j]) = hi;
+            *reinterpret_cast<float4*>(sb + dhi[j] + lo_delta(j)) = lo;
+          }
+          if (!SG_MLP_ISSUER_FENCE) fence_proxy_async();
+          stage_handover(st, false);
+          request(c + D);                                                        // refill the slot just read
+          ++uses[st];
+        }
+        cp_async_wait<0>();
+      } else {
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // Fast path (s0 % 4 == 0, W1 at least 8-byte aligned): every 16-byte chunk is wholly inside or outside a row, so
+        // the loads are unconditional (clamped address, result masked in step()) and issue back to back; a branch between
+        // two loads, or a use of a loaded value, would serialise them on the memory latency.
+        auto fetch = [&](int c, float4 (&v)[NI], int j0, int j1) {                 // items j0 <= j < j1 of chunk c
+          const int k = c * MLP_KC + ch * 4;
+          if (FAST) {
+            const int kk = min(k, s0 - 4);
+  #pragma unroll
+            for (int j = 0; j < NI; ++j) {
+              if (j < j0 || j >= j1) continue;
+              if (MLP_STAGER_ROWS * j + MLP_STAGER_ROWS <= MLP_ROWS) {            // always a row of X: 16-byte aligned, read-only
+                v[j] = __ldg(reinterpret_cast<const float4*>(src[j] + kk));
+              } else {
+  #if SG_MLP_W_LDCG   // experiment: explicit ld.global.cg (L2) instead of generic loads for the W1 operand
+                const float2 a0 = __ldcg(reinterpret_cast<const float2*>(src[j] + kk)), a1 = __ldcg(reinterpret_cast<const float2*>(src[j] + kk + 2));
+  #else
+                const float2 a0 = *reinterpret_cast<const float2*>(src[j] + kk), a1 = *reinterpret_cast<const float2*>(src[j] + kk + 2);
+  #endif
+                v[j] = make_float4(a0.x, a0.y, a1.x, a1.y);
+              }
+            }
+            return;
+          }
+          const int valid = s0 - k;
+  #pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            if (j < j0 || j >= j1) continue;
+            v[j] = (flags >> (2 * j) & 1) ? load4(src[j] + k, valid, is_x(j) ? x16 : w16, is_x(j) ? x16 : w8, false) : zero4;
+          }
+        };
+        // Prefetch depth: ONE chunk of loads in flight per thread.  With two (32 registers of prefetched values) the compiler
+        // spills the values it has just loaded - the spill store waits for the load, and the "prefetch" runs at one memory
+        // latency per chunk (ncu source view: 7 % of the kernel's stall samples on STL right behind the loads).  Keeping only
+        // the first ND items (gathered rows of X: HBM latency) two chunks ahead still spills one float4 per deep item at the
+        // 128-register cap of a 512-thread CTA (checked in the SASS for ND = 1, 2), so ND = 0.
+        constexpr int ND = SG_MLP_FWD_DEEP_ITEMS;
+        // one pipeline step: registers of chunk c -> stage c & 1, hand the stage to warp 0, refill the registers
+        auto step = [&](int c, float4 (&vd)[NI], float4 (&vs)[NI]) {
+          const int st = c & 1;
+          uint8_t* sb = region + (size_t)st * stage_bytes;
+          SG_TA(tt);
+          if (uses[st] > 0) { mbar_wait(&ms.bar[st], par[st]); par[st] ^= 1; }   // MMAs of chunk c - 2 retired
+          SG_TBT(9, tt, 32);
+          const bool in = c * MLP_KC + ch * 4 < s0;
+  #pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            if (!(flags >> (2 * j) & 2)) continue;
+            float4 x = j < ND ? vd[j] : vs[j];
+            if (FAST && !(in && (flags >> (2 * j) & 1))) x = zero4;                // out-of-range rows / columns read as zero
+            float4 hi, lo;
+            split4(x, hi, lo);
+            *reinterpret_cast<float4*>(sb + dhi[j]) = hi;
+            *reinterpret_cast<float4*>(sb + dhi[j] + lo_delta(j)) = lo;
+          }
+          SG_TBT(10, tt, 32);
+          if (!SG_MLP_ISSUER_FENCE) fence_proxy_async();   // BEFORE the next loads are issued: the fence would wait for them too
+          SG_TBT(11, tt, 32);
+          stage_handover(st, false);
+          SG_TBT(12, tt, 32);
+          if (c + 2 < n_chunks) fetch(c + 2, vd, 0, ND);
+          if (c + 1 < n_chunks) fetch(c + 1, vs, ND, NI);
+          SG_TBT(14, tt, 32);
+          ++uses[st];
+        };
+        float4 a[NI], b[NI], w[NI];
+        fetch(0, a, 0, ND);
+        fetch(0, w, ND, NI);
+        if (n_chunks > 1) fetch(1, b, 0, ND);
+  #pragma unroll 1
+        for (int c = 0; c < n_chunks; c += 2) {
+          step(c, a, w);
+          if (c + 1 < n_chunks) step(c + 1, b, w);
+        }
+    
       }
     }
     for (int st = 0; st < 2; ++st)
@@ -477,6 +561,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           if (used >> st & 1) { mbar_wait(&ms.bar[st], par >> st & 1); par ^= 1u << st; }   // (retired: the stagers waited for it)
           stage_handover(st, true);
           if (tid == 0) {
+            if (SG_MLP_ISSUER_FENCE) fence_proxy_async();
             tc_fence_after();
             const int g = npp == 2 ? u >> 1 : u, p = npp == 2 ? u & 1 : 0;       // npp <= 2: tiles_per_pass == 4
             const uint64_t dbh = desc_mn_sw128_32b(smem_u32(bhi) + (uint32_t)g * 4096u, 1024u, 512u);
@@ -528,7 +613,7 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
           *reinterpret_cast<float4*>(sb + soff) = hi;
           *reinterpret_cast<float4*>(sb + 8192 + soff) = lo;
           SG_TBT(22, tb, 32);
-          fence_proxy_async();                                   // before the next load is issued (the fence would wait for it)
+          if (!SG_MLP_ISSUER_FENCE) fence_proxy_async();         // before the next load is issued (the fence would wait for it)
           SG_TBT(23, tb, 32);
           stage_handover(st, false);
           SG_TBT(24, tb, 32);
@@ -620,7 +705,10 @@ struct FamilyGrad<SGMCMC_FAMILY_MLP> {
       const int o = tid + t * MLP_THREADS;
       ypre[t] = o < nb * wL ? __ldg(Y + (size_t)ms.idx[o / wL] * wL + o % wL) : 0.f;
     }
-    { SG_T0(); layer1_forward(m, ms, region, th, nb, R, act(1), astr(1)); SG_T1(1); }
+    // shared memory that is idle during the forward GEMM: the backward X stages and every fp32 activation / dZ buffer
+    // (act(1) is only written by the GEMM's epilogue, after the ring has drained)
+    const size_t raw_bytes = plan.total_bytes - 1024 - plan.region_bytes;
+    { SG_T0(); layer1_forward(m, ms, region, th, nb, R, act(1), astr(1), xs, raw_bytes); SG_T1(1); }
     SG_T0();
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
