@@ -87,6 +87,7 @@ struct Smem {
   float *theta, *aux1, *aux2, *grad, *center, *fb, *S, *part;
   float* mu;          // [DS] column means of the centred row table (gaussian_mean), zeros otherwise
   float* recv;        // [2][cs][DS + 4]: folded partial sums (+ log-likelihood value term) PUSHED here by every CTA of the cluster
+  unsigned long long* xbar;   // [2] mbarriers, one per recv half: complete when all cs partial-sum vectors have arrived
   float* alpha;       // [MAXL]
   float* red;         // [32] block-reduction scratch
   uint32_t* keys;     // [2 * (4 + 2*MAXL)] step keys
@@ -104,6 +105,7 @@ __device__ __forceinline__ Smem carve(float* base, int PP, int DS, int W, int cs
   s.part = base;             base += W * DS;
   s.mu = base;               base += DS;
   s.recv = base;             base += cs > 1 ? 2 * cs * (DS + 4) : 0;
+  s.xbar = reinterpret_cast<unsigned long long*>(base);   base += cs > 1 ? 4 : 0;     // 16-byte aligned: every count above is a multiple of 4
   s.alpha = base;            base += MAXL;
   s.red = base;              base += 32;
   s.keys = reinterpret_cast<uint32_t*>(base);
@@ -115,7 +117,7 @@ constexpr int SMEM_KEY_WORDS = 2 * (4 + 2 * MAXL);
 constexpr int KEY_PLAN = 4 + 2 * MAXL, KEY_NEXT = KEY_PLAN + 4;
 static_assert(KEY_NEXT + 8 <= SMEM_KEY_WORDS, "key slots");
 __host__ __device__ inline size_t vec_smem_bytes(int PP, int DS, int W, int cs) {
-  return sizeof(float) * (size_t)(6 * PP + (DS + 4) + W * DS + DS + (cs > 1 ? 2 * cs * (DS + 4) : 0) + MAXL + 32) +
+  return sizeof(float) * (size_t)(6 * PP + (DS + 4) + W * DS + DS + (cs > 1 ? 2 * cs * (DS + 4) + 4 : 0) + MAXL + 32) +
          sizeof(uint32_t) * SMEM_KEY_WORDS;
 }
 
@@ -123,6 +125,39 @@ __host__ __device__ inline size_t vec_smem_bytes(int PP, int DS, int W, int cs) 
 // cluster geometry of this CTA (1 / 0 for a launch without a cluster attribute)
 __device__ __forceinline__ unsigned cluster_size() { unsigned r; asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+
+// Cluster exchange without a cluster barrier (SG_VEC_ASYNC_EXCHANGE, default): every CTA pushes its folded partial sums into
+// the peers' recv half with st.async, each store signalling complete_tx on the RECEIVER's mbarrier of that half; a CTA only
+// waits for its own mbarrier (cs vectors expected).  `barrier.cluster.arrive.release` costs a cluster-scope memory barrier
+// per step (ncu on the README chain: 13 % of all stall samples on its ERRBAR, 4 % more in the wait); these stores need none.
+#ifndef SG_VEC_ASYNC_EXCHANGE
+#define SG_VEC_ASYNC_EXCHANGE 1
+#endif
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, unsigned rank) {   // the same location in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
+               ::"r"(remote_addr), "f"(v), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void xbar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(bar)));
+}
+__device__ __forceinline__ void xbar_expect(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xbar_wait(unsigned long long* bar, uint32_t parity) {   // acquires the peers' st.async data
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (!ok) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_addr_u32(bar)), "r"(parity) : "memory");
+    if (!ok && clock64() - t0 > 8000000000LL) __trap();     // a protocol bug traps instead of hanging the GPU
+  }
+}
 
 __device__ __forceinline__ float sigmoid_f(float z) {
   // stable logistic; expf (not __expf): per-row relative error must stay ~1e-7
@@ -401,8 +436,25 @@ __device__ __forceinline__ void fold_parts(const Smem& s, int DS, int& buf, bool
       s.S[d] = t;
     }
   } else {
+    float* slot = s.recv + ((size_t)(buf & 1) * cs + cluster_rank()) * stride;
+#if SG_VEC_ASYNC_EXCHANGE
+    // bit 0 of buf: recv half; bits 1, 2: phase parity of xbar[0], xbar[1]
+    unsigned long long* bar = s.xbar + (buf & 1);
+    if (threadIdx.x == 0) xbar_expect(bar, cs * (unsigned)n * 4u);
+    const uint32_t bar_a = smem_addr_u32(bar);
+    for (int d = threadIdx.x; d < n; d += blockDim.x) {
+      float t = 0.f;
+      if (d < DS) { for (int w = 0; w < W; ++w) t += s.part[w * DS + d]; }
+      else        { for (int w = 0; w < W; ++w) t += s.red[w]; }
+      const uint32_t dst = smem_addr_u32(slot + d);
+      for (unsigned r = 0; r < cs; ++r) st_async_f32(map_to_rank(dst, r), t, map_to_rank(bar_a, r));
+    }
+    SG_TB(5, t_f);
+    xbar_wait(bar, (buf >> (1 + (buf & 1))) & 1);
+    buf ^= 2 << (buf & 1);                                  // this half's next phase
+    SG_TB(6, t_f);
+#else
     cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
-    float* slot = s.recv + ((size_t)buf * cs + cluster_rank()) * stride;
     for (int d = threadIdx.x; d < n; d += blockDim.x) {
       float t = 0.f;
       if (d < DS) { for (int w = 0; w < W; ++w) t += s.part[w * DS + d]; }
@@ -412,7 +464,8 @@ __device__ __forceinline__ void fold_parts(const Smem& s, int DS, int& buf, bool
     SG_TB(5, t_f);
     cl.sync();
     SG_TB(6, t_f);
-    const float* mine = s.recv + (size_t)buf * cs * stride;
+#endif
+    const float* mine = s.recv + (size_t)(buf & 1) * cs * stride;
     for (int d = threadIdx.x; d < n; d += blockDim.x) {
       float t = 0.f;
       for (unsigned r = 0; r < cs; ++r) t += mine[r * stride + d];
@@ -452,7 +505,7 @@ template <int FAMILY, int CV, int NCH, bool EXT = false>
 struct ChainCtx {
   const VecModel& m;
   Smem s;
-  int buf = 0;              // recv half of the next cluster fold
+  int buf = 0;              // bit 0: recv half of the next cluster fold; bits 1, 2: phase parities of its two mbarriers
   bool plan_cached = false; // keys[KEY_PLAN ..] hold split(k2) of the estimate about to run
   int look_slot = -1;       // >= 0: the next expand_step_keys also splits look_carry into keys[KEY_NEXT + 4 look_slot ..]
   Key look_carry{0u, 0u};
@@ -785,6 +838,13 @@ __global__ void __launch_bounds__(1024 / NCH) vec_sampler_kernel(const VecModel 
   }
   for (int d = threadIdx.x; d < m.DS; d += blockDim.x)
     s.mu[d] = (FAMILY == SGMCMC_FAMILY_GAUSSIAN_MEAN && m.mu) ? m.mu[d] : 0.f;
+  if (SG_VEC_ASYNC_EXCHANGE && cs > 1) {
+    if (threadIdx.x == 0) {
+      xbar_init(s.xbar); xbar_init(s.xbar + 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cooperative_groups::this_cluster().sync();          // once per launch: every CTA's barriers exist before the first push
+  }
   __syncthreads();
 
   ChainCtx<FAMILY, CV, NCH, EXT> ctx(m, s);
