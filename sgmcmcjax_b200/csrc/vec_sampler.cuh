@@ -149,11 +149,14 @@ __device__ __forceinline__ void xbar_init(unsigned long long* bar) {
 __device__ __forceinline__ void xbar_expect(unsigned long long* bar, uint32_t bytes) {
   asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void xbar_wait(unsigned long long* bar, uint32_t parity) {   // acquires the peers' st.async data
+// The st.async data lands in THIS CTA's shared memory and its complete_tx is what completes the phase, so the default
+// (.acquire.cta) wait orders it - the pattern of every TMA-multicast consumer.  The .acquire.cluster form compiles to the
+// same wait followed by CCTL.IVALL, an invalidation of the whole L1 on every step (9 % of the stall samples of the README chain).
+__device__ __forceinline__ void xbar_wait(unsigned long long* bar, uint32_t parity) {
   uint32_t ok = 0;
   const long long t0 = clock64();
   while (!ok) {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ok) : "r"(smem_addr_u32(bar)), "r"(parity) : "memory");
     if (!ok && clock64() - t0 > 8000000000LL) __trap();     // a protocol bug traps instead of hanging the GPU
   }
