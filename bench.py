@@ -538,16 +538,33 @@ def gpu_arm(args):
             dist.all_reduce(tk, op=dist.ReduceOp.MAX)
         ms = float(tk.item())
         pairs = float(n) * n
-        flops = 6.0 * DIM * pairs                                     # 3 Gram contractions, 2 flops per MAC
+        # Flop accounting (corrected at the end of round 2).  Algorithmic: three full Gram matrices X X^T, G G^T, G X^T
+        # (x_i.g_j is the transpose of g_i.x_j): 6 D N^2 flops for all N^2 ordered pairs.  What the kernel ISSUES: it works on
+        # the upper triangle of 128 x 128 tiles, where a tile needs FOUR products - x.x, g.g and both cross products
+        # g_I.x_J and x_I.g_J (the second would be tile (J, I) of G X^T) - each as 3 tf32 MMAs: per tile and 8-wide K slice
+        # six 128 x 256 x 8 MMAs (csrc/ksd_tc.cuh PROD table), K padded from D to a multiple of 8 = 12 D' N^2 flops.
+        # Earlier rounds put 1.5 x 6 D N^2 = 9 D N^2 here (three products per tile): 0.75 of what is issued.
+        flops = 6.0 * DIM * pairs                                     # algorithmic, all N^2 ordered pairs
+        T = (n + 127) // 128
+        tiles = T * (T + 1) // 2
+        k_slices = ((DIM + 7) // 8)
+        mma_flops = float(tiles) * 6 * k_slices * (2.0 * 128 * 256 * 8)
         tf32_peak, tf32_src = tf32_peak_tflops(bf16_peak)
-        issued = 1.5 * flops / (ms * 1e-3) / 1e12
+        issued = mma_flops / (ms * 1e-3) / 1e12                      # incl. the K padding (D -> multiple of 8) and whole diagonal tiles
+        tf32_alg = 12.0 * DIM * pairs / (ms * 1e-3) / 1e12            # 4 products x 3 tf32 splits x 2 D flops on N^2 / 2 pairs
         ksd_line = {"metric": "imq_KSD pairs/sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n": n, "d": DIM,
                     "ms": ms, "ksd": float(val), "equiv_tflops": flops / (ms * 1e-3) / 1e12,
                     "method": "tcgen05 3xTF32 Gram tiles (upper triangle, dealt round-robin to ranks)",
-                    "roofline": {"bound": "tensor", "achieved": issued, "peak": world * tf32_peak, "unit": "TFLOP/s",
-                                 "frac": issued / (world * tf32_peak),
-                                 "note": "achieved = ISSUED tf32 flops over all ranks (3 split products per dot, half the "
-                                         "tiles by symmetry: 1.5 x the algorithmic 6*D*N^2); peak = n_gpus x " + tf32_src}}
+                    "roofline": {"bound": "tensor", "achieved": tf32_alg, "peak": world * tf32_peak, "unit": "TFLOP/s",
+                                 "frac": tf32_alg / (world * tf32_peak), "issued_tflops": issued,
+                                 "mma_instructions": int(tiles) * 6 * k_slices, "tiles": int(tiles),
+                                 "note": "achieved = 12 x D x N^2 tf32 flops / time: the upper triangle needs four products per "
+                                         "pair (x.x, g.g, g_i.x_j, x_i.g_j), each as 3 tf32 split products; issued_tflops "
+                                         "counts the tcgen05.mma instructions themselves (T(T+1)/2 tiles x ceil(D/8) K slices x "
+                                         "6 MMAs of 128x256x8: K padding and whole diagonal tiles included).  The whole call is "
+                                         "timed (centring + hi/lo split + tile kernel + all-reduce).  Rounds 1-2 reported "
+                                         "9 x D x N^2 here (three products per tile instead of four): 0.75 of this figure.  "
+                                         "peak = n_gpus x " + tf32_src}}
 
     checks = None
     if world > 1:
