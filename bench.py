@@ -458,6 +458,64 @@ def gpu_arm(args):
     theta_row = theta_true.cpu().numpy().astype(np.float32)
     theta0_host = np.tile(theta_row, (C, 1)).astype(np.float32)
 
+    # ---- KSD (configs[4]): 50k x 100 points, row blocks over ranks, one all-reduce of a double.  Timed FIRST: the call is
+    # tensor-bound and loses 5-20 % when it runs right after the sampler legs (same clocks reported, board warm: 4.99 ms
+    # alone, 5.2-5.9 ms after them, `tools/ksd_in_bench_probe.py`), and its roofline denominator is a burst measurement too.
+    def run_ksd():
+        n = args.ksd_n
+        pts = theta_true[None, :] + 0.02 * random.normal(random.PRNGKey(7), (n, DIM))
+        grads = -50.0 * (pts - theta_true[None, :]) + random.normal(random.PRNGKey(8), (n, DIM))
+        pts, grads = pts.contiguous(), grads.contiguous()
+        for _ in range(2):
+            ksd.imq_KSD(pts, grads, distributed=world > 1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        a.record()
+        for _ in range(reps):
+            val = ksd.imq_KSD(pts, grads, distributed=world > 1)
+        b.record()
+        torch.cuda.synchronize()
+        tk = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        ms = float(tk.item())
+        pairs = float(n) * n
+        # Flop accounting (corrected at the end of round 2).  Algorithmic: three full Gram matrices X X^T, G G^T, G X^T
+        # (x_i.g_j is the transpose of g_i.x_j): 6 D N^2 flops for all N^2 ordered pairs.  What the kernel ISSUES: it works on
+        # the upper triangle of 128 x 128 tiles, where a tile needs FOUR products - x.x, g.g and both cross products
+        # g_I.x_J and x_I.g_J (the second would be tile (J, I) of G X^T) - each as 3 tf32 MMAs: per tile and 8-wide K slice
+        # six 128 x 256 x 8 MMAs (csrc/ksd_tc.cuh PROD table), K padded from D to a multiple of 8 = 12 D' N^2 flops.
+        # Earlier rounds put 1.5 x 6 D N^2 = 9 D N^2 here (three products per tile): 0.75 of what is issued.
+        flops = 6.0 * DIM * pairs                                     # algorithmic, all N^2 ordered pairs
+        T = (n + 127) // 128
+        tiles = T * (T + 1) // 2
+        k_slices = ((DIM + 7) // 8)
+        mma_flops = float(tiles) * 6 * k_slices * (2.0 * 128 * 256 * 8)
+        tf32_peak, tf32_src = tf32_peak_tflops(bf16_peak)
+        issued = mma_flops / (ms * 1e-3) / 1e12                      # incl. the K padding (D -> multiple of 8) and whole diagonal tiles
+        tf32_alg = 12.0 * DIM * pairs / (ms * 1e-3) / 1e12            # 4 products x 3 tf32 splits x 2 D flops on N^2 / 2 pairs
+        ksd_line = {"metric": "imq_KSD pairs/sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n": n, "d": DIM,
+                    "ms": ms, "ksd": float(val), "equiv_tflops": flops / (ms * 1e-3) / 1e12,
+                    "method": "tcgen05 3xTF32 Gram tiles (upper triangle, dealt round-robin to ranks)",
+                    "roofline": {"bound": "tensor", "achieved": tf32_alg, "peak": world * tf32_peak, "unit": "TFLOP/s",
+                                 "frac": tf32_alg / (world * tf32_peak), "issued_tflops": issued,
+                                 "mma_instructions": int(tiles) * 6 * k_slices, "tiles": int(tiles),
+                                 "note": "achieved = 12 x D x N^2 tf32 flops / time: the upper triangle needs four products per "
+                                         "pair (x.x, g.g, g_i.x_j, x_i.g_j), each as 3 tf32 split products; issued_tflops "
+                                         "counts the tcgen05.mma instructions themselves (T(T+1)/2 tiles x ceil(D/8) K slices x "
+                                         "6 MMAs of 128x256x8: K padding and whole diagonal tiles included).  The whole call is "
+                                         "timed (centring + hi/lo split + tile kernel + all-reduce).  Rounds 1-2 reported "
+                                         "9 x D x N^2 here (three products per tile instead of four): 0.75 of this figure.  "
+                                         "peak = n_gpus x " + tf32_src}}
+        return ksd_line, (pts, grads)
+
+    ksd_line, ksd_inputs = None, None
+    if not args.no_ksd and not args.ksd_last:
+        ksd_line, ksd_inputs = run_ksd()
+
     # ---- device-resident timing: state lives in HBM, one launch per bench step
     clocks = ClockSampler(local) if rank == 0 else None      # already streaming when the timed region starts
     total_ms_max, per_launch_ms, launches, (t_wall0, t_wall1) = _timed_launches(
@@ -513,58 +571,8 @@ def gpu_arm(args):
            "note": f"sampler(key, {Ke}, params) with numpy in/out incl. init_fn; bytes per rank, scaled to one bench step "
                    f"({K} chain-steps per chain)"}
 
-    # ---- KSD (configs[4]): 50k x 100 points, row blocks over ranks, one all-reduce of a double
-    ksd_line, ksd_inputs = None, None
-    if not args.no_ksd:
-        n = args.ksd_n
-        pts = theta_true[None, :] + 0.02 * random.normal(random.PRNGKey(7), (n, DIM))
-        grads = -50.0 * (pts - theta_true[None, :]) + random.normal(random.PRNGKey(8), (n, DIM))
-        pts, grads = pts.contiguous(), grads.contiguous()
-        ksd_inputs = (pts, grads)
-        for _ in range(2):
-            ksd.imq_KSD(pts, grads, distributed=world > 1)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
-        a.record()
-        for _ in range(reps):
-            val = ksd.imq_KSD(pts, grads, distributed=world > 1)
-        b.record()
-        torch.cuda.synchronize()
-        tk = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
-        ms = float(tk.item())
-        pairs = float(n) * n
-        # Flop accounting (corrected at the end of round 2).  Algorithmic: three full Gram matrices X X^T, G G^T, G X^T
-        # (x_i.g_j is the transpose of g_i.x_j): 6 D N^2 flops for all N^2 ordered pairs.  What the kernel ISSUES: it works on
-        # the upper triangle of 128 x 128 tiles, where a tile needs FOUR products - x.x, g.g and both cross products
-        # g_I.x_J and x_I.g_J (the second would be tile (J, I) of G X^T) - each as 3 tf32 MMAs: per tile and 8-wide K slice
-        # six 128 x 256 x 8 MMAs (csrc/ksd_tc.cuh PROD table), K padded from D to a multiple of 8 = 12 D' N^2 flops.
-        # Earlier rounds put 1.5 x 6 D N^2 = 9 D N^2 here (three products per tile): 0.75 of what is issued.
-        flops = 6.0 * DIM * pairs                                     # algorithmic, all N^2 ordered pairs
-        T = (n + 127) // 128
-        tiles = T * (T + 1) // 2
-        k_slices = ((DIM + 7) // 8)
-        mma_flops = float(tiles) * 6 * k_slices * (2.0 * 128 * 256 * 8)
-        tf32_peak, tf32_src = tf32_peak_tflops(bf16_peak)
-        issued = mma_flops / (ms * 1e-3) / 1e12                      # incl. the K padding (D -> multiple of 8) and whole diagonal tiles
-        tf32_alg = 12.0 * DIM * pairs / (ms * 1e-3) / 1e12            # 4 products x 3 tf32 splits x 2 D flops on N^2 / 2 pairs
-        ksd_line = {"metric": "imq_KSD pairs/sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n": n, "d": DIM,
-                    "ms": ms, "ksd": float(val), "equiv_tflops": flops / (ms * 1e-3) / 1e12,
-                    "method": "tcgen05 3xTF32 Gram tiles (upper triangle, dealt round-robin to ranks)",
-                    "roofline": {"bound": "tensor", "achieved": tf32_alg, "peak": world * tf32_peak, "unit": "TFLOP/s",
-                                 "frac": tf32_alg / (world * tf32_peak), "issued_tflops": issued,
-                                 "mma_instructions": int(tiles) * 6 * k_slices, "tiles": int(tiles),
-                                 "note": "achieved = 12 x D x N^2 tf32 flops / time: the upper triangle needs four products per "
-                                         "pair (x.x, g.g, g_i.x_j, x_i.g_j), each as 3 tf32 split products; issued_tflops "
-                                         "counts the tcgen05.mma instructions themselves (T(T+1)/2 tiles x ceil(D/8) K slices x "
-                                         "6 MMAs of 128x256x8: K padding and whole diagonal tiles included).  The whole call is "
-                                         "timed (centring + hi/lo split + tile kernel + all-reduce).  Rounds 1-2 reported "
-                                         "9 x D x N^2 here (three products per tile instead of four): 0.75 of this figure.  "
-                                         "peak = n_gpus x " + tf32_src}}
+    if not args.no_ksd and args.ksd_last:
+        ksd_line, ksd_inputs = run_ksd()
 
     checks = None
     if world > 1:
@@ -611,6 +619,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of host work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ksd", action="store_true")
+    ap.add_argument("--ksd-last", action="store_true", help="time the KSD call after the sampler legs (the order of rounds 1-2)")
     ap.add_argument("--no-extras", action="store_true", help="skip the C1/C3/C4 and C2-variant lines (N=1 only)")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch from the committed ncu --set full capture (profiles/)")
