@@ -261,7 +261,12 @@ def test_multichain_equals_single_chains(cuda, case):
 
 
 @pytest.mark.parametrize("sizes,n,batch", [((784, 100, 10), 600, 100), ((50, 128, 3), 200, 130), ((7, 5), 64, 9),
-                                           ((33, 17, 11, 4), 100, 100)])
+                                           ((33, 17, 11, 4), 100, 100),
+                                           # aligned input width (the cp.async operand ring of the forward GEMM) with: five
+                                           # stager items per thread (hidden width 128); a narrow hidden layer and a ragged
+                                           # batch; a full 128-row sub-batch with 112 hidden units; two sub-batches
+                                           ((64, 128, 5), 300, 100), ((64, 16, 4), 200, 37), ((128, 112, 10), 400, 128),
+                                           ((256, 100, 10), 500, 200)])
 def test_mlp_shapes_fullbatch_grad(cuda, sizes, n, batch):
     """Layer geometries: the BASELINE config-3 net 784-100-10 (batch 100), widths up to 128, one layer
     (multinomial regression), three layers; full-batch K2 and a minibatch step."""
