@@ -155,8 +155,15 @@ __device__ __forceinline__ uint32_t randint_combine(const RandintPlan& p, uint32
 }
 
 // Stream block b -> indices for minibatch positions b and b+h (second one valid iff b+h < batch).
+#ifndef SG_RANDINT_ONE_BLOCK
+#define SG_RANDINT_ONE_BLOCK 1
+#endif
 __device__ __forceinline__ void randint_block(const RandintPlan& p, uint32_t b, uint32_t& i0, uint32_t& i1) {
   uint32_t l0, l1, h0 = 0u, h1 = 0u;
+#if !SG_RANDINT_ONE_BLOCK
+  stream_block(p.k_lo, b, p.batch, l0, l1);
+  if (p.mult != 0u) stream_block(p.k_hi, b, p.batch, h0, h1);   // mult == 0 <=> span > 65536: hi unused
+#else
   if (p.mult != 0u) {                     // span <= 65536: jax combines a hi and a lo draw
     // both threefry blocks in ONE basic block: two independent ~350-cycle dependency chains that the scheduler interleaves
     // (with the hi block alone behind the branch they ran one after the other: the README chain's index draw)
@@ -165,6 +172,7 @@ __device__ __forceinline__ void randint_block(const RandintPlan& p, uint32_t b, 
   } else {                                // mult == 0 <=> span > 65536: hi unused
     stream_block(p.k_lo, b, p.batch, l0, l1);
   }
+#endif
   i0 = randint_combine(p, h0, l0);
   i1 = randint_combine(p, h1, l1);
 }
